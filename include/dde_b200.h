@@ -1,0 +1,246 @@
+/* dde_b200 -- C-ABI of the B200-native batched integrator.
+ *
+ * This is the drop-in boundary for the hot path of mrc-ide/dde: everything
+ * below is plain C (pointers, sizes, PODs; no torch / CUDA types) and is what
+ * the reference's R<->C glue (src/r_dopri.c, src/r_difeq.c) would bind in
+ * place of its serial calls.  Every entry point names the reference
+ * interface it replaces.  Per-trajectory semantics equal one call of the
+ * reference function on that trajectory's inputs.
+ *
+ * Array layouts are the reference's (column-major R arrays):
+ *   y0      [n      x n_traj]   n fastest            (src/r_difeq.c:9-17)
+ *   parms   [n_parms x n_traj]  or one shared vector (parms_stride == 0;
+ *                               src/r_difeq.c:40 passes one `data` pointer)
+ *   y_out   [n      x nt x n_traj]                   (src/r_difeq.c:77,
+ *   out     [n_out  x nt x n_traj]                    src/r_dopri.c:168-176)
+ *   nt = n_times (return_initial) or n_times - 1     (src/r_dopri.c:124)
+ *
+ * Batch-level failures (bad arguments, CUDA errors, unknown model) return a
+ * non-zero int and set dde_last_error().  Per-trajectory solver failures do
+ * NOT abort the batch: they are reported in code[] with the reference's
+ * return_code values (src/dopri.h:24-35) -- the reference raises Rf_error at
+ * that point (src/r_dopri.c:264-297); dde_dopri_strerror() reproduces those
+ * messages.
+ */
+#ifndef DDE_B200_H
+#define DDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums ------------------------------------------------------------ */
+
+/* dopri_method, src/dopri.h:37-40 */
+#define DDE_DOPRI_5 0
+#define DDE_DOPRI_853 1
+
+/* return_code, src/dopri.h:24-35 (same values) */
+#define DDE_ERR_ZERO_TIME_DIFFERENCE (-1)
+#define DDE_ERR_INCONSISTENT_TIME (-2)
+#define DDE_ERR_TOO_MANY_STEPS (-3)
+#define DDE_ERR_STEP_SIZE_TOO_SMALL (-4)
+#define DDE_ERR_STEP_SIZE_VANISHED (-5)
+#define DDE_ERR_YLAG_FAIL (-6)
+#define DDE_ERR_STIFF (-7)
+#define DDE_NOT_SET 0
+#define DDE_OK_COMPLETE 1
+#define DDE_OK_INTERRUPTED 2
+/* Paths on which the reference calls Rf_error directly, long-jumping out of
+ * the solver; a batch needs a per-trajectory code instead. */
+#define DDE_ERR_NONFINITE_DERIV (-8) /* src/dopri.c:331-336 */
+#define DDE_ERR_DIFEQ_HISTORY (-9)   /* src/difeq.c:267-270 */
+
+/* index into stats[4 x n_traj]; order of the `statistics` attribute,
+ * src/r_dopri.c:415-422 */
+#define DDE_STAT_N_EVAL 0
+#define DDE_STAT_N_STEP 1
+#define DDE_STAT_N_ACCEPT 2
+#define DDE_STAT_N_REJECT 3
+
+/* ---- controls --------------------------------------------------------- */
+
+/* The control fields of dopri_data (src/dopri.h:133-146,158) plus the
+ * allocation-time arguments of dopri_data_alloc (src/dopri.h:163-168). */
+typedef struct dde_dopri_control {
+  double atol;              /* default 1e-6, src/dopri.c:64 */
+  double rtol;              /* default 1e-6, src/dopri.c:65 */
+  double step_size_min;     /* clamped to >= DBL_EPSILON, src/r_dopri.c:160 */
+  double step_size_max;     /* clamped to <= DBL_MAX,     src/r_dopri.c:161 */
+  double step_size_initial; /* 0 = choose (dopri_h_init), src/dopri.c:527-530 */
+  uint64_t step_max_n;      /* default 100000, src/dopri.c:83 */
+  uint64_t stiff_check;     /* 0 = never, src/dopri.c:213-215 */
+  uint64_t n_history;       /* ring capacity in accepted steps, src/dopri.c:53 */
+  int32_t method;           /* DDE_DOPRI_5 | DDE_DOPRI_853 */
+  int32_t step_size_min_allow; /* src/dopri.c:351-354 */
+  int32_t grow_history;     /* must be 0: no allocation inside kernels */
+  int32_t return_initial;   /* src/dopri.c:320-327 */
+} dde_dopri_control;
+
+/* Fill *ctl with the reference defaults for `method`
+ * (src/dopri.c:64-87, R/dopri.R:293-310). */
+void dde_dopri_control_default(dde_dopri_control *ctl, int32_t method);
+
+/* ---- library / models ------------------------------------------------- */
+
+const char *dde_last_error(void);
+const char *dde_version(void);
+
+/* Compiled models known to the library (the analogue of the reference's
+ * dyn.load'ed model .so + getNativeSymbolInfo, R/common.R:89-98).  A model
+ * is one translation unit holding `deriv`/`output`/`difeq_target` functions
+ * with the reference's model ABI (src/dopri.h:49-53, src/difeq.h:19-21)
+ * compiled as __device__ code together with the kernels. */
+size_t dde_model_count(void);
+const char *dde_model_name(size_t i);
+/* returns 0 and fills the outputs if the model exists; kind bit 0 = dopri
+ * (deriv), bit 1 = difeq (target); n == 0 means "any n" */
+int dde_model_info(const char *model, int32_t *kind, size_t *n,
+                   size_t *n_parms, size_t *n_out);
+
+/* The message r_dopri_error() raises for `code` (src/r_dopri.c:264-297).
+ * `t` is the trajectory's time at failure, `n_history` its ring capacity
+ * (ERR_YLAG_FAIL has two messages, src/r_dopri.c:284-289). */
+int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf,
+                       size_t len);
+
+/* ---- dopri: one-shot batched solve, HOST buffers ----------------------- */
+
+/* Replaces, for every trajectory j in [0, n_traj):
+ *   dopri_data_alloc(model.deriv, n, model.output, n_out, parms_j, method,
+ *                    n_history, false, VERBOSE_QUIET, R_NilValue)
+ *   + control assignment                       (src/r_dopri.c:148-166)
+ *   dopri_integrate(obj, y0_j, times, n_times, tcrit, n_tcrit, is_event=all
+ *                   false, NULL, y_out_j, out_j, return_initial)
+ *                                              (src/dopri.c:291-514)
+ *   + statistics / step_size extraction        (src/r_dopri.c:412-428)
+ *   dopri_data_free(obj)
+ * Copies inputs host->device, integrates all trajectories concurrently on
+ * the current CUDA device, copies results device->host.  Any output pointer
+ * may be NULL (not returned).  y_out/out rows that the reference would not
+ * have written (failed trajectories) are zero, like the zero-initialised R
+ * matrix (src/r_dopri.c:169). */
+int dde_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n,
+                    size_t n_out, size_t n_traj, const double *y0,
+                    const double *parms, size_t n_parms, size_t parms_stride,
+                    const double *times, size_t n_times, const double *tcrit,
+                    size_t n_tcrit, double *y_out, double *out,
+                    int32_t *stats,    /* [4 x n_traj] */
+                    int32_t *code,     /* [n_traj] obj->code */
+                    double *t_last,    /* [n_traj] obj->t on return */
+                    double *step_size  /* [n_traj] obj->step_size_initial on
+                                          return, src/dopri.c:463 */);
+
+/* ---- dopri: device-resident batch handle ------------------------------- */
+
+/* Opaque; owns all device state of n_traj concurrent solver objects: the
+ * analogue of n_traj dopri_data structs (src/dopri.h:55-161). */
+typedef struct dde_dopri_batch_s dde_dopri_batch_t;
+
+/* dopri_data_alloc (src/dopri.c:8-90) for n_traj objects on the current
+ * device.  NULL on failure. */
+dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model,
+                                         const dde_dopri_control *ctl,
+                                         size_t n, size_t n_out,
+                                         size_t n_parms, size_t n_traj);
+/* dopri_data_free (src/dopri.c:221-235) */
+void dde_dopri_batch_free(dde_dopri_batch_t *b);
+
+/* Host -> device copy of initial state and parameters (layouts above).
+ * Either pointer may be NULL to keep what is resident. */
+int dde_dopri_batch_upload(dde_dopri_batch_t *b, const double *y0,
+                           const double *parms, size_t parms_stride);
+/* Output times and critical times (shared by all trajectories, like
+ * `steps` in difeq_replicate); validated as dopri_data_reset does
+ * (src/dopri.c:168-183). */
+int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times,
+                              size_t n_times, const double *tcrit,
+                              size_t n_tcrit);
+/* dopri_integrate for every trajectory, from the resident y0/parms.
+ * Asynchronous on the handle's stream. */
+int dde_dopri_batch_run(dde_dopri_batch_t *b);
+/* Wait for the handle's stream. */
+int dde_dopri_batch_sync(dde_dopri_batch_t *b);
+/* Device -> host copy of results (any pointer may be NULL). Synchronises. */
+int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out,
+                             int32_t *stats, int32_t *code, double *t_last,
+                             double *step_size);
+/* Milliseconds the last dde_dopri_batch_run spent on the device (CUDA
+ * events on the handle's stream); < 0 if none has completed. */
+double dde_dopri_batch_last_ms(dde_dopri_batch_t *b);
+/* Number of kernels the last dde_dopri_batch_run launched. */
+int dde_dopri_batch_last_launches(dde_dopri_batch_t *b);
+/* The `history` attribute for trajectory j: ring entries oldest first, each
+ * (order*n + 2) doubles (src/r_dopri.c:401-410, src/dopri.h:94-126).  Returns
+ * the number of entries, or < 0 on error; at most max_entries are copied. */
+long dde_dopri_batch_history(dde_dopri_batch_t *b, size_t j, double *history,
+                             size_t max_entries);
+/* Raw device pointers for zero-copy consumers (torch tensors etc.):
+ * which = 0 y_out, 1 out, 2 stats, 3 code, 4 t_last, 5 step_size, 6 y0,
+ * 7 parms. */
+void *dde_dopri_batch_device_ptr(dde_dopri_batch_t *b, int which);
+
+/* ---- dopri_interpolate -------------------------------------------------- */
+
+/* Batched equivalent of R/dopri.R:577-642: evaluate the dense-output
+ * polynomial of a stored history at arbitrary times.
+ *   history [history_len x n_entries x n_traj], history_len = order*n + 2
+ *   t       [n_t]  (shared)
+ *   y       [n_t x n x n_traj]  (R returns a length(t) x n matrix)
+ * Returns non-zero (and touches nothing) if any t lies outside
+ * [t_first, t_last + h_last] of any trajectory (R/dopri.R:596-600). */
+int dde_dopri_interpolate_batch(const double *history, size_t history_len,
+                                size_t n_entries, size_t n, size_t n_traj,
+                                const double *t, size_t n_t, double *y);
+
+/* ---- difeq -------------------------------------------------------------- */
+
+/* Replaces the replicate loop of r_difeq (src/r_difeq.c:94-103) and, per
+ * replicate j, difeq_data_alloc + difeq_run (src/difeq.c:9-47,127-258):
+ *   target(n, step, y, y_next, n_out, out, parms_j) iterated from steps[0]
+ *   to steps[n_steps-1], rows stored at the requested steps.
+ * Every replicate gets FRESH history state: the documented contract
+ * (R/difeq_replicate.R:1-4: each replicate == an independent difeq() run),
+ * not the reference's shared-ring artefact (SURVEY.md finding 5).
+ *   steps [n_steps]  strictly increasing (src/difeq.c:89-93)
+ *   y_out [n x nt x n_rep], out [n_out x nt x n_rep]
+ *   code  [n_rep]: DDE_OK_COMPLETE or DDE_ERR_DIFEQ_HISTORY
+ *   y_final [n x n_rep]: obj->y1 (src/difeq.c:244), may be NULL */
+int dde_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep,
+                    const double *y0, const double *parms, size_t n_parms,
+                    size_t parms_stride, const uint64_t *steps, size_t n_steps,
+                    size_t n_history, int32_t return_initial, double *y_out,
+                    double *out, int32_t *code, double *y_final);
+
+typedef struct dde_difeq_batch_s dde_difeq_batch_t;
+dde_difeq_batch_t *dde_difeq_batch_alloc(const char *model, size_t n,
+                                         size_t n_out, size_t n_parms,
+                                         size_t n_rep, size_t n_history);
+void dde_difeq_batch_free(dde_difeq_batch_t *b);
+int dde_difeq_batch_upload(dde_difeq_batch_t *b, const double *y0,
+                           const double *parms, size_t parms_stride);
+int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps,
+                              size_t n_steps, int32_t return_initial);
+int dde_difeq_batch_run(dde_difeq_batch_t *b);
+int dde_difeq_batch_sync(dde_difeq_batch_t *b);
+int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
+                             int32_t *code, double *y_final);
+double dde_difeq_batch_last_ms(dde_difeq_batch_t *b);
+
+/* ---- math ---------------------------------------------------------------- */
+
+/* The library's pow/exp, bit-identical restatements of glibc 2.39's
+ * x86-64 FMA variants (the libm the reference links to on this platform;
+ * call sites src/dopri.c:500,517,521,569).  Host build of the same source
+ * that runs on the device; exported so tests can pin it against libm. */
+double dde_pow_host(double x, double y);
+double dde_exp_host(double x);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DDE_B200_H */
