@@ -1,0 +1,173 @@
+"""Device-resident batch handles (the analogue of n_traj `dopri_data` /
+`difeq_data` objects kept alive between calls, src/dopri.h:55-161).
+
+Inputs are uploaded once; `run()` integrates every trajectory from the
+resident state, asynchronously on the handle's own CUDA stream; results are
+fetched on demand.  Used by bench.py and by the multi-GPU sharding helpers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .api import (DdeError, DopriBatchResult, _control, _f64, _prep_batch_inputs, _steps)
+from ._lib import c_double_p, c_uint64_p
+
+
+def _ptr(a):
+    """Address of a numpy array or torch tensor (host memory)."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class DopriBatch:
+    def __init__(self, func, n, n_traj, *, n_parms=0, n_out=0, method="dopri5", rtol=1e-6,
+                 atol=1e-6, step_size_min=0.0, step_size_max=float("inf"), step_size_initial=0.0,
+                 step_max_n=100000, step_size_min_allow=False, stiff_check=0, n_history=0,
+                 return_initial=True):
+        self._lib = _lib.load()
+        self.ctl = _control(method, rtol, atol, step_size_min, step_size_max, step_size_initial,
+                            step_max_n, step_size_min_allow, stiff_check, n_history, False,
+                            return_initial)
+        self.n, self.n_traj, self.n_parms, self.n_out = int(n), int(n_traj), int(n_parms), int(n_out)
+        self.n_history = int(n_history)
+        self.return_initial = bool(return_initial)
+        self.times = None
+        self._h = self._lib.dde_dopri_batch_alloc(func.encode(), C.byref(self.ctl), self.n,
+                                                  self.n_out, self.n_parms, self.n_traj)
+        if not self._h:
+            raise DdeError(_lib.last_error())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DdeError(_lib.last_error())
+
+    def upload(self, y0=None, parms=None, shared_parms=False):
+        """Host -> device.  Arrays may be numpy arrays or (pinned) torch CPU
+        tensors of float64 in the C-ABI layout: y0 [n_traj, n], parms
+        [n_traj, n_parms] (or [n_parms] with shared_parms)."""
+        stride = 0 if shared_parms else self.n_parms
+        self._check(self._lib.dde_dopri_batch_upload(self._h, _ptr(y0), _ptr(parms), stride))
+
+    def set_times(self, times, tcrit=None):
+        times = _f64(times, "times").ravel()
+        tc = None if tcrit is None else _f64(tcrit, "tcrit").ravel()
+        self._check(self._lib.dde_dopri_batch_set_times(
+            self._h, times.ctypes.data_as(c_double_p), times.shape[0],
+            None if tc is None else tc.ctypes.data_as(c_double_p), 0 if tc is None else tc.shape[0]))
+        self.times = times
+        self.nt = times.shape[0] if self.return_initial else times.shape[0] - 1
+
+    def run(self):
+        self._check(self._lib.dde_dopri_batch_run(self._h))
+
+    def sync(self):
+        self._check(self._lib.dde_dopri_batch_sync(self._h))
+
+    def last_ms(self):
+        return self._lib.dde_dopri_batch_last_ms(self._h)
+
+    def last_launches(self):
+        return self._lib.dde_dopri_batch_last_launches(self._h)
+
+    def download_into(self, y_out=None, out=None, stats=None, code=None, t_last=None,
+                      step_size=None):
+        """Device -> host into caller buffers (numpy or pinned torch tensors)."""
+        self._check(self._lib.dde_dopri_batch_download(self._h, _ptr(y_out), _ptr(out), _ptr(stats),
+                                                       _ptr(code), _ptr(t_last), _ptr(step_size)))
+
+    def download(self, want_y=True):
+        y_out = np.empty((self.n_traj, self.nt, self.n)) if want_y else None
+        out = np.empty((self.n_traj, self.nt, self.n_out)) if (self.n_out > 0 and want_y) else None
+        stats = np.empty((self.n_traj, 4), dtype=np.int32)
+        code = np.empty((self.n_traj,), dtype=np.int32)
+        t_last = np.empty((self.n_traj,))
+        step_size = np.empty((self.n_traj,))
+        self.download_into(y_out, out, stats, code, t_last, step_size)
+        return DopriBatchResult(y_out, out, stats, code, t_last, step_size, self.times,
+                                self.n_history)
+
+    def history(self, j):
+        order = 5 if self.ctl.method == 0 else 8
+        hl = order * self.n + 2
+        cap = max(self.n_history, 1)
+        buf = np.empty((cap, hl))
+        used = self._lib.dde_dopri_batch_history(self._h, int(j), buf.ctypes.data_as(c_double_p), cap)
+        if used < 0:
+            raise DdeError(_lib.last_error())
+        return buf[:used].copy()
+
+    def device_ptr(self, which):
+        return self._lib.dde_dopri_batch_device_ptr(self._h, int(which))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dde_dopri_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DifeqBatch:
+    def __init__(self, target, n, n_rep, *, n_parms=0, n_out=0, n_history=0):
+        self._lib = _lib.load()
+        self.n, self.n_rep, self.n_parms, self.n_out = int(n), int(n_rep), int(n_parms), int(n_out)
+        self.n_history = int(n_history)
+        self._h = self._lib.dde_difeq_batch_alloc(target.encode(), self.n, self.n_out, self.n_parms,
+                                                  self.n_rep, self.n_history)
+        if not self._h:
+            raise DdeError(_lib.last_error())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DdeError(_lib.last_error())
+
+    def upload(self, y0=None, parms=None, shared_parms=False):
+        stride = 0 if shared_parms else self.n_parms
+        self._check(self._lib.dde_difeq_batch_upload(self._h, _ptr(y0), _ptr(parms), stride))
+
+    def set_steps(self, steps, return_initial=True):
+        st = _steps(steps)
+        self._check(self._lib.dde_difeq_batch_set_steps(self._h, st.ctypes.data_as(c_uint64_p),
+                                                        st.shape[0], int(bool(return_initial))))
+        self.steps = st
+        self.nt = st.shape[0] if return_initial else st.shape[0] - 1
+
+    def run(self):
+        self._check(self._lib.dde_difeq_batch_run(self._h))
+
+    def sync(self):
+        self._check(self._lib.dde_difeq_batch_sync(self._h))
+
+    def last_ms(self):
+        return self._lib.dde_difeq_batch_last_ms(self._h)
+
+    def download_into(self, y_out=None, out=None, code=None, y_final=None):
+        self._check(self._lib.dde_difeq_batch_download(self._h, _ptr(y_out), _ptr(out), _ptr(code),
+                                                       _ptr(y_final)))
+
+    def download(self):
+        y_out = np.empty((self.n_rep, self.nt, self.n))
+        out = np.empty((self.n_rep, self.nt, self.n_out)) if self.n_out > 0 else None
+        code = np.empty((self.n_rep,), dtype=np.int32)
+        y_final = np.empty((self.n_rep, self.n))
+        self.download_into(y_out, out, code, y_final)
+        return y_out, out, code, y_final
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dde_difeq_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,1113 @@
+/* capi.cu -- host side of the C-ABI declared in include/dde_b200.h.
+ *
+ * Owns device memory, streams and the model registry; validates arguments
+ * the way the reference's reset functions do (/root/reference/src/dopri.c:
+ * 138-219, src/difeq.c:74-105) and launches the model's kernels.  No solver
+ * arithmetic happens on the host: if the CUDA path is unavailable every
+ * entry point fails loudly.
+ */
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dde_b200.h"
+#include "dde_math.h"
+#include "difeq_kernels.cuh"
+#include "dopri_kernels.cuh"
+#include "registry.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+#define DDE_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t err__ = (call);                                                 \
+    if (err__ != cudaSuccess) {                                                 \
+      return fail("CUDA error %s at %s:%d (%s)", cudaGetErrorName(err__), __FILE__, __LINE__, \
+                  cudaGetErrorString(err__));                                   \
+    }                                                                           \
+  } while (0)
+
+dde::ModelDesc *g_models = nullptr;
+std::mutex g_models_mutex;
+
+/* exact-n registration wins over a runtime-n one of the same name */
+dde::ModelDesc *find_model(const char *name, int kind, size_t n) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  dde::ModelDesc *wild = nullptr;
+  for (dde::ModelDesc *m = g_models; m != nullptr; m = m->next) {
+    if (strcmp(m->name, name) != 0 || (m->kind & kind) == 0) {
+      continue;
+    }
+    if (m->n == (int) n) {
+      return m;
+    }
+    if (m->n == 0) {
+      wild = m;
+    }
+  }
+  return wild;
+}
+
+bool model_name_known(const char *name) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  for (dde::ModelDesc *m = g_models; m != nullptr; m = m->next) {
+    if (strcmp(m->name, name) == 0) {
+      return true;
+    }
+  }
+  return false;
+}
+
+int check_model_shape(const dde::ModelDesc *m, size_t n, size_t n_parms, size_t n_out) {
+  if (m->n > 0 ? n != (size_t) m->n : (n < 1 || n > (size_t) m->dyn_max_n)) {
+    return fail("model '%s' is compiled for n = %d%s, got n = %zu", m->name,
+                m->n > 0 ? m->n : m->dyn_max_n, m->n > 0 ? "" : " at most", n);
+  }
+  if (m->n_parms >= 0 ? n_parms != (size_t) m->n_parms : n_parms > (size_t) m->dyn_max_parms) {
+    return fail("model '%s' takes %d%s parameters, got %zu", m->name,
+                m->n_parms >= 0 ? m->n_parms : m->dyn_max_parms, m->n_parms >= 0 ? "" : " at most",
+                n_parms);
+  }
+  if (n_out != 0 &&
+      (m->n_out >= 0 ? n_out != (size_t) m->n_out : n_out > (size_t) m->dyn_max_out)) {
+    return fail("model '%s' has %d output variables, got n_out = %zu", m->name,
+                m->n_out >= 0 ? m->n_out : m->dyn_max_out, n_out);
+  }
+  return 0;
+}
+
+__global__ void fill_int_kernel(int *x, long long n, int value) {
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if (i < n) {
+    x[i] = value;
+  }
+}
+
+template <class T>
+void free_dev(T *&p) {
+  if (p != nullptr) {
+    cudaFree(p);
+    p = nullptr;
+  }
+}
+
+} /* namespace */
+
+extern "C" void dde_register_model(dde::ModelDesc *desc) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  desc->next = g_models;
+  g_models = desc;
+}
+
+/* ---- handles ------------------------------------------------------------- */
+
+struct dde_dopri_batch_s {
+  dde::ModelDesc *model = nullptr;
+  dde_dopri_control ctl;
+  size_t n = 0, n_out = 0, n_parms = 0, n_traj = 0;
+  size_t parms_stride = 0;
+  size_t n_times = 0, n_tcrit = 0, nt = 0;
+  size_t cap_times = 0, cap_tcrit = 0, cap_y_out = 0, cap_out = 0;
+  int device = 0, device_sms = 0;
+  int order = 5;
+  int reset_code = 0; /* ERR_ZERO_TIME_DIFFERENCE / ERR_INCONSISTENT_TIME from reset */
+  double sign = 1.0;
+  int tcrit_idx0 = 0;
+  bool have_times = false, have_y0 = false, ran = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_launches = 0;
+  /* device memory */
+  double *d_y0 = nullptr, *d_parms = nullptr, *d_times = nullptr, *d_tcrit = nullptr;
+  double *d_y_out = nullptr, *d_out = nullptr, *d_t_last = nullptr, *d_step_size = nullptr;
+  int *d_stats = nullptr, *d_code = nullptr;
+  double *d_ring = nullptr;
+  unsigned *d_ring_count = nullptr;
+  unsigned long long *d_next = nullptr;
+};
+
+struct dde_difeq_batch_s {
+  dde::ModelDesc *model = nullptr;
+  size_t n = 0, n_out = 0, n_parms = 0, n_rep = 0, n_history = 0;
+  size_t parms_stride = 0;
+  size_t n_steps = 0, nt = 0, cap_steps = 0, cap_y_out = 0, cap_out = 0;
+  int return_initial = 1;
+  int device = 0, device_sms = 0;
+  bool have_steps = false, have_y0 = false, ran = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *d_y0 = nullptr, *d_parms = nullptr, *d_y_out = nullptr, *d_out = nullptr;
+  double *d_y_final = nullptr, *d_ring = nullptr;
+  unsigned long long *d_steps = nullptr, *d_next = nullptr;
+  int *d_code = nullptr;
+};
+
+extern "C" {
+
+const char *dde_last_error(void) { return g_last_error.c_str(); }
+
+const char *dde_version(void) { return "dde_b200 0.1.0 (sm_100a)"; }
+
+void dde_dopri_control_default(dde_dopri_control *ctl, int32_t method) {
+  memset(ctl, 0, sizeof *ctl);
+  ctl->atol = 1e-6;
+  ctl->rtol = 1e-6;
+  ctl->step_size_min = 0.0;       /* R/dopri.R:296; clamped to DBL_EPSILON at use */
+  ctl->step_size_max = INFINITY;  /* R/dopri.R:296; clamped to DBL_MAX at use */
+  ctl->step_size_initial = 0.0;
+  ctl->step_max_n = 100000;
+  ctl->stiff_check = 0;
+  ctl->n_history = 0;
+  ctl->method = method;
+  ctl->step_size_min_allow = 0;
+  ctl->grow_history = 0;
+  ctl->return_initial = 1;
+}
+
+size_t dde_model_count(void) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  size_t k = 0;
+  for (dde::ModelDesc *m = g_models; m != nullptr; m = m->next) {
+    ++k;
+  }
+  return k;
+}
+
+const char *dde_model_name(size_t i) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  size_t k = 0;
+  for (dde::ModelDesc *m = g_models; m != nullptr; m = m->next, ++k) {
+    if (k == i) {
+      return m->name;
+    }
+  }
+  return nullptr;
+}
+
+int dde_model_info(const char *model, int32_t *kind, size_t *n, size_t *n_parms, size_t *n_out) {
+  std::lock_guard<std::mutex> lock(g_models_mutex);
+  for (dde::ModelDesc *m = g_models; m != nullptr; m = m->next) {
+    if (strcmp(m->name, model) == 0) {
+      if (kind) *kind = m->kind;
+      if (n) *n = (size_t) m->n;
+      if (n_parms) *n_parms = m->n_parms >= 0 ? (size_t) m->n_parms : (size_t) -1;
+      if (n_out) *n_out = m->n_out >= 0 ? (size_t) m->n_out : (size_t) -1;
+      return 0;
+    }
+  }
+  return fail("unknown model '%s'", model);
+}
+
+/* r_dopri_error, src/r_dopri.c:264-297 */
+int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf, size_t len) {
+  switch (code) {
+    case DDE_ERR_ZERO_TIME_DIFFERENCE:
+      snprintf(buf, len, "Initialisation failure: Beginning and end times are the same");
+      break;
+    case DDE_ERR_INCONSISTENT_TIME:
+      snprintf(buf, len, "Initialisation failure: Times have inconsistent sign");
+      break;
+    case DDE_ERR_TOO_MANY_STEPS:
+      snprintf(buf, len, "Integration failure: too many steps (at t = %2.5f)", t);
+      break;
+    case DDE_ERR_STEP_SIZE_TOO_SMALL:
+      snprintf(buf, len, "Integration failure: step size too small (at t = %2.5f)", t);
+      break;
+    case DDE_ERR_STEP_SIZE_VANISHED:
+      snprintf(buf, len, "Integration failure: step size vanished (at t = %2.5f)", t);
+      break;
+    case DDE_ERR_YLAG_FAIL:
+      if (n_history == 0) {
+        snprintf(buf, len, "Integration failure: can't use ylag in model with no history");
+      } else {
+        snprintf(buf, len,
+                 "Integration failure: did not find time in history (at t = %2.5f)", t);
+      }
+      break;
+    case DDE_ERR_STIFF:
+      snprintf(buf, len, "Integration failure: problem became stiff (at t = %2.5f)", t);
+      break;
+    case DDE_ERR_NONFINITE_DERIV: /* src/dopri.c:333 */
+      snprintf(buf, len, "non-finite derivative at initial time");
+      break;
+    case DDE_ERR_DIFEQ_HISTORY: /* src/difeq.c:268 */
+      snprintf(buf, len, "difeq failure: did not find step in history");
+      break;
+    case DDE_OK_COMPLETE:
+    case DDE_OK_INTERRUPTED:
+      snprintf(buf, len, "OK");
+      return 0;
+    default:
+      snprintf(buf, len, "Integration failure: (code %d) [dde bug]", (int) code);
+      break;
+  }
+  return 1;
+}
+
+double dde_pow_host(double x, double y) { return dde_pow(x, y); }
+double dde_exp_host(double x) { return dde_exp(x); }
+
+void *dde_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    fail("cudaHostAlloc(%zu) failed", bytes);
+    (void) cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void dde_host_free(void *p) {
+  if (p != nullptr) {
+    cudaFreeHost(p);
+  }
+}
+
+/* ---- dopri ----------------------------------------------------------------- */
+
+void dde_dopri_batch_free(dde_dopri_batch_t *b) {
+  if (b == nullptr) {
+    return;
+  }
+  cudaSetDevice(b->device);
+  free_dev(b->d_y0);
+  free_dev(b->d_parms);
+  free_dev(b->d_times);
+  free_dev(b->d_tcrit);
+  free_dev(b->d_y_out);
+  free_dev(b->d_out);
+  free_dev(b->d_t_last);
+  free_dev(b->d_step_size);
+  free_dev(b->d_stats);
+  free_dev(b->d_code);
+  free_dev(b->d_ring);
+  free_dev(b->d_ring_count);
+  free_dev(b->d_next);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model, const dde_dopri_control *ctl,
+                                         size_t n, size_t n_out, size_t n_parms,
+                                         size_t n_traj) {
+  if (model == nullptr || ctl == nullptr) {
+    fail("model and ctl must not be NULL");
+    return nullptr;
+  }
+  dde::ModelDesc *m = find_model(model, 1, n);
+  if (m == nullptr) {
+    if (model_name_known(model)) {
+      fail("model '%s' is not compiled for dopri with n = %zu", model, n);
+    } else {
+      fail("unknown model '%s'", model);
+    }
+    return nullptr;
+  }
+  if (check_model_shape(m, n, n_parms, n_out) != 0) {
+    return nullptr;
+  }
+  if (ctl->method != DDE_DOPRI_5 && ctl->method != DDE_DOPRI_853) {
+    fail("unknown method %d", (int) ctl->method);
+    return nullptr;
+  }
+  if (ctl->grow_history) {
+    fail("grow_history is not supported on the device (no allocation inside kernels): "
+         "pre-size n_history");
+    return nullptr;
+  }
+  if (n_traj == 0) {
+    fail("n_traj must be positive");
+    return nullptr;
+  }
+  if (ctl->n_history > 0x7fffffffULL) {
+    fail("n_history too large");
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    fail("no CUDA device available: dde_b200 has no CPU fallback");
+    (void) cudaGetLastError();
+    return nullptr;
+  }
+  dde_dopri_batch_t *b = new dde_dopri_batch_t();
+  b->model = m;
+  b->ctl = *ctl;
+  /* src/r_dopri.c:160-161 */
+  b->ctl.step_size_min = fmax(fabs(ctl->step_size_min), DBL_EPSILON);
+  b->ctl.step_size_max = fmin(fabs(ctl->step_size_max), DBL_MAX);
+  b->n = n;
+  b->n_out = n_out;
+  b->n_parms = n_parms;
+  b->n_traj = n_traj;
+  b->order = ctl->method == DDE_DOPRI_5 ? 5 : 8;
+  cudaDeviceProp prop;
+  bool ok = cudaGetDevice(&b->device) == cudaSuccess &&
+            cudaGetDeviceProperties(&prop, b->device) == cudaSuccess;
+  if (ok) {
+    b->device_sms = prop.multiProcessorCount;
+  }
+  const size_t hl = (size_t) b->order * n + 2;
+  ok = ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_y0, sizeof(double) * n * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_parms, sizeof(double) * (n_parms ? n_parms : 1) * n_traj) ==
+                 cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_t_last, sizeof(double) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_step_size, sizeof(double) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_stats, sizeof(int) * 4 * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_code, sizeof(int) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_ring_count, sizeof(unsigned) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_next, sizeof(unsigned long long)) == cudaSuccess;
+  if (ok && ctl->n_history > 0) {
+    const size_t bytes = sizeof(double) * hl * (size_t) ctl->n_history * n_traj;
+    if (cudaMalloc(&b->d_ring, bytes) != cudaSuccess) {
+      fail("cannot allocate %.2f GB of history rings (n_traj %zu x n_history %llu x %zu doubles): "
+           "shard the batch or lower n_history",
+           (double) bytes / 1e9, n_traj, (unsigned long long) ctl->n_history, hl);
+      (void) cudaGetLastError();
+      dde_dopri_batch_free(b);
+      return nullptr;
+    }
+  }
+  if (!ok) {
+    cudaError_t err = cudaGetLastError();
+    fail("device allocation failed (%s)", cudaGetErrorString(err));
+    dde_dopri_batch_free(b);
+    return nullptr;
+  }
+  return b;
+}
+
+int dde_dopri_batch_upload(dde_dopri_batch_t *b, const double *y0, const double *parms,
+                           size_t parms_stride) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y0 != nullptr) {
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, y0, sizeof(double) * b->n * b->n_traj,
+                             cudaMemcpyHostToDevice, b->stream));
+    b->have_y0 = true;
+  }
+  if (parms != nullptr && b->n_parms > 0) {
+    if (parms_stride != 0 && parms_stride != b->n_parms) {
+      return fail("parms_stride must be 0 (shared) or n_parms");
+    }
+    const size_t count = parms_stride == 0 ? b->n_parms : b->n_parms * b->n_traj;
+    DDE_CUDA(cudaMemcpyAsync(b->d_parms, parms, sizeof(double) * count, cudaMemcpyHostToDevice,
+                             b->stream));
+    b->parms_stride = parms_stride;
+  }
+  return 0;
+}
+
+int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times, size_t n_times,
+                              const double *tcrit, size_t n_tcrit) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (times == nullptr || n_times < 2) {
+    return fail("At least two times must be given"); /* src/r_dopri.c:51-53 */
+  }
+  if (n_times > 0x7fffffff || n_tcrit > 0x7fffffff) {
+    return fail("too many times");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  /* dopri_data_reset's checks, src/dopri.c:168-183 */
+  b->reset_code = 0;
+  if (times[n_times - 1] == times[0]) {
+    b->reset_code = DDE_ERR_ZERO_TIME_DIFFERENCE;
+    b->sign = 1.0;
+  } else {
+    b->sign = copysign(1.0, times[n_times - 1] - times[0]);
+    for (size_t i = 0; i + 1 < n_times; ++i) {
+      const double t0 = times[i], t1 = times[i + 1];
+      if ((b->sign > 0 && t1 < t0) || (b->sign < 0 && t1 > t0)) {
+        b->reset_code = DDE_ERR_INCONSISTENT_TIME;
+        break;
+      }
+    }
+  }
+  /* critical times already behind the start are skipped, src/dopri.c:199-206 */
+  b->tcrit_idx0 = 0;
+  if (n_tcrit > 0) {
+    const double t0 = b->sign * times[0];
+    while ((size_t) b->tcrit_idx0 < n_tcrit && b->sign * tcrit[b->tcrit_idx0] <= t0) {
+      b->tcrit_idx0++;
+    }
+  }
+  if (n_times > b->cap_times) {
+    free_dev(b->d_times);
+    DDE_CUDA(cudaMalloc(&b->d_times, sizeof(double) * n_times));
+    b->cap_times = n_times;
+  }
+  if (n_tcrit > b->cap_tcrit) {
+    free_dev(b->d_tcrit);
+    DDE_CUDA(cudaMalloc(&b->d_tcrit, sizeof(double) * n_tcrit));
+    b->cap_tcrit = n_tcrit;
+  }
+  DDE_CUDA(cudaMemcpyAsync(b->d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice,
+                           b->stream));
+  if (n_tcrit > 0) {
+    DDE_CUDA(cudaMemcpyAsync(b->d_tcrit, tcrit, sizeof(double) * n_tcrit,
+                             cudaMemcpyHostToDevice, b->stream));
+  }
+  /* the copies read caller memory that may go away */
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  b->n_times = n_times;
+  b->n_tcrit = n_tcrit;
+  b->nt = b->ctl.return_initial ? n_times : n_times - 1;
+  const size_t need_y = b->n * b->nt * b->n_traj;
+  const size_t need_o = b->n_out * b->nt * b->n_traj;
+  if (need_y > b->cap_y_out) {
+    free_dev(b->d_y_out);
+    if (cudaMalloc(&b->d_y_out, sizeof(double) * need_y) != cudaSuccess) {
+      (void) cudaGetLastError();
+      b->cap_y_out = 0;
+      return fail("cannot allocate %.2f GB for the output array [n x nt x n_traj]",
+                  (double) (sizeof(double) * need_y) / 1e9);
+    }
+    b->cap_y_out = need_y;
+  }
+  if (need_o > b->cap_out) {
+    free_dev(b->d_out);
+    DDE_CUDA(cudaMalloc(&b->d_out, sizeof(double) * need_o));
+    b->cap_out = need_o;
+  }
+  b->have_times = true;
+  return 0;
+}
+
+int dde_dopri_batch_run(dde_dopri_batch_t *b) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->have_times || !b->have_y0) {
+    return fail("upload y0 and set times before running");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  DDE_CUDA(cudaEventRecord(b->ev0, b->stream));
+  /* the R glue hands the solver zero-filled result arrays, src/r_dopri.c:169 */
+  DDE_CUDA(cudaMemsetAsync(b->d_y_out, 0, sizeof(double) * b->n * b->nt * b->n_traj, b->stream));
+  if (b->n_out > 0) {
+    DDE_CUDA(cudaMemsetAsync(b->d_out, 0, sizeof(double) * b->n_out * b->nt * b->n_traj,
+                             b->stream));
+  }
+  b->last_launches = 0;
+  if (b->reset_code != 0) {
+    /* dopri_integrate returns right after reset, src/dopri.c:298-300 */
+    DDE_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(int) * 4 * b->n_traj, b->stream));
+    DDE_CUDA(cudaMemsetAsync(b->d_t_last, 0, sizeof(double) * b->n_traj, b->stream));
+    DDE_CUDA(cudaMemsetAsync(b->d_step_size, 0, sizeof(double) * b->n_traj, b->stream));
+    DDE_CUDA(cudaMemsetAsync(b->d_ring_count, 0, sizeof(unsigned) * b->n_traj, b->stream));
+    const int threads = 256;
+    const long long blocks = ((long long) b->n_traj + threads - 1) / threads;
+    fill_int_kernel<<<(unsigned) blocks, threads, 0, b->stream>>>(b->d_code, (long long) b->n_traj,
+                                                                  b->reset_code);
+    DDE_CUDA(cudaGetLastError());
+    b->last_launches = 1;
+  } else {
+    DDE_CUDA(cudaMemsetAsync(b->d_next, 0, sizeof(unsigned long long), b->stream));
+    dde::DopriArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_traj = (long long) b->n_traj;
+    a.n = (int) b->n;
+    a.n_out = (int) b->n_out;
+    a.n_parms = (int) b->n_parms;
+    a.parms_stride = (long long) b->parms_stride;
+    a.y0 = b->d_y0;
+    a.parms = b->d_parms;
+    a.times = b->d_times;
+    a.tcrit = b->d_tcrit;
+    a.n_times = (int) b->n_times;
+    a.n_tcrit = (int) b->n_tcrit;
+    a.tcrit_idx0 = b->tcrit_idx0;
+    a.atol = b->ctl.atol;
+    a.rtol = b->ctl.rtol;
+    a.step_size_min = b->ctl.step_size_min;
+    a.step_size_max = b->ctl.step_size_max;
+    a.step_size_initial = b->ctl.step_size_initial;
+    a.step_max_n = b->ctl.step_max_n;
+    a.stiff_check = b->ctl.stiff_check;
+    a.n_history = (int) b->ctl.n_history;
+    a.step_size_min_allow = b->ctl.step_size_min_allow;
+    a.return_initial = b->ctl.return_initial;
+    a.sign = b->sign;
+    a.y_out = b->d_y_out;
+    a.out = b->d_out;
+    a.stats = b->d_stats;
+    a.code = b->d_code;
+    a.t_last = b->d_t_last;
+    a.step_size = b->d_step_size;
+    a.ring = b->d_ring;
+    a.ring_count = b->d_ring_count;
+    a.next_traj = b->d_next;
+    int launches = 0;
+    cudaError_t err = b->model->launch_dopri(b->ctl.method, a, b->device_sms, b->stream, &launches);
+    if (err != cudaSuccess) {
+      return fail("kernel launch failed for model '%s': %s", b->model->name,
+                  cudaGetErrorString(err));
+    }
+    b->last_launches = launches;
+  }
+  DDE_CUDA(cudaEventRecord(b->ev1, b->stream));
+  b->ran = true;
+  return 0;
+}
+
+int dde_dopri_batch_sync(dde_dopri_batch_t *b) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out, int32_t *stats,
+                             int32_t *code, double *t_last, double *step_size) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y_out) {
+    DDE_CUDA(cudaMemcpyAsync(y_out, b->d_y_out, sizeof(double) * b->n * b->nt * b->n_traj,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (out && b->n_out > 0) {
+    DDE_CUDA(cudaMemcpyAsync(out, b->d_out, sizeof(double) * b->n_out * b->nt * b->n_traj,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (stats) {
+    DDE_CUDA(cudaMemcpyAsync(stats, b->d_stats, sizeof(int) * 4 * b->n_traj,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (code) {
+    DDE_CUDA(cudaMemcpyAsync(code, b->d_code, sizeof(int) * b->n_traj, cudaMemcpyDeviceToHost,
+                             b->stream));
+  }
+  if (t_last) {
+    DDE_CUDA(cudaMemcpyAsync(t_last, b->d_t_last, sizeof(double) * b->n_traj,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (step_size) {
+    DDE_CUDA(cudaMemcpyAsync(step_size, b->d_step_size, sizeof(double) * b->n_traj,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+double dde_dopri_batch_last_ms(dde_dopri_batch_t *b) {
+  if (b == nullptr || !b->ran) {
+    return -1.0;
+  }
+  cudaSetDevice(b->device);
+  if (cudaEventSynchronize(b->ev1) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  return (double) ms;
+}
+
+int dde_dopri_batch_last_launches(dde_dopri_batch_t *b) {
+  return b == nullptr ? 0 : b->last_launches;
+}
+
+long dde_dopri_batch_history(dde_dopri_batch_t *b, size_t j, double *history,
+                             size_t max_entries) {
+  if (b == nullptr || !b->ran || j >= b->n_traj) {
+    fail("bad handle or trajectory index");
+    return -1;
+  }
+  if (cudaSetDevice(b->device) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    fail("CUDA error in history export");
+    return -1;
+  }
+  const size_t cap = (size_t) b->ctl.n_history;
+  if (cap == 0) {
+    return 0;
+  }
+  unsigned count = 0;
+  if (cudaMemcpy(&count, b->d_ring_count + j, sizeof count, cudaMemcpyDeviceToHost) !=
+      cudaSuccess) {
+    fail("CUDA error in history export");
+    return -1;
+  }
+  const size_t hl = (size_t) b->order * b->n + 2;
+  const size_t used = count < cap ? count : cap;
+  if (history != nullptr && used > 0) {
+    std::vector<double> ring(cap * hl);
+    if (cudaMemcpy(ring.data(), b->d_ring + j * cap * hl, sizeof(double) * cap * hl,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fail("CUDA error in history export");
+      return -1;
+    }
+    /* oldest first, like ring_buffer_read from the tail (src/r_dopri.c:401-404) */
+    const size_t first = count - used;
+    for (size_t e = 0; e < used && e < max_entries; ++e) {
+      const size_t slot = (first + e) % cap;
+      memcpy(history + e * hl, ring.data() + slot * hl, sizeof(double) * hl);
+    }
+  }
+  return (long) used;
+}
+
+void *dde_dopri_batch_device_ptr(dde_dopri_batch_t *b, int which) {
+  if (b == nullptr) {
+    return nullptr;
+  }
+  switch (which) {
+    case 0: return b->d_y_out;
+    case 1: return b->d_out;
+    case 2: return b->d_stats;
+    case 3: return b->d_code;
+    case 4: return b->d_t_last;
+    case 5: return b->d_step_size;
+    case 6: return b->d_y0;
+    case 7: return b->d_parms;
+    default: return nullptr;
+  }
+}
+
+int dde_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, size_t n_out,
+                    size_t n_traj, const double *y0, const double *parms, size_t n_parms,
+                    size_t parms_stride, const double *times, size_t n_times,
+                    const double *tcrit, size_t n_tcrit, double *y_out, double *out,
+                    int32_t *stats, int32_t *code, double *t_last, double *step_size) {
+  if (y0 == nullptr) {
+    return fail("y0 must not be NULL");
+  }
+  if (n_parms > 0 && parms == nullptr) {
+    return fail("parms must not be NULL when n_parms > 0");
+  }
+  dde_dopri_batch_t *b = dde_dopri_batch_alloc(model, ctl, n, n_out, n_parms, n_traj);
+  if (b == nullptr) {
+    return 1;
+  }
+  int rc = dde_dopri_batch_upload(b, y0, parms, parms_stride);
+  rc = rc ? rc : dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
+  rc = rc ? rc : dde_dopri_batch_run(b);
+  rc = rc ? rc : dde_dopri_batch_download(b, y_out, out, stats, code, t_last, step_size);
+  dde_dopri_batch_free(b);
+  return rc;
+}
+
+/* ---- dopri_interpolate ------------------------------------------------------ */
+
+} /* extern "C" */
+
+namespace {
+
+/* One thread per (query time, trajectory): locate the entry like R's
+ * findInterval (R/dopri.R:602) and evaluate all n components. */
+__global__ void interpolate_kernel(const double *history, int hl, int n_entries, int n,
+                                   long long n_traj, const double *t, int n_t, double *y) {
+  const long long gid = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if (gid >= n_traj * n_t) {
+    return;
+  }
+  const long long j = gid / n_t;
+  const int q = (int) (gid % n_t);
+  const int order = (hl - 2) / n;
+  const double *h = history + (size_t) j * (size_t) n_entries * (size_t) hl;
+  const double tq = t[q];
+  const int it = hl - 2;
+  int lo = 0, hi = n_entries; /* last entry with time <= tq */
+  while (hi - lo > 1) {
+    const int mid = lo + (hi - lo) / 2;
+    if (h[(size_t) mid * hl + it] <= tq) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  const double *e = h + (size_t) lo * hl;
+  const double theta = (tq - e[it]) / e[it + 1];
+  const double theta1 = 1.0 - theta;
+  double *dst = y + (size_t) j * (size_t) n * (size_t) n_t;
+  for (int i = 0; i < n; ++i) {
+    dst[(size_t) i * n_t + q] = order == 5 ? dde::interp5(n, theta, theta1, e + i)
+                                           : dde::interp853(n, theta, theta1, e + i);
+  }
+}
+
+} /* namespace */
+
+extern "C" {
+
+int dde_dopri_interpolate_batch(const double *history, size_t history_len, size_t n_entries,
+                                size_t n, size_t n_traj, const double *t, size_t n_t,
+                                double *y) {
+  if (history == nullptr || t == nullptr || y == nullptr) {
+    return fail("NULL argument");
+  }
+  if (n == 0 || history_len < 2 || (history_len - 2) % n != 0) {
+    return fail("Corrupt history object: incorrect number of rows"); /* R/dopri.R:590-594 */
+  }
+  const size_t order = (history_len - 2) / n;
+  if (order != 5 && order != 8) {
+    return fail("Corrupt history object: incorrect number of rows");
+  }
+  if (n_entries == 0 || n_t == 0 || n_traj == 0) {
+    return fail("empty history or no times");
+  }
+  /* range check, R/dopri.R:596-600 */
+  double tmin = t[0], tmax = t[0];
+  for (size_t q = 1; q < n_t; ++q) {
+    tmin = fmin(tmin, t[q]);
+    tmax = fmax(tmax, t[q]);
+  }
+  for (size_t j = 0; j < n_traj; ++j) {
+    const double *h = history + j * n_entries * history_len;
+    const double first = h[history_len - 2];
+    const double *le = h + (n_entries - 1) * history_len;
+    const double end = le[history_len - 2] + le[history_len - 1];
+    if (tmin < first || tmax > end) {
+      return fail("Time falls outside of range of known history [%g, %g]", first, end);
+    }
+  }
+  double *d_h = nullptr, *d_t = nullptr, *d_y = nullptr;
+  const size_t hb = sizeof(double) * history_len * n_entries * n_traj;
+  const size_t yb = sizeof(double) * n_t * n * n_traj;
+  cudaError_t err = cudaMalloc(&d_h, hb);
+  err = err ? err : cudaMalloc(&d_t, sizeof(double) * n_t);
+  err = err ? err : cudaMalloc(&d_y, yb);
+  err = err ? err : cudaMemcpy(d_h, history, hb, cudaMemcpyHostToDevice);
+  err = err ? err : cudaMemcpy(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) {
+    const long long total = (long long) n_traj * (long long) n_t;
+    const int threads = 128;
+    interpolate_kernel<<<(unsigned) ((total + threads - 1) / threads), threads>>>(
+        d_h, (int) history_len, (int) n_entries, (int) n, (long long) n_traj, d_t, (int) n_t, d_y);
+    err = cudaGetLastError();
+  }
+  err = err ? err : cudaMemcpy(y, d_y, yb, cudaMemcpyDeviceToHost);
+  cudaFree(d_h);
+  cudaFree(d_t);
+  cudaFree(d_y);
+  if (err != cudaSuccess) {
+    (void) cudaGetLastError();
+    return fail("CUDA error in dde_dopri_interpolate_batch: %s", cudaGetErrorString(err));
+  }
+  return 0;
+}
+
+/* ---- difeq -------------------------------------------------------------------- */
+
+void dde_difeq_batch_free(dde_difeq_batch_t *b) {
+  if (b == nullptr) {
+    return;
+  }
+  cudaSetDevice(b->device);
+  free_dev(b->d_y0);
+  free_dev(b->d_parms);
+  free_dev(b->d_y_out);
+  free_dev(b->d_out);
+  free_dev(b->d_y_final);
+  free_dev(b->d_ring);
+  free_dev(b->d_steps);
+  free_dev(b->d_next);
+  free_dev(b->d_code);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+dde_difeq_batch_t *dde_difeq_batch_alloc(const char *model, size_t n, size_t n_out,
+                                         size_t n_parms, size_t n_rep, size_t n_history) {
+  if (model == nullptr) {
+    fail("model must not be NULL");
+    return nullptr;
+  }
+  dde::ModelDesc *m = find_model(model, 2, n);
+  if (m == nullptr) {
+    if (model_name_known(model)) {
+      fail("model '%s' is not compiled for difeq with n = %zu", model, n);
+    } else {
+      fail("unknown model '%s'", model);
+    }
+    return nullptr;
+  }
+  if (check_model_shape(m, n, n_parms, n_out) != 0) {
+    return nullptr;
+  }
+  if (n_rep == 0) {
+    fail("n_rep must be positive");
+    return nullptr;
+  }
+  if (n_history > 0 && n_history < 2) {
+    fail("If given, n_history must be at least 2"); /* R/difeq.R:119-121 */
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    fail("no CUDA device available: dde_b200 has no CPU fallback");
+    (void) cudaGetLastError();
+    return nullptr;
+  }
+  dde_difeq_batch_t *b = new dde_difeq_batch_t();
+  b->model = m;
+  b->n = n;
+  b->n_out = n_out;
+  b->n_parms = n_parms;
+  b->n_rep = n_rep;
+  b->n_history = n_history;
+  cudaDeviceProp prop;
+  bool ok = cudaGetDevice(&b->device) == cudaSuccess &&
+            cudaGetDeviceProperties(&prop, b->device) == cudaSuccess;
+  if (ok) {
+    b->device_sms = prop.multiProcessorCount;
+  }
+  ok = ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_y0, sizeof(double) * n * n_rep) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_parms, sizeof(double) * (n_parms ? n_parms : 1) * n_rep) ==
+                 cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_y_final, sizeof(double) * n * n_rep) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_code, sizeof(int) * n_rep) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_next, sizeof(unsigned long long)) == cudaSuccess;
+  if (ok && n_history > 0) {
+    ok = cudaMalloc(&b->d_ring, sizeof(double) * (1 + n + n_out) * n_history * n_rep) ==
+         cudaSuccess;
+  }
+  if (!ok) {
+    cudaError_t err = cudaGetLastError();
+    fail("device allocation failed (%s)", cudaGetErrorString(err));
+    dde_difeq_batch_free(b);
+    return nullptr;
+  }
+  return b;
+}
+
+int dde_difeq_batch_upload(dde_difeq_batch_t *b, const double *y0, const double *parms,
+                           size_t parms_stride) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y0 != nullptr) {
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, y0, sizeof(double) * b->n * b->n_rep,
+                             cudaMemcpyHostToDevice, b->stream));
+    b->have_y0 = true;
+  }
+  if (parms != nullptr && b->n_parms > 0) {
+    if (parms_stride != 0 && parms_stride != b->n_parms) {
+      return fail("parms_stride must be 0 (shared) or n_parms");
+    }
+    const size_t count = parms_stride == 0 ? b->n_parms : b->n_parms * b->n_rep;
+    DDE_CUDA(cudaMemcpyAsync(b->d_parms, parms, sizeof(double) * count, cudaMemcpyHostToDevice,
+                             b->stream));
+    b->parms_stride = parms_stride;
+  }
+  return 0;
+}
+
+int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps, size_t n_steps,
+                              int32_t return_initial) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (steps == nullptr || n_steps < 2) {
+    return fail("At least two steps must be given");
+  }
+  /* difeq_data_reset, src/difeq.c:85-93 */
+  if (steps[n_steps - 1] == steps[0]) {
+    return fail("Initialisation failure: Beginning and end steps are the same");
+  }
+  for (size_t i = 0; i + 1 < n_steps; ++i) {
+    if (steps[i + 1] <= steps[i]) {
+      return fail("Initialisation failure: Steps not strictly increasing");
+    }
+  }
+  if (n_steps > 0x7fffffff || steps[n_steps - 1] > 0x7fffffffULL) {
+    return fail("steps must fit an int (yprev takes int steps, src/difeq.c:274)");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (n_steps > b->cap_steps) {
+    free_dev(b->d_steps);
+    DDE_CUDA(cudaMalloc(&b->d_steps, sizeof(unsigned long long) * n_steps));
+    b->cap_steps = n_steps;
+  }
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "uint64_t layout");
+  DDE_CUDA(cudaMemcpyAsync(b->d_steps, steps, sizeof(uint64_t) * n_steps, cudaMemcpyHostToDevice,
+                           b->stream));
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  b->n_steps = n_steps;
+  b->return_initial = return_initial != 0;
+  b->nt = return_initial ? n_steps : n_steps - 1;
+  const size_t need_y = b->n * b->nt * b->n_rep;
+  const size_t need_o = b->n_out * b->nt * b->n_rep;
+  if (need_y > b->cap_y_out) {
+    free_dev(b->d_y_out);
+    if (cudaMalloc(&b->d_y_out, sizeof(double) * need_y) != cudaSuccess) {
+      (void) cudaGetLastError();
+      b->cap_y_out = 0;
+      return fail("cannot allocate %.2f GB for the output array [n x nt x n_rep]",
+                  (double) (sizeof(double) * need_y) / 1e9);
+    }
+    b->cap_y_out = need_y;
+  }
+  if (need_o > b->cap_out) {
+    free_dev(b->d_out);
+    DDE_CUDA(cudaMalloc(&b->d_out, sizeof(double) * need_o));
+    b->cap_out = need_o;
+  }
+  b->have_steps = true;
+  return 0;
+}
+
+int dde_difeq_batch_run(dde_difeq_batch_t *b) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->have_steps || !b->have_y0) {
+    return fail("upload y0 and set steps before running");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  DDE_CUDA(cudaEventRecord(b->ev0, b->stream));
+  DDE_CUDA(cudaMemsetAsync(b->d_y_out, 0, sizeof(double) * b->n * b->nt * b->n_rep, b->stream));
+  if (b->n_out > 0) {
+    DDE_CUDA(cudaMemsetAsync(b->d_out, 0, sizeof(double) * b->n_out * b->nt * b->n_rep,
+                             b->stream));
+  }
+  DDE_CUDA(cudaMemsetAsync(b->d_next, 0, sizeof(unsigned long long), b->stream));
+  dde::DifeqArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_rep = (long long) b->n_rep;
+  a.n = (int) b->n;
+  a.n_out = (int) b->n_out;
+  a.n_parms = (int) b->n_parms;
+  a.parms_stride = (long long) b->parms_stride;
+  a.y0 = b->d_y0;
+  a.parms = b->d_parms;
+  a.steps = b->d_steps;
+  a.n_steps = (int) b->n_steps;
+  a.n_history = (int) b->n_history;
+  a.return_initial = b->return_initial;
+  a.y_out = b->d_y_out;
+  a.out = b->d_out;
+  a.code = b->d_code;
+  a.y_final = b->d_y_final;
+  a.ring = b->d_ring;
+  a.next_rep = b->d_next;
+  int launches = 0;
+  cudaError_t err = b->model->launch_difeq(a, b->device_sms, b->stream, &launches);
+  if (err != cudaSuccess) {
+    return fail("kernel launch failed for model '%s': %s", b->model->name,
+                cudaGetErrorString(err));
+  }
+  DDE_CUDA(cudaEventRecord(b->ev1, b->stream));
+  b->ran = true;
+  return 0;
+}
+
+int dde_difeq_batch_sync(dde_difeq_batch_t *b) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out, int32_t *code,
+                             double *y_final) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y_out) {
+    DDE_CUDA(cudaMemcpyAsync(y_out, b->d_y_out, sizeof(double) * b->n * b->nt * b->n_rep,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (out && b->n_out > 0) {
+    DDE_CUDA(cudaMemcpyAsync(out, b->d_out, sizeof(double) * b->n_out * b->nt * b->n_rep,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  if (code) {
+    DDE_CUDA(cudaMemcpyAsync(code, b->d_code, sizeof(int) * b->n_rep, cudaMemcpyDeviceToHost,
+                             b->stream));
+  }
+  if (y_final) {
+    DDE_CUDA(cudaMemcpyAsync(y_final, b->d_y_final, sizeof(double) * b->n * b->n_rep,
+                             cudaMemcpyDeviceToHost, b->stream));
+  }
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+double dde_difeq_batch_last_ms(dde_difeq_batch_t *b) {
+  if (b == nullptr || !b->ran) {
+    return -1.0;
+  }
+  cudaSetDevice(b->device);
+  if (cudaEventSynchronize(b->ev1) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  return (double) ms;
+}
+
+int dde_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep, const double *y0,
+                    const double *parms, size_t n_parms, size_t parms_stride,
+                    const uint64_t *steps, size_t n_steps, size_t n_history,
+                    int32_t return_initial, double *y_out, double *out, int32_t *code,
+                    double *y_final) {
+  if (y0 == nullptr) {
+    return fail("y0 must not be NULL");
+  }
+  if (n_parms > 0 && parms == nullptr) {
+    return fail("parms must not be NULL when n_parms > 0");
+  }
+  dde_difeq_batch_t *b = dde_difeq_batch_alloc(model, n, n_out, n_parms, n_rep, n_history);
+  if (b == nullptr) {
+    return 1;
+  }
+  int rc = dde_difeq_batch_upload(b, y0, parms, parms_stride);
+  rc = rc ? rc : dde_difeq_batch_set_steps(b, steps, n_steps, return_initial);
+  rc = rc ? rc : dde_difeq_batch_run(b);
+  rc = rc ? rc : dde_difeq_batch_download(b, y_out, out, code, y_final);
+  dde_difeq_batch_free(b);
+  return rc;
+}
+
+} /* extern "C" */

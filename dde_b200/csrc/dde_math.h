@@ -36,7 +36,7 @@
 
 #if defined(__CUDACC__)
 #define DDE_HD __host__ __device__ __forceinline__
-#define DDE_HD_NOINLINE __host__ __device__ __noinline__
+#define DDE_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define DDE_HD static inline
 #define DDE_HD_NOINLINE static

@@ -1,0 +1,138 @@
+/* dde_model.cuh -- what a dde_b200 model translation unit includes.
+ *
+ * A model file looks like the reference's (compare
+ * /root/reference/inst/examples/seir.c): model functions written against
+ * <dde/dde.h>, then -- where the reference has `#include <dde/dde.c>` once
+ * per shared library -- one DDE_REGISTER_* line per model, which
+ * instantiates the solver kernels around the (inlined) model functions and
+ * records a launcher under the model's name:
+ *
+ *     #include "dde_model.cuh"
+ *     #include "my_model.h"     // DDE_MODEL_FN void my_rhs(size_t n, double t, ...)
+ *     DDE_REGISTER_DOPRI(my_model, my_rhs, 3, 2)              // n = 3, 2 parms
+ *     DDE_REGISTER_DOPRI_OUTPUT(lorenz, lorenz, 3, 3, lorenz_output, 2)
+ *     DDE_REGISTER_DIFEQ(logistic, logistic, 0, -1, 0)        // any n
+ *
+ * n > 0 fixes the number of equations at compile time (state in registers);
+ * n = 0 compiles a runtime-n variant (n <= DDE_DYN_MAXN, state in local
+ * memory).  n_parms / n_out: >= 0 fixed, -1 runtime.
+ *
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA
+ * contraction -- bit-parity with the reference depends on it).
+ */
+#ifndef DDE_MODEL_CUH
+#define DDE_MODEL_CUH
+
+#include <math.h>
+#include <stddef.h>
+
+#include <dde/dde.h>
+
+#include "difeq_kernels.cuh"
+#include "dopri_kernels.cuh"
+#include "registry.h"
+
+/* Model sources call libm by name; give them the bit-reproducible versions
+   (see dde_math.h). */
+#define pow(x, y) dde_pow((x), (y))
+#define exp(x) dde_exp((x))
+
+namespace dde {
+
+template <class Kernel>
+inline int persistent_grid(Kernel kernel, long long n_items, int device_sms) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DDE_TPB, 0) != cudaSuccess ||
+      per_sm < 1) {
+    per_sm = 1;
+    (void) cudaGetLastError();
+  }
+  /* one resident wave: a multiple of the SM count, never more blocks than
+     there is work */
+  const long long wanted = (n_items + DDE_TPB - 1) / DDE_TPB;
+  const long long resident = (long long) device_sms * per_sm;
+  const long long grid = wanted < resident ? wanted : resident;
+  return (int) (grid < 1 ? 1 : grid);
+}
+
+template <class M>
+cudaError_t launch_dopri_model(int method, const DopriArgs &args, int device_sms,
+                               cudaStream_t stream, int *n_launches) {
+  if (method == 0) {
+    const int grid = persistent_grid(dopri_tpt_kernel<M, 0>, args.n_traj, device_sms);
+    dopri_tpt_kernel<M, 0><<<grid, DDE_TPB, 0, stream>>>(args);
+  } else {
+    const int grid = persistent_grid(dopri_tpt_kernel<M, 1>, args.n_traj, device_sms);
+    dopri_tpt_kernel<M, 1><<<grid, DDE_TPB, 0, stream>>>(args);
+  }
+  *n_launches = 1;
+  return cudaGetLastError();
+}
+
+template <class M>
+cudaError_t launch_difeq_model(const DifeqArgs &args, int device_sms, cudaStream_t stream,
+                               int *n_launches) {
+  const int grid = persistent_grid(difeq_tpt_kernel<M>, args.n_rep, device_sms);
+  difeq_tpt_kernel<M><<<grid, DDE_TPB, 0, stream>>>(args);
+  *n_launches = 1;
+  return cudaGetLastError();
+}
+
+} /* namespace dde */
+
+#define DDE_DYN_OR(v, dyn) ((v) > 0 ? 0 : (dyn))
+
+#define DDE_REGISTER_DOPRI_OUTPUT(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT)                      \
+  struct dde_dopri_model_##NAME {                                                              \
+    static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT);                             \
+    static __device__ __forceinline__ void deriv(size_t n, double t, const double *y,          \
+                                                 double *dydt, const void *data) {             \
+      DERIV(n, t, y, dydt, data);                                                              \
+    }                                                                                          \
+    static __device__ __forceinline__ void output(size_t n, double t, const double *y,         \
+                                                  size_t n_out, double *out,                   \
+                                                  const void *data) {                          \
+      OUTPUT(n, t, y, n_out, out, data);                                                       \
+    }                                                                                          \
+  };                                                                                           \
+  static dde::ModelDesc dde_dopri_desc_##NAME = {#NAME,                                        \
+                                                 1,                                            \
+                                                 (NEQ),                                        \
+                                                 (NPARMS),                                     \
+                                                 (NOUT),                                       \
+                                                 DDE_DYN_MAXN,                                 \
+                                                 DDE_DYN_MAXP,                                 \
+                                                 DDE_DYN_MAXOUT,                               \
+                                                 &dde::launch_dopri_model<dde_dopri_model_##NAME>, \
+                                                 nullptr,                                      \
+                                                 nullptr};                                     \
+  static const int dde_dopri_reg_##NAME = (dde_register_model(&dde_dopri_desc_##NAME), 0);
+
+#define DDE_NO_OUTPUT(n, t, y, n_out, out, data) ((void) 0)
+
+#define DDE_REGISTER_DOPRI(NAME, DERIV, NEQ, NPARMS) \
+  DDE_REGISTER_DOPRI_OUTPUT(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0)
+
+#define DDE_REGISTER_DIFEQ(NAME, TARGET, NEQ, NPARMS, NOUT)                                    \
+  struct dde_difeq_model_##NAME {                                                              \
+    static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT);                             \
+    static __device__ __forceinline__ void target(size_t n, size_t step, const double *y,      \
+                                                  double *y_next, size_t n_out, double *out,   \
+                                                  const void *data) {                          \
+      TARGET(n, step, y, y_next, n_out, out, data);                                            \
+    }                                                                                          \
+  };                                                                                           \
+  static dde::ModelDesc dde_difeq_desc_##NAME = {#NAME,                                        \
+                                                 2,                                            \
+                                                 (NEQ),                                        \
+                                                 (NPARMS),                                     \
+                                                 (NOUT),                                       \
+                                                 DDE_DYN_MAXN,                                 \
+                                                 DDE_DYN_MAXP,                                 \
+                                                 DDE_DYN_MAXOUT,                               \
+                                                 nullptr,                                      \
+                                                 &dde::launch_difeq_model<dde_difeq_model_##NAME>, \
+                                                 nullptr};                                     \
+  static const int dde_difeq_reg_##NAME = (dde_register_model(&dde_difeq_desc_##NAME), 0);
+
+#endif /* DDE_MODEL_CUH */

@@ -1,0 +1,213 @@
+/* difeq_kernels.cuh -- batched difference-equation iteration, one replicate
+ * per thread.
+ *
+ * Device restatement of difeq_run (/root/reference/src/difeq.c:127-258) and
+ * of the replicate loop around it (src/r_difeq.c:94-103) for n_rep
+ * independent replicates at once.  Each replicate has FRESH history state:
+ * the documented contract of difeq_replicate (R/difeq_replicate.R:1-4), not
+ * the reference's one-ring-for-all-replicates artefact (SURVEY.md finding 5).
+ *
+ * What is kept from the reference:
+ *   - the initial state is committed to the ring as the entry for steps[0]
+ *     before the first target() call (src/difeq.c:140-156), so yprev(step)
+ *     at offset 0 is the current state;
+ *   - yprev(step <= step0) is y0, any other miss is an error
+ *     (src/difeq.c:261-281) that ends the replicate (Rf_error there);
+ *   - rows are stored when step == steps[idx] (src/difeq.c:215-225);
+ *   - outputs computed by target(step = s, y(s)) belong to row s, hence the
+ *     one-iteration delay and the trailing target() call
+ *     (src/difeq.c:204-213,249-255).
+ * Ring entries are {step as double, y[n], out[n_out]} (src/difeq.c:31-37);
+ * the out block is NA-filled as src/difeq.c:146 does -- the reference's
+ * later writes into stale out slots are not observable through yprev or
+ * through the replicate results and are not reproduced.
+ *
+ * The per-step arithmetic is whatever the model does in FP64, compiled
+ * without contraction, so deterministic models are bit-exact.
+ */
+#ifndef DDE_DIFEQ_KERNELS_CUH
+#define DDE_DIFEQ_KERNELS_CUH
+
+#include "dopri_kernels.cuh"
+
+namespace dde {
+
+struct DifeqArgs {
+  long long n_rep;
+  int n, n_out, n_parms;
+  long long parms_stride;
+  const double *y0;                 /* [n x n_rep] */
+  const double *parms;
+  const unsigned long long *steps;  /* [n_steps], strictly increasing */
+  int n_steps;
+  int n_history, return_initial;
+  double *y_out;   /* [n x nt x n_rep] */
+  double *out;     /* [n_out x nt x n_rep] */
+  int *code;       /* [n_rep] */
+  double *y_final; /* [n x n_rep], obj->y1 (src/difeq.c:244) */
+  double *ring;    /* [n_rep][n_history][1 + n + n_out] */
+  unsigned long long *next_rep;
+};
+
+template <class M>
+__global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
+  constexpr int NC = M::N;
+  constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
+  constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
+  constexpr int OMAX = M::N_OUT > 0 ? M::N_OUT : (M::N_OUT == 0 ? 1 : DDE_DYN_MAXOUT);
+  const int n = NC > 0 ? NC : a.n;
+  const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
+  const int n_out = M::N_OUT == 0 ? 0 : a.n_out; /* 0 = output function not requested */
+  const int hl = 1 + n + n_out;
+  const int s = threadIdx.x;
+  const int cap = a.n_history;
+
+  if (threadIdx.x == 0) {
+    s_lag_u.sign = 1.0;
+    s_lag_u.cap = cap;
+    s_lag_u.n = n;
+    s_lag_u.hl = hl;
+    s_lag_u.order = 0;
+  }
+  __syncthreads();
+
+  const int n_steps = a.n_steps;
+  const int nt = a.return_initial ? n_steps : n_steps - 1;
+  const unsigned long long step_first = a.steps[0];
+  const unsigned long long step_last = a.steps[n_steps - 1];
+  const bool has_output = n_out > 0;
+
+  for (;;) {
+    const long long rep = (long long) atomicAdd(a.next_rep, 1ULL);
+    if (rep >= a.n_rep) {
+      break;
+    }
+    double p[PMAX];
+#pragma unroll
+    for (int i = 0; i < PMAX; ++i) {
+      if (i < n_parms) {
+        p[i] = a.parms[rep * a.parms_stride + i];
+      }
+    }
+    double y[NMAX], y_next[NMAX], o[OMAX];
+    const double *y0 = a.y0 + rep * n;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      y[i] = y0[i];
+    }
+    /* difeq_data_reset, src/difeq.c:74-105 (step checks run on the host) */
+    unsigned long long step = step_first;
+    int steps_idx = 1;
+    double *ring = a.ring + (size_t) rep * (size_t) cap * (size_t) hl;
+    s_ring[s] = ring;
+    s_y0[s] = y0;
+    s_step0[s] = (long long) step_first;
+    s_step[s] = (long long) step;
+    s_count[s] = 0;
+    s_head[s] = 0;
+    s_code[s] = 0;
+    s_error[s] = 0;
+
+    int head = 0;
+    unsigned count = 0;
+#define DDE_DIFEQ_COMMIT(yy)                                  \
+  do {                                                        \
+    if (cap > 0) {                                            \
+      double *dst = ring + (size_t) head * (size_t) hl;       \
+      dst[0] = (double) step; /* src/difeq.c:327-330 */       \
+      _Pragma("unroll") for (int i = 0; i < n; ++i) {         \
+        dst[1 + i] = (yy)[i];                                 \
+      }                                                       \
+      for (int i = 0; i < n_out; ++i) {                       \
+        dst[1 + n + i] = na_real();                           \
+      }                                                       \
+      head = head + 1 == cap ? 0 : head + 1;                  \
+      ++count;                                                \
+      s_head[s] = head;                                       \
+      s_count[s] = count;                                     \
+    }                                                         \
+  } while (0)
+
+    /* the initial state is the first entry, src/difeq.c:140-156 */
+    DDE_DIFEQ_COMMIT(y);
+
+    double *wy = a.y_out + (size_t) rep * (size_t) nt * (size_t) n;
+    double *wo = has_output ? a.out + (size_t) rep * (size_t) nt * (size_t) n_out : nullptr;
+    bool store_next_output = false;
+    if (a.return_initial) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        wy[i] = y[i];
+      }
+      wy += n;
+      store_next_output = true;
+    }
+
+    bool failed = false;
+    for (;;) {
+      s_step[s] = (long long) step;
+      M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
+      if (s_error[s]) {
+        failed = true; /* Rf_error in difeq_find_step, src/difeq.c:267-270 */
+        break;
+      }
+      ++step;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        y[i] = y_next[i];
+      }
+      if (has_output && store_next_output) {
+        /* `o` was computed from the previous y, whose row was just stored */
+#pragma unroll
+        for (int i = 0; i < OMAX; ++i) {
+          if (i < n_out) {
+            wo[i] = o[i];
+          }
+        }
+        wo += n_out;
+        store_next_output = false;
+      }
+      if (steps_idx < n_steps && step == a.steps[steps_idx]) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          wy[i] = y[i];
+        }
+        wy += n;
+        store_next_output = true;
+        ++steps_idx;
+      }
+      DDE_DIFEQ_COMMIT(y);
+      if (step == step_last) {
+        if (a.y_final != nullptr) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            a.y_final[rep * n + i] = y[i];
+          }
+        }
+        break;
+      }
+    }
+    if (!failed && has_output && store_next_output) {
+      /* trailing call for the outputs of the last stored row,
+         src/difeq.c:249-255 */
+      s_step[s] = (long long) step;
+      M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
+      if (s_error[s]) {
+        failed = true;
+      } else {
+#pragma unroll
+        for (int i = 0; i < OMAX; ++i) {
+          if (i < n_out) {
+            wo[i] = o[i];
+          }
+        }
+      }
+    }
+#undef DDE_DIFEQ_COMMIT
+    a.code[rep] = failed ? s_code[s] : 1; /* OK_COMPLETE */
+  }
+}
+
+} /* namespace dde */
+
+#endif /* DDE_DIFEQ_KERNELS_CUH */

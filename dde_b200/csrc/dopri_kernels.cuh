@@ -1,0 +1,685 @@
+/* dopri_kernels.cuh -- batched Dormand-Prince integrator, one trajectory per
+ * thread, state in registers.
+ *
+ * This is the device restatement of the reference's solver core for n_traj
+ * independent solver objects at once:
+ *   adaptive loop            /root/reference/src/dopri.c:291-514
+ *   reset                    src/dopri.c:138-219
+ *   controller / h_init      src/dopri.c:516-572
+ *   dopri5 step/error/dense  src/dopri_5.c:42-127
+ *   dop853 step/error/dense  src/dopri_853.c:159-380
+ *   stiffness test           src/dopri.c:668-693, dopri_5.c:129-140, dopri_853.c:382-394
+ * Every floating-point expression keeps the reference's operand order and is
+ * compiled without FMA contraction (-fmad=false), and pow() is dde_pow, so a
+ * trajectory takes bit-for-bit the same steps as the reference C solver
+ * (finding 1).  The reference's documented departures
+ * from Hairer's Fortran are reproduced on purpose.
+ *
+ * Design (B200): the whole solver object of src/dopri.h:55-161 lives in the
+ * thread's registers -- y, k1..k7 (dopri5) or k1..k10 (dop853) and the dense
+ * coefficients of the in-progress step -- so for small n the only HBM
+ * traffic is: y0/parms in, output rows out, ring commits, lag look-ups.
+ * The model's deriv() is inlined into the kernel (one translation unit,
+ * template on the model), which is what keeps y/dydt in registers despite
+ * the pointer-based model ABI.  Divergence: lanes run their own adaptive
+ * loops; the compiler-generated reconvergence point is the loop head, and
+ * lanes that finish early are refilled with the next trajectory from an
+ * atomic counter (persistent threads) so a warp's cost is the mean, not the
+ * max, of its lanes' step counts.
+ */
+#ifndef DDE_DOPRI_KERNELS_CUH
+#define DDE_DOPRI_KERNELS_CUH
+
+#include <float.h>
+
+#include "lag_ctx.cuh"
+#include "tableau.h"
+
+namespace dde {
+
+#ifndef DDE_DYN_MAXN
+#define DDE_DYN_MAXN 16 /* largest n of a model compiled with runtime n */
+#endif
+#ifndef DDE_DYN_MAXP
+#define DDE_DYN_MAXP 16
+#endif
+#ifndef DDE_DYN_MAXOUT
+#define DDE_DYN_MAXOUT 8
+#endif
+
+/* Kernel arguments: the per-batch constants of dopri_data plus array bases. */
+struct DopriArgs {
+  /* problem */
+  long long n_traj;
+  int n, n_out, n_parms;
+  long long parms_stride;
+  const double *y0;    /* [n x n_traj] */
+  const double *parms; /* [n_parms x n_traj] or one shared vector */
+  const double *times; /* [n_times] */
+  const double *tcrit; /* [n_tcrit] */
+  int n_times, n_tcrit, tcrit_idx0;
+  /* controls (src/dopri.h:133-146) */
+  double atol, rtol, step_size_min, step_size_max, step_size_initial;
+  unsigned long long step_max_n, stiff_check;
+  int n_history, step_size_min_allow, return_initial;
+  double sign; /* src/dopri.c:173 */
+  /* results */
+  double *y_out, *out;
+  int *stats, *code;
+  double *t_last, *step_size;
+  /* history */
+  double *ring;          /* [n_traj][n_history][order*n + 2] */
+  unsigned *ring_count;  /* [n_traj] entries committed (for export) */
+  /* work distribution: next trajectory index to hand out */
+  unsigned long long *next_traj;
+};
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+template <class M, int METHOD>
+__global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
+  constexpr int NC = M::N;
+  constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
+  constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
+  constexpr int OMAX = M::N_OUT > 0 ? M::N_OUT : (M::N_OUT == 0 ? 1 : DDE_DYN_MAXOUT);
+  constexpr int ORDER = METHOD == 0 ? 5 : 8;
+  const int n = NC > 0 ? NC : a.n;
+  const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
+  const int n_out = M::N_OUT == 0 ? 0 : a.n_out; /* 0 = output function not requested */
+  const int hl = ORDER * n + 2;
+  const int s = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    s_lag_u.sign = a.sign;
+    s_lag_u.cap = a.n_history;
+    s_lag_u.n = n;
+    s_lag_u.hl = hl;
+    s_lag_u.order = ORDER;
+  }
+  __syncthreads();
+
+  /* method constants, src/dopri.c:67-78 and :142-153 */
+  constexpr double step_factor_min = METHOD == 0 ? 0.2 : 0.333;
+  constexpr double step_factor_max = METHOD == 0 ? 10.0 : 6.0;
+  constexpr double step_beta = METHOD == 0 ? 0.04 : 0.0;
+  constexpr double step_factor_safe = 0.9;
+  const double step_constant = METHOD == 0 ? 0.2 - step_beta * 0.75 : 0.125 - step_beta * 0.2;
+  const double sign = a.sign;
+  const double atol = a.atol, rtol = a.rtol;
+  const int n_times = a.n_times;
+  const int nt = a.return_initial ? n_times : n_times - 1;
+  const double t_end = a.times[n_times - 1];
+
+  /* ---- per-lane solver object (src/dopri.h:55-161), in registers ---- */
+  long long traj = -1;
+  bool active = false; /* this lane holds a trajectory */
+  bool done = false;   /* ... whose integration has ended */
+  double p[PMAX];
+  double y[NMAX], k1[NMAX];
+  double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0, t_stop = t_end;
+  double step_size_exit = 0.0;
+  bool stop = false, last = false, reject = false;
+  int times_idx = 1, tcrit_idx = 0;
+  int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
+  unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
+  double *yo = nullptr, *oo = nullptr;
+
+#define DDE_EVAL(tt, yy, dd)                      \
+  do {                                            \
+    M::deriv((size_t) n, (tt), (yy), (dd), p);    \
+    ++n_eval;                                     \
+  } while (0)
+
+  /* One flat loop per lane.  Each trip is: [refill] -> one step attempt ->
+     [accept work] -> [retire].  The bracketed parts are the only divergent
+     regions and reconverge before the next attempt, so lanes of a warp
+     execute the expensive stage evaluations together even though each one
+     carries its own t, h and trajectory. */
+  for (;;) {
+    if (!active) {
+      /* persistent threads: take the next trajectory, or leave */
+      traj = (long long) atomicAdd(a.next_traj, 1ULL);
+      if (traj >= a.n_traj) {
+        break;
+      }
+      active = true;
+      done = false;
+#pragma unroll
+      for (int i = 0; i < PMAX; ++i) {
+        if (i < n_parms) {
+          p[i] = a.parms[traj * a.parms_stride + i];
+        }
+      }
+      const double *y0 = a.y0 + traj * n;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        y[i] = y0[i];
+      }
+      /* dopri_data_reset, src/dopri.c:138-219 (the time checks run once on
+         the host: times are shared by all trajectories) */
+      t = a.times[0];
+      times_idx = 1;
+      tcrit_idx = a.tcrit_idx0;
+      n_eval = n_step = n_accept = n_reject = 0;
+      stiff_n_stiff = stiff_n_nonstiff = 0;
+      s_ring[s] = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) hl;
+      s_y0[s] = y0;
+      s_t0[s] = sign * a.times[0];
+      s_count[s] = 0;
+      s_head[s] = 0;
+      s_hint[s] = 0;
+      s_code[s] = 0; /* NOT_SET */
+      s_error[s] = 0;
+
+      /* dopri_integrate prologue, src/dopri.c:300-339 */
+      fac_old = 1e-4;
+      stop = last = reject = false;
+      h_save = 0.0;
+      step_size_exit = a.step_size_initial;
+      t_stop = t_end;
+      if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
+        t_stop = a.tcrit[tcrit_idx];
+      }
+      yo = a.y_out + (size_t) traj * (size_t) nt * (size_t) n;
+      oo = n_out > 0 ? a.out + (size_t) traj * (size_t) nt * (size_t) n_out : nullptr;
+      if (a.return_initial) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          yo[i] = y[i];
+        }
+        yo += n;
+        if (n_out > 0) {
+          double o[OMAX];
+          M::output((size_t) n, a.times[0], y, (size_t) n_out, o, p);
+#pragma unroll
+          for (int i = 0; i < OMAX; ++i) {
+            if (i < n_out) {
+              oo[i] = o[i];
+            }
+          }
+          oo += n_out;
+        }
+      }
+      DDE_EVAL(t, y, k1);
+      bool finite0 = true;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        finite0 = finite0 && isfinite(k1[i]);
+      }
+      if (!finite0) {
+        s_code[s] = -8; /* DDE_ERR_NONFINITE_DERIV, src/dopri.c:331-336 */
+        done = true;
+      } else if (a.step_size_initial > 0.0) {
+        h = a.step_size_initial; /* src/dopri.c:528-530 */
+      } else {
+        /* dopri_h_init, src/dopri.c:527-572 */
+        double norm_f = 0.0, norm_y = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const double sk = atol + rtol * fabs(y[i]);
+          norm_f += sq(k1[i] / sk);
+          norm_y += sq(y[i] / sk);
+        }
+        h = (norm_f <= 1e-10 || norm_y <= 1e-10) ? 1e-6 : sqrt(norm_y / norm_f) * 0.01;
+        h = copysign(fmin(h, a.step_size_max), sign);
+        double f1[NMAX], ye[NMAX];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          ye[i] = y[i] + h * k1[i];
+        }
+        DDE_EVAL(t + h, ye, f1);
+        double der2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const double sk = atol + rtol * fabs(y[i]);
+          der2 += sq((f1[i] - k1[i]) / sk);
+        }
+        der2 = sqrt(der2) / h;
+        const double der12 = fmax(fabs(der2), sqrt(norm_f));
+        const double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3)
+                                           : dde_pow(0.01 / der12, 1.0 / ORDER);
+        h = fmin(fmin(100 * fabs(h), h1), a.step_size_max);
+        h = copysign(h, sign);
+      }
+    }
+
+    /* ---- one trip of the adaptive loop, src/dopri.c:343-510 ---- */
+    if (!done) {
+      do {
+        bool force_this_step = false;
+        if ((unsigned long long) n_step > a.step_max_n) {
+          s_error[s] = 1;
+          s_code[s] = -3; /* ERR_TOO_MANY_STEPS */
+          done = true;
+          break;
+        }
+        if (fabs(h) <= a.step_size_min) {
+          if (a.step_size_min_allow) {
+            h = copysign(a.step_size_min, sign);
+            force_this_step = true;
+          } else {
+            s_error[s] = 1;
+            s_code[s] = -4; /* ERR_STEP_SIZE_TOO_SMALL */
+            done = true;
+            break;
+          }
+        } else if (fabs(h) <= fabs(t) * DBL_EPSILON) {
+          s_error[s] = 1;
+          s_code[s] = -5; /* ERR_STEP_SIZE_VANISHED */
+          done = true;
+          break;
+        }
+        if ((t + 1.01 * h - t_stop) * sign > 0.0) {
+          h = t_stop - t;
+          stop = true;
+        }
+        if ((t + 1.01 * h - t_end) * sign > 0.0) {
+          h_save = h;
+          h = t_end - t;
+          last = true;
+        }
+        ++n_step;
+
+        /* stage storage: k1 is carried (FSAL); dopri5 uses k2..k6 and k7 as
+           its `ysti`; dop853 uses k2..k10 */
+        double k2[NMAX], k3[NMAX], k4[NMAX], k5[NMAX], k6[NMAX], k7[NMAX], k8[NMAX],
+            k9[NMAX], k10[NMAX], y1[NMAX];
+        double err;
+
+        if (METHOD == 0) {
+          /* dopri5_step, src/dopri_5.c:42-95 */
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * DP5_A21 * k1[i];
+          }
+          DDE_EVAL(t + DP5_C2 * h, y1, k2);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
+          }
+          DDE_EVAL(t + DP5_C3 * h, y1, k3);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
+          }
+          DDE_EVAL(t + DP5_C4 * h, y1, k4);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
+                                DP5_A54 * k4[i]);
+          }
+          DDE_EVAL(t + DP5_C5 * h, y1, k5);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            k7[i] = y[i] + h * (DP5_A61 * k1[i] + DP5_A62 * k2[i] + DP5_A63 * k3[i] +
+                                DP5_A64 * k4[i] + DP5_A65 * k5[i]);
+          }
+          const double t_next = t + h;
+          DDE_EVAL(t_next, k7, k6);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP5_A71 * k1[i] + DP5_A73 * k3[i] + DP5_A74 * k4[i] +
+                                DP5_A75 * k5[i] + DP5_A76 * k6[i]);
+          }
+          DDE_EVAL(t_next, y1, k2);
+          /* The reference also writes the fifth dense coefficient into the
+             ring head on every attempt (dopri_5.c:84-89) and overwrites k4
+             with the error combination (:91-94).  Only accepted steps read
+             the head, so here k4 is kept and that coefficient is formed on
+             acceptance from the same operands in the same order. */
+          if (s_error[s]) {
+            done = true; /* src/dopri.c:387-389 */
+            break;
+          }
+          /* dopri5_error, src/dopri_5.c:97-104 */
+          err = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double ke = h * (DP5_E1 * k1[i] + DP5_E3 * k3[i] + DP5_E4 * k4[i] +
+                                   DP5_E5 * k5[i] + DP5_E6 * k6[i] + DP5_E7 * k2[i]);
+            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
+            err += sq(ke / sk);
+          }
+          err = sqrt(err / (double) n);
+        } else {
+          /* dopri853_step, src/dopri_853.c:159-247 */
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * DP8_A21 * k1[i];
+          }
+          DDE_EVAL(t + DP8_C2 * h, y1, k2);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
+          }
+          DDE_EVAL(t + DP8_C3 * h, y1, k3);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
+          }
+          DDE_EVAL(t + DP8_C4 * h, y1, k4);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
+          }
+          DDE_EVAL(t + DP8_C5 * h, y1, k5);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
+          }
+          DDE_EVAL(t + DP8_C6 * h, y1, k6);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
+                                DP8_A76 * k6[i]);
+          }
+          DDE_EVAL(t + DP8_C7 * h, y1, k7);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
+                                DP8_A86 * k6[i] + DP8_A87 * k7[i]);
+          }
+          DDE_EVAL(t + DP8_C8 * h, y1, k8);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
+                                DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
+          }
+          DDE_EVAL(t + DP8_C9 * h, y1, k9);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A101 * k1[i] + DP8_A104 * k4[i] + DP8_A105 * k5[i] +
+                                DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
+                                DP8_A109 * k9[i]);
+          }
+          DDE_EVAL(t + DP8_C10 * h, y1, k10);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A111 * k1[i] + DP8_A114 * k4[i] + DP8_A115 * k5[i] +
+                                DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
+                                DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
+          }
+          DDE_EVAL(t + DP8_C11 * h, y1, k2);
+          const double t_next = t + h;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y1[i] = y[i] + h * (DP8_A121 * k1[i] + DP8_A124 * k4[i] + DP8_A125 * k5[i] +
+                                DP8_A126 * k6[i] + DP8_A127 * k7[i] + DP8_A128 * k8[i] +
+                                DP8_A129 * k9[i] + DP8_A1210 * k10[i] + DP8_A1211 * k2[i]);
+          }
+          DDE_EVAL(t_next, y1, k3);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            k4[i] = DP8_B1 * k1[i] + DP8_B6 * k6[i] + DP8_B7 * k7[i] + DP8_B8 * k8[i] +
+                    DP8_B9 * k9[i] + DP8_B10 * k10[i] + DP8_B11 * k2[i] + DP8_B12 * k3[i];
+            k5[i] = y[i] + h * k4[i];
+          }
+          if (s_error[s]) {
+            done = true; /* src/dopri.c:387-389 */
+            break;
+          }
+          /* dopri853_error, src/dopri_853.c:249-283: scaled by sign, not
+             |h|, guarded by deno < 0 */
+          err = 0.0;
+          double err2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(k5[i]));
+            double erri = k4[i] - DP8_BHH1 * k1[i] - DP8_BHH2 * k9[i] - DP8_BHH3 * k3[i];
+            err2 += sq(erri / sk);
+            erri = DP8_ER1 * k1[i] + DP8_ER6 * k6[i] + DP8_ER7 * k7[i] + DP8_ER8 * k8[i] +
+                   DP8_ER9 * k9[i] + DP8_ER10 * k10[i] + DP8_ER11 * k2[i] + DP8_ER12 * k3[i];
+            err += sq(erri / sk);
+          }
+          double deno = err + 0.01 * err2;
+          deno = deno < 0 ? 1.0 : deno;
+          err = sign * err * sqrt(1.0 / ((double) n * deno));
+        }
+
+        /* dopri_h_new, src/dopri.c:516-525 */
+        const double fac11 = dde_pow(err, step_constant);
+        /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
+        const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
+        double fac = fac11 / facb;
+        fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
+        double h_new = h / fac;
+        const bool accept = err <= 1;
+
+        if (accept || force_this_step) {
+          /* src/dopri.c:396-494 */
+          fac_old = fmax(err, 1e-4);
+          ++n_accept;
+          if (METHOD == 1) {
+            /* the redundant evaluation at the OLD time, src/dopri.c:400-403
+               (SURVEY.md A.1#2): it counts, and its lag look-ups can fail */
+            DDE_EVAL(t, k5, k4);
+          }
+          /* dopri_test_stiff, src/dopri.c:668-693 */
+          if (a.stiff_check != 0 &&
+              (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
+            double stnum = 0, stden = 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              if (METHOD == 0) { /* src/dopri_5.c:129-140 */
+                stnum += sq(k2[i] - k6[i]);
+                stden += sq(y1[i] - k7[i]);
+              } else { /* src/dopri_853.c:382-394 */
+                stnum += sq(k4[i] - k3[i]);
+                stden += sq(k5[i] - y1[i]);
+              }
+            }
+            const bool stiff =
+                stden > 0 && fabs(h) * sqrt(stnum / stden) > (METHOD == 0 ? 3.25 : 6.1);
+            bool give_up = false;
+            if (stiff) {
+              stiff_n_nonstiff = 0;
+              if (stiff_n_stiff++ >= 15) {
+                give_up = true;
+              }
+            } else if (stiff_n_stiff > 0) {
+              if (stiff_n_nonstiff++ >= 6) {
+                stiff_n_stiff = 0;
+              }
+            }
+            if (give_up) {
+              s_error[s] = 1;
+              s_code[s] = -7; /* ERR_STIFF */
+              done = true;
+              break;
+            }
+          }
+
+          /* dopri_save_history: the dense-output coefficients of this step,
+             i.e. the ring's head entry, kept in registers until committed */
+          double hd[ORDER * NMAX];
+          if (METHOD == 0) {
+            /* src/dopri_5.c:106-118 and :84-89 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const double ydiff = y1[i] - y[i];
+              const double bspl = h * k1[i] - ydiff;
+              hd[i] = y[i];
+              hd[n + i] = ydiff;
+              hd[2 * n + i] = bspl;
+              hd[3 * n + i] = -h * k2[i] + ydiff - bspl;
+              hd[4 * n + i] = h * (DP5_D1 * k1[i] + DP5_D3 * k3[i] + DP5_D4 * k4[i] +
+                                   DP5_D5 * k5[i] + DP5_D6 * k6[i] + DP5_D7 * k2[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              k1[i] = k2[i]; /* src/dopri.c:416-417 */
+              y[i] = y1[i];
+            }
+          } else {
+            /* src/dopri_853.c:285-367 */
+            DDE_EVAL(t + h, k5, k4);
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const double ydiff = k5[i] - y[i];
+              const double bspl = h * k1[i] - ydiff;
+              hd[i] = y[i];
+              hd[n + i] = ydiff;
+              hd[2 * n + i] = bspl;
+              hd[3 * n + i] = ydiff - h * k4[i] - bspl;
+              hd[4 * n + i] = DP8_D41 * k1[i] + DP8_D46 * k6[i] + DP8_D47 * k7[i] +
+                              DP8_D48 * k8[i] + DP8_D49 * k9[i] + DP8_D410 * k10[i] +
+                              DP8_D411 * k2[i] + DP8_D412 * k3[i];
+              hd[5 * n + i] = DP8_D51 * k1[i] + DP8_D56 * k6[i] + DP8_D57 * k7[i] +
+                              DP8_D58 * k8[i] + DP8_D59 * k9[i] + DP8_D510 * k10[i] +
+                              DP8_D511 * k2[i] + DP8_D512 * k3[i];
+              hd[6 * n + i] = DP8_D61 * k1[i] + DP8_D66 * k6[i] + DP8_D67 * k7[i] +
+                              DP8_D68 * k8[i] + DP8_D69 * k9[i] + DP8_D610 * k10[i] +
+                              DP8_D611 * k2[i] + DP8_D612 * k3[i];
+              hd[7 * n + i] = DP8_D71 * k1[i] + DP8_D76 * k6[i] + DP8_D77 * k7[i] +
+                              DP8_D78 * k8[i] + DP8_D79 * k9[i] + DP8_D710 * k10[i] +
+                              DP8_D711 * k2[i] + DP8_D712 * k3[i];
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              y1[i] = y[i] + h * (DP8_A141 * k1[i] + DP8_A147 * k7[i] + DP8_A148 * k8[i] +
+                                  DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
+                                  DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
+            }
+            DDE_EVAL(t + DP8_C14 * h, y1, k10);
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              y1[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
+                                  DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
+                                  DP8_A1513 * k4[i] + DP8_A1514 * k10[i]);
+            }
+            DDE_EVAL(t + DP8_C15 * h, y1, k2);
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              y1[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
+                                  DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
+                                  DP8_A1614 * k10[i] + DP8_A1615 * k2[i]);
+            }
+            DDE_EVAL(t + DP8_C16 * h, y1, k3);
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              hd[4 * n + i] = h * (hd[4 * n + i] + DP8_D413 * k4[i] + DP8_D414 * k10[i] +
+                                   DP8_D415 * k2[i] + DP8_D416 * k3[i]);
+              hd[5 * n + i] = h * (hd[5 * n + i] + DP8_D513 * k4[i] + DP8_D514 * k10[i] +
+                                   DP8_D515 * k2[i] + DP8_D516 * k3[i]);
+              hd[6 * n + i] = h * (hd[6 * n + i] + DP8_D613 * k4[i] + DP8_D614 * k10[i] +
+                                   DP8_D615 * k2[i] + DP8_D616 * k3[i]);
+              hd[7 * n + i] = h * (hd[7 * n + i] + DP8_D713 * k4[i] + DP8_D714 * k10[i] +
+                                   DP8_D715 * k2[i] + DP8_D716 * k3[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              k1[i] = k4[i]; /* src/dopri.c:420-421 */
+              y[i] = k5[i];
+            }
+          }
+          const double t_old = t;
+          t += h;
+
+          /* output rows, src/dopri.c:437-456: interpolate from the head */
+          for (;;) {
+            if (times_idx >= n_times) {
+              break;
+            }
+            const double tq = a.times[times_idx];
+            if (!(last || sign * tq <= sign * t)) {
+              break;
+            }
+            const double theta = (tq - t_old) / h;
+            const double theta1 = 1 - theta;
+            double row[NMAX];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
+                                   : interp853(n, theta, theta1, hd + i);
+              yo[i] = row[i];
+            }
+            if (n_out > 0) {
+              double o[OMAX];
+              M::output((size_t) n, tq, row, (size_t) n_out, o, p);
+#pragma unroll
+              for (int i = 0; i < OMAX; ++i) {
+                if (i < n_out) {
+                  oo[i] = o[i];
+                }
+              }
+              oo += n_out;
+            }
+            yo += n;
+            ++times_idx;
+          }
+
+          /* ring_buffer_head_advance, src/dopri.c:460: commit to HBM */
+          if (a.n_history > 0) {
+            int head = s_head[s];
+            double *dst = s_ring[s] + (size_t) head * (size_t) hl;
+#pragma unroll
+            for (int i = 0; i < ORDER * n; ++i) {
+              dst[i] = hd[i];
+            }
+            dst[ORDER * n] = t_old;
+            dst[ORDER * n + 1] = h;
+            head = head + 1 == a.n_history ? 0 : head + 1;
+            s_head[s] = head;
+            s_count[s] = s_count[s] + 1;
+          }
+
+          if (last) {
+            step_size_exit = h_save; /* src/dopri.c:463 */
+            s_code[s] = 1;           /* OK_COMPLETE */
+            done = true;
+            break;
+          }
+          if (fabs(h_new) >= a.step_size_max) {
+            h_new = copysign(a.step_size_max, sign);
+          }
+          if (reject) {
+            h_new = copysign(fmin(fabs(h_new), fabs(h)), sign);
+            reject = false;
+          }
+          if (stop) {
+            /* critical times, src/dopri.c:476-491 */
+            while (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] <= sign * t) {
+              ++tcrit_idx;
+            }
+            if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
+              t_stop = a.tcrit[tcrit_idx];
+            } else {
+              t_stop = t_end;
+            }
+            stop = false;
+          } else {
+            h = h_new;
+          }
+        } else {
+          /* rejected, src/dopri.c:495-509 */
+          h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);
+          reject = true;
+          if (n_accept >= 1) {
+            ++n_reject;
+          }
+          last = false;
+          stop = false;
+          h = h_new;
+        }
+      } while (0);
+    }
+
+    if (done) {
+      /* retire: statistics as r_dopri_cleanup reads them, src/r_dopri.c:412-428 */
+      a.stats[4 * traj + 0] = n_eval;
+      a.stats[4 * traj + 1] = n_step;
+      a.stats[4 * traj + 2] = n_accept;
+      a.stats[4 * traj + 3] = n_reject;
+      a.code[traj] = s_code[s];
+      a.t_last[traj] = t;
+      a.step_size[traj] = step_size_exit;
+      a.ring_count[traj] = s_count[s];
+      active = false;
+    }
+  }
+#undef DDE_EVAL
+}
+
+} /* namespace dde */
+
+#endif /* DDE_DOPRI_KERNELS_CUH */

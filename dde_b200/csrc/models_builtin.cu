@@ -1,0 +1,32 @@
+/* models_builtin.cu -- the models compiled into libdde_b200.so.
+ *
+ * The same sources (dde_b200/models/) are compiled as plain C against
+ * the reference solver for the oracle, so host and device run
+ * character-identical model code.  These are the reference's own fixture
+ * models restated (see each file's header) plus the BASELINE.json workloads.
+ */
+#include "dde_model.cuh"
+
+#include "../models/difeq_models.h"
+#include "../models/growth.h"
+#include "../models/lorenz.h"
+#include "../models/mackey_glass.h"
+#include "../models/rossler.h"
+#include "../models/seir.h"
+
+/*                         name            deriv           n  n_parms  output        n_out */
+DDE_REGISTER_DOPRI_OUTPUT(lorenz,         lorenz,         3, 3,       lorenz_output, 2)
+DDE_REGISTER_DOPRI(       rossler,        rossler,        3, 3)
+DDE_REGISTER_DOPRI(       mackey_glass,   mackey_glass,   1, 3)
+DDE_REGISTER_DOPRI_OUTPUT(seir,           seir,           4, -1,      seir_output,   1)
+DDE_REGISTER_DOPRI_OUTPUT(seir_int,       seir_int,       4, -1,      seir_output,   1)
+DDE_REGISTER_DOPRI(       exponential,    exponential,    0, -1)
+DDE_REGISTER_DOPRI(       linear,         linear,         0, -1)
+DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
+
+/*                  name       target     n  n_parms n_out */
+DDE_REGISTER_DIFEQ(logistic,  logistic,  0, -1,     0)
+DDE_REGISTER_DIFEQ(additive,  additive,  0, -1,     -1)
+DDE_REGISTER_DIFEQ(fibonacci, fibonacci, 5, -1,     0)
+DDE_REGISTER_DIFEQ(fib_out,   fib_out,   1, -1,     1)
+DDE_REGISTER_DIFEQ(sir_delay, sir_delay, 3, 2,      0)

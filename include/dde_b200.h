@@ -230,6 +230,14 @@ int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
                              int32_t *code, double *y_final);
 double dde_difeq_batch_last_ms(dde_difeq_batch_t *b);
 
+/* ---- host memory ------------------------------------------------------------ */
+
+/* Page-locked host buffers (cudaHostAlloc) so the upload/download calls above
+ * are true asynchronous DMA.  Ordinary malloc'ed / R-owned memory works too,
+ * through a staging copy. */
+void *dde_host_alloc(size_t bytes);
+void dde_host_free(void *p);
+
 /* ---- math ---------------------------------------------------------------- */
 
 /* The library's pow/exp, bit-identical restatements of glibc 2.39's

@@ -1,0 +1,261 @@
+"""GPU parity: the CUDA path through the C-ABI against the CPU checkers
+(oracle/_ref = the unmodified reference; oracle/liboracle.so = the C
+restatement) on identical inputs.  Bar: bit-exact outputs, identical
+per-trajectory statistics and return codes."""
+import numpy as np
+import pytest
+
+import dde_b200
+from dde_b200 import workloads
+from oracle import pyoracle
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def check_dopri(backend, model, y, times, parms, n_out=0, tcrit=None, **kw):
+    got = dde_b200.dopri_batch(y, times, model, parms, n_out=n_out, tcrit=tcrit, **kw)
+    want = pyoracle.dopri_batch(backend, model, y, times, parms, n_out=n_out, tcrit=tcrit, **kw)
+    np.testing.assert_array_equal(got.code, want.code)
+    np.testing.assert_array_equal(got.statistics, want.statistics)
+    assert_bits_equal(got.t_last, want.t_last, "t_last")
+    assert_bits_equal(got.step_size, want.step_size, "step_size")
+    assert_bits_equal(got.y, want.y, "y")
+    if n_out:
+        assert_bits_equal(got.output, want.output, "output")
+    return got, want
+
+
+def test_c1_lorenz_single(backend):
+    # BASELINE.json configs[0]; SURVEY.md A.4: 4565 steps / 4365 acc / 200 rej / 27392 evals
+    got, _ = check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], np.linspace(0, 100, 1001),
+                         [10.0, 28.0, 8.0 / 3.0])
+    assert got.statistics[0].tolist() == [27392, 4565, 4365, 200]
+    assert got.code[0] == 1
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dopri853"])
+def test_lorenz_output_function(backend, method):
+    check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0], [1.0, 1.0, 1.0]], np.linspace(0, 5, 51),
+                [10.0, 28.0, 8.0 / 3.0], n_out=2, method=method)
+
+
+@pytest.mark.parametrize("return_initial", [True, False])
+def test_c3_sweeps(backend, return_initial):
+    for gen in (workloads.lorenz_sweep, workloads.rossler_sweep):
+        model, y0, parms, times, kw = gen(1024, n_times=101)
+        kw["return_initial"] = return_initial
+        check_dopri(backend, model, y0, times, parms, **kw)
+
+
+def test_c2_mackey_glass(backend):
+    model, y0, parms, times, kw = workloads.mackey_glass(4096)
+    got, want = check_dopri(backend, model, y0, times, parms, **kw)
+    # the failing trajectories are part of parity
+    assert (got.code != 1).sum() > 0
+
+
+def test_mackey_glass_known_answer(backend):
+    # 173 steps / 114 acc / 59 rej / 2475 evals, y(500) = 1.059911058006217
+    got, _ = check_dopri(backend, "mackey_glass", [[1.2]], np.linspace(0, 500, 11),
+                         [0.2, 0.1, 10.0], method="dopri853", n_history=1000)
+    assert got.statistics[0].tolist() == [2475, 173, 114, 59]
+    assert got.y[0, -1, 0] == 1.059911058006217
+
+
+@pytest.mark.parametrize("model", ["seir", "seir_int"])
+@pytest.mark.parametrize("method,steps", [("dopri5", [500, 83, 74, 9]), ("dopri853", None)])
+def test_seir(backend, model, method, steps):
+    # SURVEY.md A.4 KAT; seir == seir_int is pinned by tests/testthat/test-dde.R:272-283
+    y0 = [[1e7 - 1, 0.0, 1.0, 0.0]]
+    got, _ = check_dopri(backend, model, y0, np.linspace(0, 30, 301), None, n_out=1, method=method,
+                         rtol=1e-7, atol=1e-7, n_history=1000)
+    if steps:
+        assert got.statistics[0].tolist() == steps
+
+
+def test_seir_history_underflow(backend):
+    # tests/testthat/test-dde.R:266-270: n_history = 2 -> "did not find time in history"
+    got, _ = check_dopri(backend, "seir", [[1e7 - 1, 0.0, 1.0, 0.0]], np.linspace(0, 30, 301), None,
+                         rtol=1e-7, atol=1e-7, n_history=2)
+    assert got.code[0] == -6
+    assert "did not find time in history" in got.message(0)
+
+
+def test_ylag_without_history(backend):
+    # tests/testthat/test-dde.R:285-295
+    got, _ = check_dopri(backend, "seir", [[1e7 - 1, 0.0, 1.0, 0.0]], np.linspace(0, 30, 31), None)
+    assert got.code[0] == -6
+    assert got.message(0) == "Integration failure: can't use ylag in model with no history"
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dopri853"])
+def test_growth_models_runtime_n(backend, method):
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 5):
+        y0 = rng.uniform(0.5, 2.0, size=(7, n))
+        r = rng.uniform(0.1, 1.0, size=(7, n))
+        check_dopri(backend, "exponential", y0, np.linspace(0, 3, 13), r, method=method)
+        check_dopri(backend, "linear", y0, np.linspace(0, 3, 13), r, method=method)
+        check_dopri(backend, "delayed_growth", y0, np.linspace(0, 3, 13), r, method=method,
+                    n_history=200)
+
+
+def test_negative_time(backend):
+    # tests/testthat/test-ode.R:511-591 (dopri5); the dop853 backward quirk is
+    # SURVEY.md A.1#1 and must be reproduced too
+    y0 = [[1.0, 2.0]]
+    r = [[0.5, 0.25]]
+    check_dopri(backend, "exponential", y0, -np.linspace(0, 2, 9), r, method="dopri5")
+    got, _ = check_dopri(backend, "exponential", y0, -np.linspace(0, 2, 9), r, method="dopri853")
+    assert got.code[0] == -4
+
+
+def test_critical_times(backend):
+    check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], np.linspace(0, 2, 21), [10.0, 28.0, 8.0 / 3.0],
+                tcrit=[0.55, 1.0, 1.25, 7.0])
+    check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], np.linspace(0, 2, 21), [10.0, 28.0, 8.0 / 3.0],
+                tcrit=[-1.0, 0.0, 0.3], method="dopri853")
+
+
+def test_controls(backend):
+    lor = ("lorenz", [[10.0, 1.0, 1.0]], np.linspace(0, 3, 31), [10.0, 28.0, 8.0 / 3.0])
+    # n_eval drops by exactly 1 with step_size_initial (tests/testthat/test-ode.R:398-404)
+    a, _ = check_dopri(backend, *lor)
+    b, _ = check_dopri(backend, *lor, step_size_initial=1e-3)
+    assert b.statistics[0, 0] < a.statistics[0, 0] + 100
+    got, _ = check_dopri(backend, *lor, step_max_n=10)
+    assert got.code[0] == -3
+    check_dopri(backend, *lor, step_size_max=0.01)
+    got, _ = check_dopri(backend, *lor, step_size_min=0.05)
+    assert got.code[0] == -4
+    check_dopri(backend, *lor, step_size_min=0.05, step_size_min_allow=True)
+    check_dopri(backend, *lor, rtol=1e-9, atol=1e-11, method="dopri853")
+    for method in ("dopri5", "dopri853"):
+        check_dopri(backend, *lor, stiff_check=1, method=method)
+        # a stiff problem trips the detector: y' = -r y with huge r
+        got, _ = check_dopri(backend, "exponential", [[1.0]], [0.0, 10.0], [[1e5]], stiff_check=1,
+                             method=method)
+        assert got.code[0] == -7
+
+
+def test_time_validation(backend):
+    got, _ = check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], [0.0, 1.0, 0.0], [10.0, 28.0, 2.0])
+    assert got.code[0] == -1
+    got, _ = check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], [0.0, 2.0, 1.0, 3.0], [10.0, 28.0, 2.0])
+    assert got.code[0] == -2
+    # duplicated times are allowed (tests/testthat/test-ode.R:23-28)
+    check_dopri(backend, "lorenz", [[10.0, 1.0, 1.0]], [0.0, 0.5, 0.5, 1.0, 1.0], [10.0, 28.0, 2.0])
+
+
+def test_nonfinite_initial_derivative(backend):
+    got, _ = check_dopri(backend, "exponential", [[np.inf, 1.0]], [0.0, 1.0], [[1.0, 1.0]])
+    assert got.code[0] == -8
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dopri853"])
+def test_history_and_interpolate(backend, method):
+    # tests/testthat/test-ode.R:50-59: history has one entry per accepted step;
+    # dense output from the history equals direct output
+    y0 = [10.0, 1.0, 1.0]
+    p = [10.0, 28.0, 8.0 / 3.0]
+    times = np.linspace(0, 2, 41)
+    res = dde_b200.dopri(y0, times, "lorenz", p, method=method, n_history=1000,
+                         return_statistics=True)
+    want = pyoracle.dopri_history(backend, "lorenz", y0, times, p, method=method, n_history=1000)
+    assert res.history.shape == want.history.shape
+    assert res.history.shape[0] == res.statistics["n_accept"]
+    assert_bits_equal(res.history, want.history, "history")
+    assert_bits_equal(np.asarray(res)[:, 1:], want.y, "y")
+    dense = dde_b200.dopri_interpolate(res, times)
+    # R's dopri_interpolate uses the entry with t_entry <= t (findInterval),
+    # the solver the step that crossed t: equal to 1e-10 (test-ode.R:56-59)
+    np.testing.assert_allclose(dense, want.y, rtol=1e-10, atol=1e-12)
+    with pytest.raises(dde_b200.DdeError, match="outside of range"):
+        dde_b200.dopri_interpolate(res, [2.5])
+
+
+def test_ring_overwrite_history(backend):
+    # overwrite policy: the ring keeps the newest n_history entries, oldest first
+    y0 = [10.0, 1.0, 1.0]
+    p = [10.0, 28.0, 8.0 / 3.0]
+    times = np.linspace(0, 2, 5)
+    res = dde_b200.dopri(y0, times, "lorenz", p, n_history=7)
+    want = pyoracle.dopri_history(backend, "lorenz", y0, times, p, n_history=7)
+    assert res.history.shape[0] == 7
+    assert_bits_equal(res.history, want.history, "history")
+
+
+# ---- difeq -------------------------------------------------------------------
+
+
+def check_difeq(backend, model, y, steps, parms, n_out=0, n_history=0, return_initial=True):
+    y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    st = np.asarray(steps, dtype=np.uint64)
+    b = dde_b200.DifeqBatch(model, y.shape[1], y.shape[0], n_parms=0 if parms is None else
+                            np.atleast_2d(parms).shape[1], n_out=n_out, n_history=n_history)
+    pa = None if parms is None else np.ascontiguousarray(np.atleast_2d(parms), dtype=np.float64)
+    shared = pa is not None and pa.shape[0] == 1 and y.shape[0] > 1
+    b.upload(np.ascontiguousarray(y), pa, shared_parms=shared)
+    b.set_steps(st, return_initial)
+    b.run()
+    y_out, out, code, y_final = b.download()
+    b.close()
+    want = pyoracle.difeq_batch(backend, model, y, st, None if pa is None else
+                                (pa[0] if shared else pa), n_out=n_out, n_history=n_history,
+                                return_initial=return_initial)
+    np.testing.assert_array_equal(code, want.code)
+    assert_bits_equal(y_out, want.y, "y")
+    ok = want.code == 1
+    assert_bits_equal(y_final[ok], want.y_final[ok], "y_final")
+    if n_out:
+        assert_bits_equal(out, want.output, "output")
+    return y_out, out, code
+
+
+def test_difeq_logistic(backend):
+    # tests/testthat/test-difeq.R:222-233: r = 1.5, y0 = 0.1, 20 steps
+    y, _, _ = check_difeq(backend, "logistic", [[0.1]], np.arange(21), [[1.5]])
+    ref = [0.1]
+    for _ in range(20):
+        ref.append(1.5 * ref[-1] * (1 - ref[-1]))
+    np.testing.assert_array_equal(y[0, :, 0], np.array(ref))
+    rng = np.random.default_rng(3)
+    check_difeq(backend, "logistic", rng.uniform(0.1, 0.9, (33, 4)), [0, 5, 6, 50],
+                rng.uniform(1.0, 3.9, (33, 4)), return_initial=False)
+
+
+def test_difeq_additive_outputs(backend):
+    # tests/testthat/test-difeq.R:13-50: y + p, with outputs paired to their row
+    for hist in (0, 8):
+        for ri in (True, False):
+            check_difeq(backend, "additive", [[1.0, 2.0, 3.0]], np.arange(11), [[1.0, 2.0, 3.0]],
+                        n_out=2, n_history=hist, return_initial=ri)
+            check_difeq(backend, "additive", [[1.0, 2.0, 3.0]], [2, 5, 6, 11], [[1.0, 2.0, 3.0]],
+                        n_out=2, n_history=hist, return_initial=ri)
+
+
+def test_difeq_fibonacci(backend):
+    # tests/testthat/test-difeq-delay.R:3-24: 1 2 3 5 8 ... 144 with n_history = 2
+    y, _, _ = check_difeq(backend, "fibonacci", [[1.0] * 5], np.arange(11), None, n_history=2)
+    assert y[0, :, 0].tolist() == [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144]
+    y, out, _ = check_difeq(backend, "fib_out", [[1.0]], np.arange(11), None, n_out=1, n_history=2)
+    assert y[0, :, 0].tolist() == [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144]
+    assert out[0, :, 0].tolist() == [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89]
+
+
+def test_difeq_history_miss(backend):
+    # the lag reaches further back than the ring holds: src/difeq.c:267-270
+    model, y0, parms, steps, kw = workloads.sir_delay(4, n_steps=100)
+    _, _, code = check_difeq(backend, model, y0, steps, parms, n_history=8,
+                             return_initial=kw["return_initial"])
+    assert (code == -9).all()
+
+
+def test_c4_delayed_sir(backend):
+    model, y0, parms, steps, kw = workloads.sir_delay(2048, n_steps=2000)
+    check_difeq(backend, model, y0, steps, parms, **kw)
+    # every replicate equals an independent difeq() run (R/difeq_replicate.R:1-4)
+    single = dde_b200.difeq(y0[5], [0, 2000], model, parms[5], n_history=16)
+    many = dde_b200.difeq_replicate(2048, y0, [0, 2000], model, parms, n_history=16)
+    assert_bits_equal(np.asarray(single), np.asarray(many)[:, :, 5], "replicate slice")
