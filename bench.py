@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Mackey-Glass DDE trajectories/sec.
+
+Workload (BASELINE.json configs[1]): 1,048,576
+Mackey-Glass trajectories (tau = 17) per GPU, random (beta, gamma, n, y0) from
+the fixed splitmix64 stream, dop853, rtol = atol = 1e-6, n_history = 64, 11
+output times on [0, 500].  One "step" = one pass of the hot path over that
+batch (every trajectory integrated from t = 0 to t = 500).
+
+  value  trajectories/s, whole job, inputs already resident in HBM, timed with
+         CUDA events on the launching stream, max over ranks.
+  e2e    the same metric through the reference-facing C-ABI with HOST
+         (pinned) buffers: per step H2D of y0/parms, the solve, and D2H of
+         y_out, statistics, codes, t_last, step_size, wall clock between
+         device synchronisations.
+  --impl reference   the reference's own CPU code (oracle/_ref: unmodified
+         src/dopri*.c, one forked process per host core) on a bounded sample
+         of the same workload.
+
+Multi-GPU: trajectories are independent, so ranks take disjoint slices of the
+parameter stream (weak scaling, no collective on the data path); torch
+distributed is used only for the barrier and the max-over-ranks of the time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_TRAJ_PER_GPU = 1 << 20
+F_POW = 43          # FP64 instructions of dde_pow's main path
+F_RHS_MG = 6 + 17 + F_POW  # model 6, lag theta + 853 Horner 3 + 14, pow
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-traj", type=int, default=N_TRAJ_PER_GPU, help="trajectories per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="trajectories in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": the upper half of the samples (idle gaps between steps drop the clock)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_work(stats, n=1, n_parms=3, n_lags=1, n_lag_idx=1, nt=11, order=8):
+    """Per-batch algorithmic FLOPs and bytes from the per-trajectory statistics
+    (SURVEY.md section 8d, dop853 row)."""
+    E = stats[:, 0].astype(np.float64)
+    S = stats[:, 1].astype(np.float64)
+    A = stats[:, 2].astype(np.float64)
+    T = float(nt)
+    flops = n * (158.0 * S + 153.0 * A + 14.0 * T) + 3.0 * T + E * F_RHS_MG + S * (F_POW + 12.0)
+    hist = 8.0 * (order * n + 2) * A + 8.0 * (order * n_lag_idx + 2) * S * n_lags
+    bytes_ = 8.0 * (n + n_parms) + 8.0 * n * T + hist + 4.0 * 5 + 8.0 * 2
+    return float(flops.sum()), float(bytes_.sum())
+
+
+def cpu_reference_run(n_sample, first, n_proc):
+    """Time the unmodified reference on `n_sample` trajectories of the workload."""
+    from dde_b200 import workloads
+    from oracle import pyoracle
+    backend = "ref" if pyoracle.available("ref") else "oracle"
+    model, y0, parms, times, kw = workloads.mackey_glass(n_sample, first=first)
+    r = pyoracle.dopri_batch(backend, model, y0, times, parms, n_proc=n_proc if backend == "ref"
+                             else 0, want_y=True, **kw)
+    return backend, r
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    # ~1.5-3 k trajectories/s/core: keep each step to a few seconds
+    n_sample = args.cpu_sample or max(2048, 1024 * cores)
+    times_s = []
+    backend = "ref"
+    for i in range(args.warmup + args.steps):
+        backend, r = cpu_reference_run(n_sample, first=0, n_proc=cores)
+        if i >= args.warmup:
+            times_s.append(r.seconds)
+    total = float(np.sum(times_s))
+    value = n_sample * len(times_s) / total
+    kind = "reference" if backend == "ref" else "port"
+    sample = ("first %d trajectories of the 1,048,576-trajectory Mackey-Glass batch per step, "
+              "%s, %d forked processes" % (n_sample, "unmodified reference C (oracle/_ref)"
+                                           if backend == "ref" else "oracle port", cores))
+    line = {
+        "impl": "reference", "metric": "Mackey-Glass DDE trajectories/sec", "value": value,
+        "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times_s), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "mackey_glass_dop853_tau17 (BASELINE.json configs[1])",
+                   "n_traj_per_step": n_sample, "rtol": 1e-6, "atol": 1e-6, "n_history": 64,
+                   "times": "0,50,...,500"},
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import dde_b200
+    from dde_b200 import workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dde_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_traj = args.n_traj
+    model, y0, parms, times, kw = workloads.mackey_glass(n_traj, first=rank * n_traj)
+    nt = times.shape[0]
+
+    # pinned host buffers: what a caller of the C-ABI hands over / gets back
+    h_y0 = torch.from_numpy(y0).pin_memory()
+    h_parms = torch.from_numpy(parms).pin_memory()
+    h_y = torch.empty((n_traj, nt, 1), dtype=torch.float64).pin_memory()
+    h_stats = torch.empty((n_traj, 4), dtype=torch.int32).pin_memory()
+    h_code = torch.empty((n_traj,), dtype=torch.int32).pin_memory()
+    h_t = torch.empty((n_traj,), dtype=torch.float64).pin_memory()
+    h_h = torch.empty((n_traj,), dtype=torch.float64).pin_memory()
+    h2d = h_y0.numel() * 8 + h_parms.numel() * 8
+    d2h = h_y.numel() * 8 + h_stats.numel() * 4 + h_code.numel() * 4 + h_t.numel() * 8 + h_h.numel() * 8
+
+    b = dde_b200.DopriBatch(model, 1, n_traj, n_parms=3, **kw)
+    b.set_times(times)
+    b.upload(h_y0, h_parms)
+    b.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: warm-up, then K timed steps -------------------------
+    for _ in range(args.warmup):
+        b.run()
+    b.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.run()
+        b.sync()
+        kernel_ms.append(b.last_ms())  # CUDA events on the handle's stream
+    t_wall = time.perf_counter() - t0
+    launches = args.steps * b.last_launches()
+    barrier()
+    dev_ms = float(np.sum(kernel_ms))
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t_dev.item())
+
+    # ---- end to end through the C-ABI with host buffers ------------------------
+    for _ in range(1):
+        b.upload(h_y0, h_parms)
+        b.run()
+        b.download_into(h_y, None, h_stats, h_code, h_t, h_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.upload(h_y0, h_parms)
+        b.run()
+        b.download_into(h_y, None, h_stats, h_code, h_t, h_h)  # synchronises
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s_max = float(t_e2e.item())
+
+    stats = h_stats.numpy()
+    code = h_code.numpy()
+    acc = torch.tensor([float(stats[:, 2].sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        total_traj = n_traj * world
+        value = total_traj * args.steps / (dev_ms_max * 1e-3)
+        e2e_value = total_traj * args.steps / e2e_s_max
+        flops, bytes_ = algorithmic_work(stats, nt=nt)
+        ms_kernel = dev_ms / args.steps
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            hbm_peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            hbm_peak = 6650.0
+            peak_src = "fallback (B200_PROFILING.md)"
+        achieved_gbs = bytes_ / (ms_kernel * 1e-3) / 1e9
+        fp64 = measure_fp64_peaks(torch)
+        achieved_tflops = flops / (ms_kernel * 1e-3) / 1e12
+        line = {
+            "metric": "Mackey-Glass DDE trajectories/sec", "value": value, "unit": "trajectories/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "mackey_glass_dop853_tau17 (BASELINE.json configs[1])",
+                "n_traj_per_gpu": n_traj, "rtol": 1e-6, "atol": 1e-6, "n_history": 64,
+                "times": "0,50,...,500", "parallelism": "replicate-sharded x%d" % world,
+                "l2": "working set per step (%.1f GB of history rings) exceeds the 126 MB L2"
+                      % (n_traj * 64 * 10 * 8 / 1e9)},
+            "accepted_steps_per_s_per_gpu": float(acc.item()) / world * args.steps /
+                                            (dev_ms_max * 1e-3),
+            "failed_trajectories": int((code != 1).sum()),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "note": "kernel is FP64-issue bound, not HBM bound: see fp64",
+                "fp64": {"achieved_tflops": achieved_tflops,
+                         "peak_nofma_tflops": fp64["nofma"], "peak_fma_tflops": fp64["fma"],
+                         "frac_of_nofma": achieved_tflops / fp64["nofma"] if fp64["nofma"] else None,
+                         "flops_convention": "SURVEY.md 8d: one + - * / fmax as written = 1 flop; "
+                                             "F_pow = %d" % F_POW}},
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "host_wall_ms_per_step": 1e3 * t_wall / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            n1 = args.cpu_sample or 4096
+            backend, r1 = cpu_reference_run(n1, 0, 0)
+            nN = max(n1, 1024 * cores)
+            _, rN = cpu_reference_run(nN, 0, cores)
+            # parity spot check on the sample the baseline just integrated
+            same = bool(np.array_equal(r1.statistics, stats[:n1]) and
+                        np.array_equal(r1.code, code[:n1]))
+            line["cpu_baseline"] = {
+                "value": nN / rN.seconds, "unit": "trajectories/s", "cores": cores,
+                "kind": "reference" if backend == "ref" else "port",
+                "sample": "first %d trajectories of the batch over %d forked processes "
+                          "(unmodified reference C, gcc -O2); single core: first %d trajectories"
+                          % (nN, cores, n1),
+                "single_core_value": n1 / r1.seconds,
+                "gpu_matches_cpu_statistics_on_sample": same}
+        print(json.dumps(line))
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_fp64_peaks(torch):
+    """FP64 issue ceilings measured live: register-resident dependent-free
+    chains of DFMA (2 flop/instr) and of alternating DMUL/DADD (1 flop/instr,
+    the ceiling that applies to FMA-free code)."""
+    try:
+        from dde_b200 import _lib
+        lib = _lib.load()
+        import ctypes as C
+        fn = lib.dde_fp64_peak
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_int]
+        return {"fma": fn(1), "nofma": fn(0)}
+    except Exception:
+        return {"fma": None, "nofma": None}
+
+
+if __name__ == "__main__":
+    main()

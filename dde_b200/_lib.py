@@ -84,6 +84,7 @@ SYMBOLS = [
     ("dde_host_free", None, [C.c_void_p]),
     ("dde_pow_host", C.c_double, [C.c_double, C.c_double]),
     ("dde_exp_host", C.c_double, [C.c_double]),
+    ("dde_fp64_peak", C.c_double, [C.c_int]),
 ]
 
 _lib = None

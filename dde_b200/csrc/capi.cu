@@ -110,6 +110,32 @@ void free_dev(T *&p) {
   }
 }
 
+/* FP64 issue-rate probe: 8 independent register chains per thread, no memory
+ * traffic.  fma = 1: DFMA (2 flop/instr); fma = 0: alternating DMUL / DADD
+ * (1 flop/instr), the ceiling that applies to the FMA-free solver code. */
+template <int FMA>
+__global__ void fp64_peak_kernel(double *sink, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    if (FMA) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    } else {
+      x0 = x0 * a; x1 = x1 * a; x2 = x2 * a; x3 = x3 * a;
+      x4 = x4 * a; x5 = x5 * a; x6 = x6 * a; x7 = x7 * a;
+      x0 = x0 + b; x1 = x1 + b; x2 = x2 + b; x3 = x3 + b;
+      x4 = x4 + b; x5 = x5 + b; x6 = x6 + b; x7 = x7 + b;
+    }
+  }
+  const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == 123.456) {
+    sink[0] = r;
+  }
+}
+
 } /* namespace */
 
 extern "C" void dde_register_model(dde::ModelDesc *desc) {
@@ -265,6 +291,49 @@ int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf, si
 
 double dde_pow_host(double x, double y) { return dde_pow(x, y); }
 double dde_exp_host(double x) { return dde_exp(x); }
+
+/* TFLOP/s of the FP64 pipe on the current device (see fp64_peak_kernel). */
+double dde_fp64_peak(int fma) {
+  cudaDeviceProp prop;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  double *sink = nullptr;
+  if (cudaMalloc(&sink, sizeof(double)) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return -1.0;
+  }
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    if (fma) {
+      fp64_peak_kernel<1><<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+    } else {
+      fp64_peak_kernel<0><<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+    }
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) {
+      best = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (cudaGetLastError() != cudaSuccess) {
+    return -1.0;
+  }
+  const double instr = (double) blocks * threads * (double) iters * 16.0;
+  return instr * (fma ? 2.0 : 1.0) / (best * 1e-3) / 1e12;
+}
 
 void *dde_host_alloc(size_t bytes) {
   void *p = nullptr;

@@ -21,11 +21,20 @@
  * traffic is: y0/parms in, output rows out, ring commits, lag look-ups.
  * The model's deriv() is inlined into the kernel (one translation unit,
  * template on the model), which is what keeps y/dydt in registers despite
- * the pointer-based model ABI.  Divergence: lanes run their own adaptive
- * loops; the compiler-generated reconvergence point is the loop head, and
- * lanes that finish early are refilled with the next trajectory from an
- * atomic counter (persistent threads) so a warp's cost is the mean, not the
- * max, of its lanes' step counts.
+ * the pointer-based model ABI.
+ *
+ * Control flow.  Each lane carries its own trajectory, t and h, but a warp
+ * walks the stages of a step attempt in lock-step: the attempt is a loop over
+ * RHS evaluations ("stages") with a warp-uniform stage counter, a switch that
+ * forms the stage input, ONE inlined instance of the model's deriv(), and a
+ * switch that files the result.  That keeps the code small enough for the
+ * instruction caches (18 inlined copies of deriv + pow + lag look-up were
+ * 160 KB and stalled on instruction fetch, profiles/r1a) and makes the
+ * expensive part -- deriv, pow, the ring look-up -- execute convergently.
+ * Lanes that rejected the step idle through the accept-only stages (dop853's
+ * 5 extra evaluations); lanes whose trajectory has ended are refilled with
+ * the next one from an atomic counter (persistent threads), so a warp's cost
+ * follows the mean, not the max, of its lanes' step counts.
  */
 #ifndef DDE_DOPRI_KERNELS_CUH
 #define DDE_DOPRI_KERNELS_CUH
@@ -83,6 +92,11 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
   constexpr int OMAX = M::N_OUT > 0 ? M::N_OUT : (M::N_OUT == 0 ? 1 : DDE_DYN_MAXOUT);
   constexpr int ORDER = METHOD == 0 ? 5 : 8;
+  /* RHS evaluations per attempt, and extra ones per accepted step
+     (src/dopri_5.c:42-95; src/dopri_853.c:159-247, src/dopri.c:400-403,
+     src/dopri_853.c:304,330-347) */
+  constexpr int NST_STEP = METHOD == 0 ? 6 : 11;
+  constexpr int NST = METHOD == 0 ? 6 : 16;
   const int n = NC > 0 ? NC : a.n;
   const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
   const int n_out = M::N_OUT == 0 ? 0 : a.n_out; /* 0 = output function not requested */
@@ -124,17 +138,6 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
   double *yo = nullptr, *oo = nullptr;
 
-#define DDE_EVAL(tt, yy, dd)                      \
-  do {                                            \
-    M::deriv((size_t) n, (tt), (yy), (dd), p);    \
-    ++n_eval;                                     \
-  } while (0)
-
-  /* One flat loop per lane.  Each trip is: [refill] -> one step attempt ->
-     [accept work] -> [retire].  The bracketed parts are the only divergent
-     regions and reconverge before the next attempt, so lanes of a warp
-     execute the expensive stage evaluations together even though each one
-     carries its own t, h and trajectory. */
   for (;;) {
     if (!active) {
       /* persistent threads: take the next trajectory, or leave */
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
       s_count[s] = 0;
       s_head[s] = 0;
       s_hint[s] = 0;
+      s_win[s] = DDE_WIN_EMPTY;
       s_code[s] = 0; /* NOT_SET */
       s_error[s] = 0;
 
@@ -200,7 +204,10 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
           oo += n_out;
         }
       }
-      DDE_EVAL(t, y, k1);
+      /* k1 = f(t0, y0), src/dopri.c:329 (a cold second copy of deriv: it
+         runs once per trajectory) */
+      M::deriv((size_t) n, t, y, k1, p);
+      ++n_eval;
       bool finite0 = true;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -227,7 +234,8 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
         for (int i = 0; i < n; ++i) {
           ye[i] = y[i] + h * k1[i];
         }
-        DDE_EVAL(t + h, ye, f1);
+        M::deriv((size_t) n, t + h, ye, f1, p);
+        ++n_eval;
         double der2 = 0.0;
 #pragma unroll
         for (int i = 0; i < n; ++i) {
@@ -244,277 +252,337 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
     }
 
     /* ---- one trip of the adaptive loop, src/dopri.c:343-510 ---- */
-    if (!done) {
-      do {
-        bool force_this_step = false;
-        if ((unsigned long long) n_step > a.step_max_n) {
-          s_error[s] = 1;
-          s_code[s] = -3; /* ERR_TOO_MANY_STEPS */
-          done = true;
-          break;
-        }
-        if (fabs(h) <= a.step_size_min) {
-          if (a.step_size_min_allow) {
-            h = copysign(a.step_size_min, sign);
-            force_this_step = true;
-          } else {
-            s_error[s] = 1;
-            s_code[s] = -4; /* ERR_STEP_SIZE_TOO_SMALL */
-            done = true;
-            break;
-          }
-        } else if (fabs(h) <= fabs(t) * DBL_EPSILON) {
-          s_error[s] = 1;
-          s_code[s] = -5; /* ERR_STEP_SIZE_VANISHED */
-          done = true;
-          break;
-        }
-        if ((t + 1.01 * h - t_stop) * sign > 0.0) {
-          h = t_stop - t;
-          stop = true;
-        }
-        if ((t + 1.01 * h - t_end) * sign > 0.0) {
-          h_save = h;
-          h = t_end - t;
-          last = true;
-        }
-        ++n_step;
-
-        /* stage storage: k1 is carried (FSAL); dopri5 uses k2..k6 and k7 as
-           its `ysti`; dop853 uses k2..k10 */
-        double k2[NMAX], k3[NMAX], k4[NMAX], k5[NMAX], k6[NMAX], k7[NMAX], k8[NMAX],
-            k9[NMAX], k10[NMAX], y1[NMAX];
-        double err;
-
-        if (METHOD == 0) {
-          /* dopri5_step, src/dopri_5.c:42-95 */
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * DP5_A21 * k1[i];
-          }
-          DDE_EVAL(t + DP5_C2 * h, y1, k2);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
-          }
-          DDE_EVAL(t + DP5_C3 * h, y1, k3);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
-          }
-          DDE_EVAL(t + DP5_C4 * h, y1, k4);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
-                                DP5_A54 * k4[i]);
-          }
-          DDE_EVAL(t + DP5_C5 * h, y1, k5);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            k7[i] = y[i] + h * (DP5_A61 * k1[i] + DP5_A62 * k2[i] + DP5_A63 * k3[i] +
-                                DP5_A64 * k4[i] + DP5_A65 * k5[i]);
-          }
-          const double t_next = t + h;
-          DDE_EVAL(t_next, k7, k6);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP5_A71 * k1[i] + DP5_A73 * k3[i] + DP5_A74 * k4[i] +
-                                DP5_A75 * k5[i] + DP5_A76 * k6[i]);
-          }
-          DDE_EVAL(t_next, y1, k2);
-          /* The reference also writes the fifth dense coefficient into the
-             ring head on every attempt (dopri_5.c:84-89) and overwrites k4
-             with the error combination (:91-94).  Only accepted steps read
-             the head, so here k4 is kept and that coefficient is formed on
-             acceptance from the same operands in the same order. */
-          if (s_error[s]) {
-            done = true; /* src/dopri.c:387-389 */
-            break;
-          }
-          /* dopri5_error, src/dopri_5.c:97-104 */
-          err = 0.0;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const double ke = h * (DP5_E1 * k1[i] + DP5_E3 * k3[i] + DP5_E4 * k4[i] +
-                                   DP5_E5 * k5[i] + DP5_E6 * k6[i] + DP5_E7 * k2[i]);
-            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
-            err += sq(ke / sk);
-          }
-          err = sqrt(err / (double) n);
+    bool run = !done;
+    bool force_this_step = false;
+    if (run) {
+      if ((unsigned long long) n_step > a.step_max_n) {
+        s_error[s] = 1;
+        s_code[s] = -3; /* ERR_TOO_MANY_STEPS */
+        done = true;
+      } else if (fabs(h) <= a.step_size_min) {
+        if (a.step_size_min_allow) {
+          h = copysign(a.step_size_min, sign);
+          force_this_step = true;
         } else {
-          /* dopri853_step, src/dopri_853.c:159-247 */
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * DP8_A21 * k1[i];
-          }
-          DDE_EVAL(t + DP8_C2 * h, y1, k2);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
-          }
-          DDE_EVAL(t + DP8_C3 * h, y1, k3);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
-          }
-          DDE_EVAL(t + DP8_C4 * h, y1, k4);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
-          }
-          DDE_EVAL(t + DP8_C5 * h, y1, k5);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
-          }
-          DDE_EVAL(t + DP8_C6 * h, y1, k6);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
-                                DP8_A76 * k6[i]);
-          }
-          DDE_EVAL(t + DP8_C7 * h, y1, k7);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
-                                DP8_A86 * k6[i] + DP8_A87 * k7[i]);
-          }
-          DDE_EVAL(t + DP8_C8 * h, y1, k8);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
-                                DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
-          }
-          DDE_EVAL(t + DP8_C9 * h, y1, k9);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A101 * k1[i] + DP8_A104 * k4[i] + DP8_A105 * k5[i] +
-                                DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
-                                DP8_A109 * k9[i]);
-          }
-          DDE_EVAL(t + DP8_C10 * h, y1, k10);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A111 * k1[i] + DP8_A114 * k4[i] + DP8_A115 * k5[i] +
-                                DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
-                                DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
-          }
-          DDE_EVAL(t + DP8_C11 * h, y1, k2);
-          const double t_next = t + h;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y1[i] = y[i] + h * (DP8_A121 * k1[i] + DP8_A124 * k4[i] + DP8_A125 * k5[i] +
-                                DP8_A126 * k6[i] + DP8_A127 * k7[i] + DP8_A128 * k8[i] +
-                                DP8_A129 * k9[i] + DP8_A1210 * k10[i] + DP8_A1211 * k2[i]);
-          }
-          DDE_EVAL(t_next, y1, k3);
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            k4[i] = DP8_B1 * k1[i] + DP8_B6 * k6[i] + DP8_B7 * k7[i] + DP8_B8 * k8[i] +
-                    DP8_B9 * k9[i] + DP8_B10 * k10[i] + DP8_B11 * k2[i] + DP8_B12 * k3[i];
-            k5[i] = y[i] + h * k4[i];
-          }
-          if (s_error[s]) {
-            done = true; /* src/dopri.c:387-389 */
-            break;
-          }
-          /* dopri853_error, src/dopri_853.c:249-283: scaled by sign, not
-             |h|, guarded by deno < 0 (SURVEY.md A.1#1) */
-          err = 0.0;
-          double err2 = 0.0;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(k5[i]));
-            double erri = k4[i] - DP8_BHH1 * k1[i] - DP8_BHH2 * k9[i] - DP8_BHH3 * k3[i];
-            err2 += sq(erri / sk);
-            erri = DP8_ER1 * k1[i] + DP8_ER6 * k6[i] + DP8_ER7 * k7[i] + DP8_ER8 * k8[i] +
-                   DP8_ER9 * k9[i] + DP8_ER10 * k10[i] + DP8_ER11 * k2[i] + DP8_ER12 * k3[i];
-            err += sq(erri / sk);
-          }
-          double deno = err + 0.01 * err2;
-          deno = deno < 0 ? 1.0 : deno;
-          err = sign * err * sqrt(1.0 / ((double) n * deno));
+          s_error[s] = 1;
+          s_code[s] = -4; /* ERR_STEP_SIZE_TOO_SMALL */
+          done = true;
         }
+      } else if (fabs(h) <= fabs(t) * DBL_EPSILON) {
+        s_error[s] = 1;
+        s_code[s] = -5; /* ERR_STEP_SIZE_VANISHED */
+        done = true;
+      }
+      run = !done;
+    }
+    if (run) {
+      if ((t + 1.01 * h - t_stop) * sign > 0.0) {
+        h = t_stop - t;
+        stop = true;
+      }
+      if ((t + 1.01 * h - t_end) * sign > 0.0) {
+        h_save = h;
+        h = t_end - t;
+        last = true;
+      }
+      ++n_step;
+    }
 
-        /* dopri_h_new, src/dopri.c:516-525 */
-        const double fac11 = dde_pow(err, step_constant);
-        /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
-        const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
-        double fac = fac11 / facb;
-        fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
-        double h_new = h / fac;
-        const bool accept = err <= 1;
+    /* stage storage: k1 is carried (FSAL); dopri5 uses k2..k6, dop853
+       k2..k10.  ysave: the stage input the stiffness test needs (dopri5's
+       `ysti`, dop853's last y1).  hd: dense-output coefficients of this
+       step, i.e. the ring's head entry, in registers until committed. */
+    double k2[NMAX], k3[NMAX], k4[NMAX], k5[NMAX], k6[NMAX], k7[NMAX], k8[NMAX], k9[NMAX],
+        k10[NMAX], ysave[NMAX], hd[ORDER * NMAX];
+    bool accepted = false;
+    double h_new = 0.0;
 
-        if (accept || force_this_step) {
-          /* src/dopri.c:396-494 */
-          fac_old = fmax(err, 1e-4);
-          ++n_accept;
-          if (METHOD == 1) {
-            /* the redundant evaluation at the OLD time, src/dopri.c:400-403
-               (SURVEY.md A.1#2): it counts, and its lag look-ups can fail */
-            DDE_EVAL(t, k5, k4);
-          }
-          /* dopri_test_stiff, src/dopri.c:668-693 */
-          if (a.stiff_check != 0 &&
-              (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
-            double stnum = 0, stden = 0;
+#pragma unroll 1
+    for (int st = 0; st < NST; ++st) {
+      if (!(run && (st < NST_STEP || accepted))) {
+        continue;
+      }
+      /* -- 1. the input of evaluation `st` (warp-uniform switch) -- */
+      double yin[NMAX], kt[NMAX], tt;
+      if (METHOD == 0) {
+        switch (st) { /* dopri5_step, src/dopri_5.c:54-80 */
+          case 0:
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              if (METHOD == 0) { /* src/dopri_5.c:129-140 */
-                stnum += sq(k2[i] - k6[i]);
-                stden += sq(y1[i] - k7[i]);
-              } else { /* src/dopri_853.c:382-394 */
-                stnum += sq(k4[i] - k3[i]);
-                stden += sq(k5[i] - y1[i]);
-              }
+              yin[i] = y[i] + h * DP5_A21 * k1[i];
             }
-            const bool stiff =
-                stden > 0 && fabs(h) * sqrt(stnum / stden) > (METHOD == 0 ? 3.25 : 6.1);
-            bool give_up = false;
-            if (stiff) {
-              stiff_n_nonstiff = 0;
-              if (stiff_n_stiff++ >= 15) {
-                give_up = true;
-              }
-            } else if (stiff_n_stiff > 0) {
-              if (stiff_n_nonstiff++ >= 6) {
-                stiff_n_stiff = 0;
-              }
+            tt = t + DP5_C2 * h;
+            break;
+          case 1:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
             }
-            if (give_up) {
-              s_error[s] = 1;
-              s_code[s] = -7; /* ERR_STIFF */
-              done = true;
-              break;
+            tt = t + DP5_C3 * h;
+            break;
+          case 2:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
             }
-          }
+            tt = t + DP5_C4 * h;
+            break;
+          case 3:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
+                                   DP5_A54 * k4[i]);
+            }
+            tt = t + DP5_C5 * h;
+            break;
+          case 4:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A61 * k1[i] + DP5_A62 * k2[i] + DP5_A63 * k3[i] +
+                                   DP5_A64 * k4[i] + DP5_A65 * k5[i]);
+              ysave[i] = yin[i];
+            }
+            tt = t + h;
+            break;
+          default: /* 5 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A71 * k1[i] + DP5_A73 * k3[i] + DP5_A74 * k4[i] +
+                                   DP5_A75 * k5[i] + DP5_A76 * k6[i]);
+            }
+            tt = t + h;
+            break;
+        }
+      } else {
+        switch (st) { /* dopri853_step, src/dopri_853.c:178-240 */
+          case 0:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * DP8_A21 * k1[i];
+            }
+            tt = t + DP8_C2 * h;
+            break;
+          case 1:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
+            }
+            tt = t + DP8_C3 * h;
+            break;
+          case 2:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
+            }
+            tt = t + DP8_C4 * h;
+            break;
+          case 3:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
+            }
+            tt = t + DP8_C5 * h;
+            break;
+          case 4:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
+            }
+            tt = t + DP8_C6 * h;
+            break;
+          case 5:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
+                                   DP8_A76 * k6[i]);
+            }
+            tt = t + DP8_C7 * h;
+            break;
+          case 6:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
+                                   DP8_A86 * k6[i] + DP8_A87 * k7[i]);
+            }
+            tt = t + DP8_C8 * h;
+            break;
+          case 7:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
+                                   DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
+            }
+            tt = t + DP8_C9 * h;
+            break;
+          case 8:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A101 * k1[i] + DP8_A104 * k4[i] + DP8_A105 * k5[i] +
+                                   DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
+                                   DP8_A109 * k9[i]);
+            }
+            tt = t + DP8_C10 * h;
+            break;
+          case 9:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A111 * k1[i] + DP8_A114 * k4[i] + DP8_A115 * k5[i] +
+                                   DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
+                                   DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
+            }
+            tt = t + DP8_C11 * h;
+            break;
+          case 10:
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A121 * k1[i] + DP8_A124 * k4[i] + DP8_A125 * k5[i] +
+                                   DP8_A126 * k6[i] + DP8_A127 * k7[i] + DP8_A128 * k8[i] +
+                                   DP8_A129 * k9[i] + DP8_A1210 * k10[i] + DP8_A1211 * k2[i]);
+              ysave[i] = yin[i];
+            }
+            tt = t + h;
+            break;
+          case 11: /* the redundant evaluation at the OLD time, src/dopri.c:400-403
+                      (SURVEY.md A.1#2): it counts, and its lag look-ups can fail */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = k5[i];
+            }
+            tt = t;
+            break;
+          case 12: /* dopri853_save_history, src/dopri_853.c:304 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = k5[i];
+            }
+            tt = t + h;
+            break;
+          case 13: /* src/dopri_853.c:330-335 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A141 * k1[i] + DP8_A147 * k7[i] + DP8_A148 * k8[i] +
+                                   DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
+                                   DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
+            }
+            tt = t + DP8_C14 * h;
+            break;
+          case 14: /* src/dopri_853.c:336-341 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
+                                   DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
+                                   DP8_A1513 * k4[i] + DP8_A1514 * k10[i]);
+            }
+            tt = t + DP8_C15 * h;
+            break;
+          default: /* 15, src/dopri_853.c:342-347 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
+                                   DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
+                                   DP8_A1614 * k10[i] + DP8_A1615 * k2[i]);
+            }
+            tt = t + DP8_C16 * h;
+            break;
+        }
+      }
 
-          /* dopri_save_history: the dense-output coefficients of this step,
-             i.e. the ring's head entry, kept in registers until committed */
-          double hd[ORDER * NMAX];
-          if (METHOD == 0) {
-            /* src/dopri_5.c:106-118 and :84-89 */
+      /* -- 2. dopri_eval, src/dopri.c:831-835: the one hot copy of the model -- */
+      M::deriv((size_t) n, tt, yin, kt, p);
+      ++n_eval;
+
+      /* -- 3. file the result; after the last stage of the attempt: error
+            estimate, controller, accept / reject -- */
+      bool attempt_done = false; /* all NST_STEP evaluations of the attempt are in */
+      bool step_done = false;    /* ... and so are the accept-only ones */
+      if (METHOD == 0) {
+        switch (st) {
+          case 0:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            break;
+          case 1:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k3[i] = kt[i];
+            break;
+          case 2:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            break;
+          case 3:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k5[i] = kt[i];
+            break;
+          case 4:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k6[i] = kt[i];
+            break;
+          default: /* 5: k2 = f(t + h, y1); yin is y1 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            attempt_done = true;
+            break;
+        }
+      } else {
+        switch (st) {
+          case 0:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            break;
+          case 1:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k3[i] = kt[i];
+            break;
+          case 2:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            break;
+          case 3:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k5[i] = kt[i];
+            break;
+          case 4:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k6[i] = kt[i];
+            break;
+          case 5:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k7[i] = kt[i];
+            break;
+          case 6:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k8[i] = kt[i];
+            break;
+          case 7:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k9[i] = kt[i];
+            break;
+          case 8:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k10[i] = kt[i];
+            break;
+          case 9:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            break;
+          case 10: /* src/dopri_853.c:242-246 */
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              const double ydiff = y1[i] - y[i];
-              const double bspl = h * k1[i] - ydiff;
-              hd[i] = y[i];
-              hd[n + i] = ydiff;
-              hd[2 * n + i] = bspl;
-              hd[3 * n + i] = -h * k2[i] + ydiff - bspl;
-              hd[4 * n + i] = h * (DP5_D1 * k1[i] + DP5_D3 * k3[i] + DP5_D4 * k4[i] +
-                                   DP5_D5 * k5[i] + DP5_D6 * k6[i] + DP5_D7 * k2[i]);
+              k3[i] = kt[i];
+              k4[i] = DP8_B1 * k1[i] + DP8_B6 * k6[i] + DP8_B7 * k7[i] + DP8_B8 * k8[i] +
+                      DP8_B9 * k9[i] + DP8_B10 * k10[i] + DP8_B11 * k2[i] + DP8_B12 * k3[i];
+              k5[i] = y[i] + h * k4[i];
             }
+            attempt_done = true;
+            break;
+          case 11: /* k4 = f(t_old, k5): only the stiffness test reads it */
+#pragma unroll
+            for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            break;
+          case 12: /* src/dopri_853.c:306-327 */
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              k1[i] = k2[i]; /* src/dopri.c:416-417 */
-              y[i] = y1[i];
-            }
-          } else {
-            /* src/dopri_853.c:285-367 */
-            DDE_EVAL(t + h, k5, k4);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
+              k4[i] = kt[i];
               const double ydiff = k5[i] - y[i];
               const double bspl = h * k1[i] - ydiff;
               hd[i] = y[i];
@@ -534,29 +602,19 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
                               DP8_D78 * k8[i] + DP8_D79 * k9[i] + DP8_D710 * k10[i] +
                               DP8_D711 * k2[i] + DP8_D712 * k3[i];
             }
+            break;
+          case 13:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k10[i] = kt[i];
+            break;
+          case 14:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            break;
+          default: /* 15, src/dopri_853.c:350-366 */
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              y1[i] = y[i] + h * (DP8_A141 * k1[i] + DP8_A147 * k7[i] + DP8_A148 * k8[i] +
-                                  DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
-                                  DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
-            }
-            DDE_EVAL(t + DP8_C14 * h, y1, k10);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              y1[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
-                                  DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
-                                  DP8_A1513 * k4[i] + DP8_A1514 * k10[i]);
-            }
-            DDE_EVAL(t + DP8_C15 * h, y1, k2);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              y1[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
-                                  DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
-                                  DP8_A1614 * k10[i] + DP8_A1615 * k2[i]);
-            }
-            DDE_EVAL(t + DP8_C16 * h, y1, k3);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
+              k3[i] = kt[i];
               hd[4 * n + i] = h * (hd[4 * n + i] + DP8_D413 * k4[i] + DP8_D414 * k10[i] +
                                    DP8_D415 * k2[i] + DP8_D416 * k3[i]);
               hd[5 * n + i] = h * (hd[5 * n + i] + DP8_D513 * k4[i] + DP8_D514 * k10[i] +
@@ -566,89 +624,64 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
               hd[7 * n + i] = h * (hd[7 * n + i] + DP8_D713 * k4[i] + DP8_D714 * k10[i] +
                                    DP8_D715 * k2[i] + DP8_D716 * k3[i]);
             }
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              k1[i] = k4[i]; /* src/dopri.c:420-421 */
-              y[i] = k5[i];
-            }
-          }
-          const double t_old = t;
-          t += h;
-
-          /* output rows, src/dopri.c:437-456: interpolate from the head */
-          for (;;) {
-            if (times_idx >= n_times) {
-              break;
-            }
-            const double tq = a.times[times_idx];
-            if (!(last || sign * tq <= sign * t)) {
-              break;
-            }
-            const double theta = (tq - t_old) / h;
-            const double theta1 = 1 - theta;
-            double row[NMAX];
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
-                                   : interp853(n, theta, theta1, hd + i);
-              yo[i] = row[i];
-            }
-            if (n_out > 0) {
-              double o[OMAX];
-              M::output((size_t) n, tq, row, (size_t) n_out, o, p);
-#pragma unroll
-              for (int i = 0; i < OMAX; ++i) {
-                if (i < n_out) {
-                  oo[i] = o[i];
-                }
-              }
-              oo += n_out;
-            }
-            yo += n;
-            ++times_idx;
-          }
-
-          /* ring_buffer_head_advance, src/dopri.c:460: commit to HBM */
-          if (a.n_history > 0) {
-            int head = s_head[s];
-            double *dst = s_ring[s] + (size_t) head * (size_t) hl;
-#pragma unroll
-            for (int i = 0; i < ORDER * n; ++i) {
-              dst[i] = hd[i];
-            }
-            dst[ORDER * n] = t_old;
-            dst[ORDER * n + 1] = h;
-            head = head + 1 == a.n_history ? 0 : head + 1;
-            s_head[s] = head;
-            s_count[s] = s_count[s] + 1;
-          }
-
-          if (last) {
-            step_size_exit = h_save; /* src/dopri.c:463 */
-            s_code[s] = 1;           /* OK_COMPLETE */
-            done = true;
+            step_done = true;
             break;
+        }
+      }
+
+      if (attempt_done) {
+        if (s_error[s]) {
+          done = true; /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
+          run = false;
+          continue;
+        }
+        double err;
+        if (METHOD == 0) {
+          /* dopri5_error, src/dopri_5.c:97-104.  (The reference first
+             overwrites k4 with this combination, :91-94, and writes the
+             fifth dense coefficient into the ring head on every attempt,
+             :84-89; only accepted steps read the head, so k4 is kept and that
+             coefficient is formed on acceptance from the same operands.) */
+          err = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double ke = h * (DP5_E1 * k1[i] + DP5_E3 * k3[i] + DP5_E4 * k4[i] +
+                                   DP5_E5 * k5[i] + DP5_E6 * k6[i] + DP5_E7 * k2[i]);
+            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(yin[i]));
+            err += sq(ke / sk);
           }
-          if (fabs(h_new) >= a.step_size_max) {
-            h_new = copysign(a.step_size_max, sign);
+          err = sqrt(err / (double) n);
+        } else {
+          /* dopri853_error, src/dopri_853.c:249-283: scaled by sign, not
+             |h|, guarded by deno < 0 (SURVEY.md A.1#1) */
+          err = 0.0;
+          double err2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double sk = atol + rtol * fmax(fabs(y[i]), fabs(k5[i]));
+            double erri = k4[i] - DP8_BHH1 * k1[i] - DP8_BHH2 * k9[i] - DP8_BHH3 * k3[i];
+            err2 += sq(erri / sk);
+            erri = DP8_ER1 * k1[i] + DP8_ER6 * k6[i] + DP8_ER7 * k7[i] + DP8_ER8 * k8[i] +
+                   DP8_ER9 * k9[i] + DP8_ER10 * k10[i] + DP8_ER11 * k2[i] + DP8_ER12 * k3[i];
+            err += sq(erri / sk);
           }
-          if (reject) {
-            h_new = copysign(fmin(fabs(h_new), fabs(h)), sign);
-            reject = false;
-          }
-          if (stop) {
-            /* critical times, src/dopri.c:476-491 */
-            while (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] <= sign * t) {
-              ++tcrit_idx;
-            }
-            if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
-              t_stop = a.tcrit[tcrit_idx];
-            } else {
-              t_stop = t_end;
-            }
-            stop = false;
-          } else {
-            h = h_new;
+          double deno = err + 0.01 * err2;
+          deno = deno < 0 ? 1.0 : deno;
+          err = sign * err * sqrt(1.0 / ((double) n * deno));
+        }
+        /* dopri_h_new, src/dopri.c:516-525 */
+        const double fac11 = dde_pow(err, step_constant);
+        /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
+        const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
+        double fac = fac11 / facb;
+        fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
+        h_new = h / fac;
+        accepted = (err <= 1) || force_this_step;
+        if (accepted) {
+          fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
+          ++n_accept;
+          if (METHOD == 0) {
+            step_done = true;
           }
         } else {
           /* rejected, src/dopri.c:495-509 */
@@ -661,7 +694,150 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
           stop = false;
           h = h_new;
         }
-      } while (0);
+      }
+
+      /* dopri_test_stiff, src/dopri.c:668-693: after the redundant
+         evaluation for dop853, right after acceptance for dopri5 */
+      if ((METHOD == 0 ? step_done : st == 11) && a.stiff_check != 0 &&
+          (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
+        double stnum = 0, stden = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          if (METHOD == 0) { /* src/dopri_5.c:129-140; yin is y1 */
+            stnum += sq(k2[i] - k6[i]);
+            stden += sq(yin[i] - ysave[i]);
+          } else { /* src/dopri_853.c:382-394 */
+            stnum += sq(k4[i] - k3[i]);
+            stden += sq(k5[i] - ysave[i]);
+          }
+        }
+        const bool stiff =
+            stden > 0 && fabs(h) * sqrt(stnum / stden) > (METHOD == 0 ? 3.25 : 6.1);
+        bool give_up = false;
+        if (stiff) {
+          stiff_n_nonstiff = 0;
+          if (stiff_n_stiff++ >= 15) {
+            give_up = true;
+          }
+        } else if (stiff_n_stiff > 0) {
+          if (stiff_n_nonstiff++ >= 6) {
+            stiff_n_stiff = 0;
+          }
+        }
+        if (give_up) {
+          s_error[s] = 1;
+          s_code[s] = -7; /* ERR_STIFF */
+          done = true;
+          run = false;
+          continue;
+        }
+      }
+
+      if (step_done) {
+        /* ---- the rest of an accepted step, src/dopri.c:410-494 ---- */
+        if (METHOD == 0) {
+          /* dopri5_save_history, src/dopri_5.c:106-118 and :84-89; yin is y1 */
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double ydiff = yin[i] - y[i];
+            const double bspl = h * k1[i] - ydiff;
+            hd[i] = y[i];
+            hd[n + i] = ydiff;
+            hd[2 * n + i] = bspl;
+            hd[3 * n + i] = -h * k2[i] + ydiff - bspl;
+            hd[4 * n + i] = h * (DP5_D1 * k1[i] + DP5_D3 * k3[i] + DP5_D4 * k4[i] +
+                                 DP5_D5 * k5[i] + DP5_D6 * k6[i] + DP5_D7 * k2[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            k1[i] = k2[i]; /* src/dopri.c:416-417 */
+            y[i] = yin[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            k1[i] = k4[i]; /* src/dopri.c:420-421 */
+            y[i] = k5[i];
+          }
+        }
+        const double t_old = t;
+        t += h;
+
+        /* output rows, src/dopri.c:437-456: interpolate from the head */
+        for (;;) {
+          if (times_idx >= n_times) {
+            break;
+          }
+          const double tq = a.times[times_idx];
+          if (!(last || sign * tq <= sign * t)) {
+            break;
+          }
+          const double theta = (tq - t_old) / h;
+          const double theta1 = 1 - theta;
+          double row[NMAX];
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
+                                 : interp853(n, theta, theta1, hd + i);
+            yo[i] = row[i];
+          }
+          if (n_out > 0) {
+            double o[OMAX];
+            M::output((size_t) n, tq, row, (size_t) n_out, o, p);
+#pragma unroll
+            for (int i = 0; i < OMAX; ++i) {
+              if (i < n_out) {
+                oo[i] = o[i];
+              }
+            }
+            oo += n_out;
+          }
+          yo += n;
+          ++times_idx;
+        }
+
+        /* ring_buffer_head_advance, src/dopri.c:460: the head entry goes to
+           its slot in HBM and becomes visible to lag queries */
+        if (a.n_history > 0) {
+          double *dst = s_ring[s] + (size_t) s_head[s] * (size_t) hl;
+#pragma unroll
+          for (int i = 0; i < ORDER * n; ++i) {
+            dst[i] = hd[i];
+          }
+          dst[ORDER * n] = t_old;
+          dst[ORDER * n + 1] = h;
+          ring_advance(s, a.n_history);
+        }
+
+        if (last) {
+          step_size_exit = h_save; /* src/dopri.c:463 */
+          s_code[s] = 1;           /* OK_COMPLETE */
+          done = true;
+          run = false;
+          continue;
+        }
+        if (fabs(h_new) >= a.step_size_max) {
+          h_new = copysign(a.step_size_max, sign);
+        }
+        if (reject) {
+          h_new = copysign(fmin(fabs(h_new), fabs(h)), sign);
+          reject = false;
+        }
+        if (stop) {
+          /* critical times, src/dopri.c:476-491 */
+          while (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] <= sign * t) {
+            ++tcrit_idx;
+          }
+          if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
+            t_stop = a.tcrit[tcrit_idx];
+          } else {
+            t_stop = t_end;
+          }
+          stop = false;
+        } else {
+          h = h_new;
+        }
+      }
     }
 
     if (done) {
@@ -677,7 +853,6 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
       active = false;
     }
   }
-#undef DDE_EVAL
 }
 
 } /* namespace dde */

@@ -36,6 +36,7 @@
 #ifndef DDE_TPB
 #define DDE_TPB 128 /* threads per block of the thread-per-trajectory kernels */
 #endif
+#define DDE_WIN_EMPTY 0xffffffffu
 
 namespace dde {
 
@@ -56,6 +57,14 @@ __shared__ double s_t0[DDE_TPB];           /* sign * start time (src/dopri.c:186
 __shared__ unsigned s_count[DDE_TPB];      /* entries committed so far */
 __shared__ int s_head[DDE_TPB];            /* slot the next commit goes to */
 __shared__ unsigned s_hint[DDE_TPB];       /* logical index the last search found */
+/* Staged bracket of the lag window: two adjacent committed entries a = s_win
+ * and b = a + 1 with their sign-adjusted start times, the (exclusive) upper
+ * bound of b, and their step sizes.  A query that falls in [ta, tc) needs no
+ * search and no dependent load: slot and theta come from shared memory while
+ * the coefficient loads from the ring are already in flight. */
+__shared__ unsigned s_win[DDE_TPB];        /* logical index of a; DDE_WIN_EMPTY = none */
+__shared__ double s_win_ta[DDE_TPB], s_win_tb[DDE_TPB], s_win_tc[DDE_TPB];
+__shared__ double s_win_ha[DDE_TPB], s_win_hb[DDE_TPB];
 __shared__ int s_code[DDE_TPB];            /* obj->code */
 __shared__ int s_error[DDE_TPB];           /* obj->error */
 __shared__ long long s_step[DDE_TPB];      /* difeq: obj->step */
@@ -73,36 +82,60 @@ __device__ __forceinline__ int ring_slot_back(int head, int back, int cap) {
   return slot < 0 ? slot + cap : slot;
 }
 
-/* Commit one entry: the thread-local head becomes visible to lag queries. */
-__device__ __forceinline__ void ring_commit(int s, const double *entry, int hl) {
-  const int cap = s_lag_u.cap;
-  if (cap == 0) {
-    return; /* zero capacity: head advances over the single spare slot */
-  }
+/* Bookkeeping after the integrating thread has written the head entry to
+ * its slot: advance the ring (ring_buffer_head_advance, src/dopri.c:460) and
+ * drop the staged bracket if the commit changes what it stands for -- its
+ * upper bound was open (b or b's successor did not exist yet), or the
+ * overwrite policy just recycled one of its slots. */
+__device__ __forceinline__ void ring_advance(int s, int cap) {
   int head = s_head[s];
-  double *dst = s_ring[s] + (size_t) head * hl;
-  for (int i = 0; i < hl; ++i) {
-    dst[i] = entry[i];
-  }
   head = head + 1 == cap ? 0 : head + 1;
   s_head[s] = head;
-  s_count[s] = s_count[s] + 1;
+  const unsigned count = s_count[s] + 1;
+  s_count[s] = count;
+  const unsigned win = s_win[s];
+  if (win != DDE_WIN_EMPTY) {
+    const bool open_top = win + 3 >= count;                /* a + 2 was not committed before */
+    const bool recycled = count > (unsigned) cap && win < count - (unsigned) cap;
+    if (open_top || recycled) {
+      s_win[s] = DDE_WIN_EMPTY;
+    }
+  }
 }
 
+struct LagHit {
+  const double *entry; /* NULL: no entry (error already recorded) */
+  double t_old, h;     /* the entry's start time and step */
+};
+
 /* The last committed entry whose time is <= t (>= t when integrating
- * backwards); NULL, with obj->error / ERR_YLAG_FAIL set, if there is none. */
-__device__ __forceinline__ const double *find_time(int s, double t) {
+ * backwards), src/dopri.c:742-769.  On failure obj->error / ERR_YLAG_FAIL
+ * are set and entry is NULL. */
+__device__ __forceinline__ LagHit find_time(int s, double t) {
   const int cap = s_lag_u.cap;
   const int hl = s_lag_u.hl;
-  const bool fwd = s_lag_u.sign > 0;
+  const double sign = s_lag_u.sign;
+  const double st = sign * t; /* entries are ordered by sign * time */
   const unsigned count = s_count[s];
-  const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   const int head = s_head[s];
   const double *ring = s_ring[s];
+  LagHit hit;
+  /* fast path: the staged bracket */
+  const unsigned win = s_win[s];
+  if (win != DDE_WIN_EMPTY && st >= s_win_ta[s] && st < s_win_tc[s]) {
+    const bool second = st >= s_win_tb[s];
+    const unsigned idx = win + (second ? 1u : 0u);
+    hit.entry = ring + (size_t) ring_slot_back(head, (int) (count - idx), cap) * hl;
+    hit.t_old = sign * (second ? s_win_tb[s] : s_win_ta[s]);
+    hit.h = second ? s_win_hb[s] : s_win_ha[s];
+    return hit;
+  }
+  /* slow path: bisection over the stored step times, started from the last
+     result (the search path is free, only its result is defined) */
+  const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   const int idx_t = hl - 2;
-#define DDE_PRED(j)                                                                 \
-  (fwd ? ring[(size_t) ring_slot_back(head, (int) (count - (j)), cap) * hl + idx_t] <= t \
-       : ring[(size_t) ring_slot_back(head, (int) (count - (j)), cap) * hl + idx_t] >= t)
+#define DDE_ENTRY(j) (ring + (size_t) ring_slot_back(head, (int) (count - (j)), cap) * hl)
+#define DDE_PRED(j) (sign * DDE_ENTRY(j)[idx_t] <= st)
   unsigned lo = count - used, hi = count; /* want: pred(lo) holds, pred(hi) fails */
   bool ok = used > 0;
   if (ok) {
@@ -126,7 +159,10 @@ __device__ __forceinline__ const double *find_time(int s, double t) {
   if (!ok) {
     s_error[s] = 1;
     s_code[s] = -6; /* ERR_YLAG_FAIL */
-    return nullptr;
+    hit.entry = nullptr;
+    hit.t_old = 0.0;
+    hit.h = 1.0;
+    return hit;
   }
   while (hi - lo > 1) {
     const unsigned mid = lo + (hi - lo) / 2;
@@ -136,9 +172,32 @@ __device__ __forceinline__ const double *find_time(int s, double t) {
       hi = mid;
     }
   }
-#undef DDE_PRED
   s_hint[s] = lo;
-  return ring + (size_t) ring_slot_back(head, (int) (count - lo), cap) * hl;
+  /* stage the bracket [lo, lo + 1] */
+  const double *ea = DDE_ENTRY(lo);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double ta = ea[idx_t], ha = ea[idx_t + 1];
+  double tb = inf, tc = inf, hb = 1.0;
+  if (lo + 1 < count) {
+    const double *eb = DDE_ENTRY(lo + 1);
+    tb = sign * eb[idx_t];
+    hb = eb[idx_t + 1];
+    if (lo + 2 < count) {
+      tc = sign * DDE_ENTRY(lo + 2)[idx_t];
+    }
+  }
+#undef DDE_PRED
+#undef DDE_ENTRY
+  s_win[s] = lo;
+  s_win_ta[s] = sign * ta;
+  s_win_tb[s] = tb;
+  s_win_tc[s] = tc;
+  s_win_ha[s] = ha;
+  s_win_hb[s] = hb;
+  hit.entry = ea;
+  hit.t_old = ta;
+  hit.h = ha;
+  return hit;
 }
 
 /* Dense-output polynomial of one component; c points at the component's
@@ -168,15 +227,14 @@ static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   if (dde::s_lag_u.sign * t <= dde::s_t0[s]) {
     return dde::s_y0[s][i];
   }
-  const double *e = dde::find_time(s, t);
-  if (e == nullptr) {
+  const dde::LagHit hit = dde::find_time(s, t);
+  if (hit.entry == nullptr) {
     return dde::na_real();
   }
   const int n = dde::s_lag_u.n, order = dde::s_lag_u.order;
-  const double t_old = e[order * n], h = e[order * n + 1];
-  const double theta = (t - t_old) / h;
+  const double theta = (t - hit.t_old) / hit.h;
   const double theta1 = 1 - theta;
-  return dde::interp_entry(e, order, n, theta, theta1, i);
+  return dde::interp_entry(hit.entry, order, n, theta, theta1, i);
 }
 
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
@@ -188,14 +246,13 @@ static __device__ __forceinline__ void ylag_all(double t, double *y) {
     }
     return;
   }
-  const double *e = dde::find_time(s, t);
-  if (e != nullptr) {
+  const dde::LagHit hit = dde::find_time(s, t);
+  if (hit.entry != nullptr) {
     const int order = dde::s_lag_u.order;
-    const double t_old = e[order * n], h = e[order * n + 1];
-    const double theta = (t - t_old) / h;
+    const double theta = (t - hit.t_old) / hit.h;
     const double theta1 = 1 - theta;
     for (int i = 0; i < n; ++i) {
-      y[i] = dde::interp_entry(e, order, n, theta, theta1, (size_t) i);
+      y[i] = dde::interp_entry(hit.entry, order, n, theta, theta1, (size_t) i);
     }
   }
 }
@@ -210,14 +267,13 @@ static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *i
     }
     return;
   }
-  const double *e = dde::find_time(s, t);
-  if (e != nullptr) {
+  const dde::LagHit hit = dde::find_time(s, t);
+  if (hit.entry != nullptr) {
     const int n = dde::s_lag_u.n, order = dde::s_lag_u.order;
-    const double t_old = e[order * n], h = e[order * n + 1];
-    const double theta = (t - t_old) / h;
+    const double theta = (t - hit.t_old) / hit.h;
     const double theta1 = 1 - theta;
     for (size_t i = 0; i < nidx; ++i) {
-      y[i] = dde::interp_entry(e, order, n, theta, theta1, (size_t) idx[i]);
+      y[i] = dde::interp_entry(hit.entry, order, n, theta, theta1, (size_t) idx[i]);
     }
   }
 }

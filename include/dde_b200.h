@@ -247,6 +247,11 @@ void dde_host_free(void *p);
 double dde_pow_host(double x, double y);
 double dde_exp_host(double x);
 
+/* Measured FP64 issue ceiling of the current device in TFLOP/s: fma != 0 a
+ * chain of DFMA (2 flop/instr), fma == 0 alternating DMUL/DADD (1 flop/instr,
+ * what FMA-free code can reach).  Roofline denominator for bench.py. */
+double dde_fp64_peak(int fma);
+
 #ifdef __cplusplus
 }
 #endif
