@@ -7,9 +7,14 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false
        -Xcompiler -fPIC,-mfma,-ffp-contract=off,-Wall,-Wno-unused-function
        -Iinclude -Idde_b200/csrc ${DDE_NVCC_EXTRA:-})
+# DDE_OUT / DDE_TAG: build an experimental variant next to the product library
+OUT=${DDE_OUT:-dde_b200/libdde_b200.so}
+TAG=${DDE_TAG:-}
 mkdir -p build
-"$NVCC" "${FLAGS[@]}" -c dde_b200/csrc/capi.cu -o build/capi.o &
-"$NVCC" "${FLAGS[@]}" -Xptxas -v -c dde_b200/csrc/models_builtin.cu -o build/models_builtin.o 2> build/ptxas_models.log &
+"$NVCC" "${FLAGS[@]}" -c dde_b200/csrc/capi.cu -o build/capi$TAG.o 2> build/nvcc_capi$TAG.log &
+"$NVCC" "${FLAGS[@]}" -Xptxas -v -c dde_b200/csrc/models_builtin.cu -o build/models_builtin$TAG.o 2> build/ptxas_models$TAG.log &
 wait
-"$NVCC" -shared -o dde_b200/libdde_b200.so build/capi.o build/models_builtin.o -lcudart
-echo "built dde_b200/libdde_b200.so"
+grep -v "offline compilation" build/nvcc_capi$TAG.log | grep -i -B2 -A6 "error\|warning" || true
+grep -i -B2 -A6 "error" build/ptxas_models$TAG.log || true
+"$NVCC" -shared -o "$OUT" build/capi$TAG.o build/models_builtin$TAG.o -lcudart
+echo "built $OUT"

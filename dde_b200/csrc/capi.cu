@@ -167,6 +167,7 @@ struct dde_dopri_batch_s {
   double *d_y_out = nullptr, *d_out = nullptr, *d_t_last = nullptr, *d_step_size = nullptr;
   int *d_stats = nullptr, *d_code = nullptr;
   double *d_ring = nullptr;
+  double *d_init_k1 = nullptr, *d_init_h = nullptr;
   unsigned *d_ring_count = nullptr;
   unsigned long long *d_next = nullptr;
 };
@@ -369,6 +370,8 @@ void dde_dopri_batch_free(dde_dopri_batch_t *b) {
   free_dev(b->d_stats);
   free_dev(b->d_code);
   free_dev(b->d_ring);
+  free_dev(b->d_init_k1);
+  free_dev(b->d_init_h);
   free_dev(b->d_ring_count);
   free_dev(b->d_next);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -447,6 +450,8 @@ dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model, const dde_dopri_cont
   ok = ok && cudaMalloc(&b->d_stats, sizeof(int) * 4 * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_code, sizeof(int) * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_ring_count, sizeof(unsigned) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_init_k1, sizeof(double) * n * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_init_h, sizeof(double) * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_next, sizeof(unsigned long long)) == cudaSuccess;
   if (ok && ctl->n_history > 0) {
     const size_t bytes = sizeof(double) * hl * (size_t) ctl->n_history * n_traj;
@@ -630,6 +635,8 @@ int dde_dopri_batch_run(dde_dopri_batch_t *b) {
     a.t_last = b->d_t_last;
     a.step_size = b->d_step_size;
     a.ring = b->d_ring;
+    a.init_k1 = b->d_init_k1;
+    a.init_h = b->d_init_h;
     a.ring_count = b->d_ring_count;
     a.next_traj = b->d_next;
     int launches = 0;

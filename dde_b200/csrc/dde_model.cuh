@@ -40,9 +40,10 @@
 namespace dde {
 
 template <class Kernel>
-inline int persistent_grid(Kernel kernel, long long n_items, int device_sms) {
+inline int persistent_grid(Kernel kernel, long long n_items, int device_sms, size_t dyn_smem = 0) {
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DDE_TPB, 0) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DDE_TPB, dyn_smem) !=
+          cudaSuccess ||
       per_sm < 1) {
     per_sm = 1;
     (void) cudaGetLastError();
@@ -55,18 +56,44 @@ inline int persistent_grid(Kernel kernel, long long n_items, int device_sms) {
   return (int) (grid < 1 ? 1 : grid);
 }
 
+template <class M, int METHOD>
+cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaStream_t stream) {
+  DopriArgs args = args_in;
+  /* stage the lag window's coefficients in shared memory when they fit */
+  const size_t order = METHOD == 0 ? 5 : 8;
+  size_t dyn = 0;
+  args.win_staged = 0;
+  if (args.n_history > 0) {
+    const size_t bytes = sizeof(double) * DDE_WIN * order * (size_t) args.n * DDE_TPB;
+    if (bytes <= DDE_WIN_COEF_BUDGET) {
+      dyn = bytes;
+      args.win_staged = 1;
+    }
+  }
+  /* start-up of every trajectory (row 0, k1, first step size) */
+  const long long init_grid = (args.n_traj + DDE_TPB - 1) / DDE_TPB;
+  dopri_init_kernel<M, METHOD><<<(unsigned) init_grid, DDE_TPB, 0, stream>>>(args);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    return err;
+  }
+  /* the stepping kernel: one resident wave of persistent threads */
+  auto kernel = dopri_tpt_kernel<M, METHOD>;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
+  if (err != cudaSuccess) {
+    return err;
+  }
+  const int grid = persistent_grid(kernel, args.n_traj, device_sms, dyn);
+  kernel<<<grid, DDE_TPB, dyn, stream>>>(args);
+  return cudaGetLastError();
+}
+
 template <class M>
 cudaError_t launch_dopri_model(int method, const DopriArgs &args, int device_sms,
                                cudaStream_t stream, int *n_launches) {
-  if (method == 0) {
-    const int grid = persistent_grid(dopri_tpt_kernel<M, 0>, args.n_traj, device_sms);
-    dopri_tpt_kernel<M, 0><<<grid, DDE_TPB, 0, stream>>>(args);
-  } else {
-    const int grid = persistent_grid(dopri_tpt_kernel<M, 1>, args.n_traj, device_sms);
-    dopri_tpt_kernel<M, 1><<<grid, DDE_TPB, 0, stream>>>(args);
-  }
-  *n_launches = 1;
-  return cudaGetLastError();
+  *n_launches = 2;
+  return method == 0 ? launch_dopri_method<M, 0>(args, device_sms, stream)
+                     : launch_dopri_method<M, 1>(args, device_sms, stream);
 }
 
 template <class M>

@@ -46,6 +46,9 @@
 
 namespace dde {
 
+#ifndef DDE_MIN_BLOCKS
+#define DDE_MIN_BLOCKS 1 /* resident blocks per SM the register allocation must allow */
+#endif
 #ifndef DDE_DYN_MAXN
 #define DDE_DYN_MAXN 16 /* largest n of a model compiled with runtime n */
 #endif
@@ -76,9 +79,13 @@ struct DopriArgs {
   double *y_out, *out;
   int *stats, *code;
   double *t_last, *step_size;
+  /* start-up values from dopri_init_kernel */
+  double *init_k1; /* [n x n_traj] f(t0, y0) */
+  double *init_h;  /* [n_traj] first step size */
   /* history */
   double *ring;          /* [n_traj][n_history][order*n + 2] */
   unsigned *ring_count;  /* [n_traj] entries committed (for export) */
+  int win_staged;        /* lag-window coefficients in (dynamic) shared memory */
   /* work distribution: next trajectory index to hand out */
   unsigned long long *next_traj;
 };
@@ -86,7 +93,7 @@ struct DopriArgs {
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 template <class M, int METHOD>
-__global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
+__global__ void __launch_bounds__(DDE_TPB, DDE_MIN_BLOCKS) dopri_tpt_kernel(const DopriArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
     s_lag_u.n = n;
     s_lag_u.hl = hl;
     s_lag_u.order = ORDER;
+    s_lag_u.staged = a.win_staged;
   }
   __syncthreads();
 
@@ -170,8 +178,7 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
       s_t0[s] = sign * a.times[0];
       s_count[s] = 0;
       s_head[s] = 0;
-      s_hint[s] = 0;
-      s_win[s] = DDE_WIN_EMPTY;
+      lag_window_reset(s);
       s_code[s] = 0; /* NOT_SET */
       s_error[s] = 0;
 
@@ -186,68 +193,25 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
       }
       yo = a.y_out + (size_t) traj * (size_t) nt * (size_t) n;
       oo = n_out > 0 ? a.out + (size_t) traj * (size_t) nt * (size_t) n_out : nullptr;
-      if (a.return_initial) {
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          yo[i] = y[i];
-        }
+      if (a.return_initial) { /* row 0 was written by dopri_init_kernel */
         yo += n;
-        if (n_out > 0) {
-          double o[OMAX];
-          M::output((size_t) n, a.times[0], y, (size_t) n_out, o, p);
-#pragma unroll
-          for (int i = 0; i < OMAX; ++i) {
-            if (i < n_out) {
-              oo[i] = o[i];
-            }
-          }
-          oo += n_out;
-        }
+        oo += n_out;
       }
-      /* k1 = f(t0, y0), src/dopri.c:329 (a cold second copy of deriv: it
-         runs once per trajectory) */
-      M::deriv((size_t) n, t, y, k1, p);
-      ++n_eval;
-      bool finite0 = true;
+      /* k1 = f(t0, y0) and the first step size come from dopri_init_kernel */
+      const double *k0 = a.init_k1 + traj * n;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        finite0 = finite0 && isfinite(k1[i]);
+        k1[i] = k0[i];
       }
-      if (!finite0) {
-        s_code[s] = -8; /* DDE_ERR_NONFINITE_DERIV, src/dopri.c:331-336 */
+      h = a.init_h[traj];
+      n_eval = a.stats[4 * traj + 0];
+      const int code0 = a.code[traj];
+      if (code0 == -8) { /* non-finite initial derivative, src/dopri.c:331-336 */
+        s_code[s] = code0;
         done = true;
-      } else if (a.step_size_initial > 0.0) {
-        h = a.step_size_initial; /* src/dopri.c:528-530 */
-      } else {
-        /* dopri_h_init, src/dopri.c:527-572 */
-        double norm_f = 0.0, norm_y = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          const double sk = atol + rtol * fabs(y[i]);
-          norm_f += sq(k1[i] / sk);
-          norm_y += sq(y[i] / sk);
-        }
-        h = (norm_f <= 1e-10 || norm_y <= 1e-10) ? 1e-6 : sqrt(norm_y / norm_f) * 0.01;
-        h = copysign(fmin(h, a.step_size_max), sign);
-        double f1[NMAX], ye[NMAX];
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          ye[i] = y[i] + h * k1[i];
-        }
-        M::deriv((size_t) n, t + h, ye, f1, p);
-        ++n_eval;
-        double der2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          const double sk = atol + rtol * fabs(y[i]);
-          der2 += sq((f1[i] - k1[i]) / sk);
-        }
-        der2 = sqrt(der2) / h;
-        const double der12 = fmax(fabs(der2), sqrt(norm_f));
-        const double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3)
-                                           : dde_pow(0.01 / der12, 1.0 / ORDER);
-        h = fmin(fmin(100 * fabs(h), h1), a.step_size_max);
-        h = copysign(h, sign);
+      } else if (code0 != 0) { /* a lag look-up failed during start-up */
+        s_code[s] = code0;
+        s_error[s] = 1;
       }
     }
 
@@ -286,6 +250,10 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
         last = true;
       }
       ++n_step;
+      if (a.n_history > 0) {
+        /* top up the staged lag window while the warp is in step */
+        lag_window_ensure(s, sign * (t + h));
+      }
     }
 
     /* stage storage: k1 is carried (FSAL); dopri5 uses k2..k6, dop853
@@ -806,7 +774,7 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
           }
           dst[ORDER * n] = t_old;
           dst[ORDER * n + 1] = h;
-          ring_advance(s, a.n_history);
+          ring_advance<ORDER * NMAX>(s, a.n_history, hd, ORDER * n, t_old, h);
         }
 
         if (last) {
@@ -853,6 +821,137 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_tpt_kernel(const DopriArgs a) {
       active = false;
     }
   }
+}
+
+/* Start-up of every trajectory, one thread each: row 0 of the results, k1 =
+ * f(t0, y0), the finiteness check and dopri_h_init -- the part of
+ * dopri_integrate before its loop, src/dopri.c:320-339,527-572.  Kept out of
+ * the stepping kernel so that kernel's instruction footprint stays small and
+ * its lanes never run start-up code one at a time.  Leaves code = 0 (go),
+ * -8 (non-finite derivative: trajectory over) or -6 (a lag look-up failed:
+ * the stepping kernel ends the trajectory after its first attempt,
+ * src/dopri.c:387-389) and n_eval in stats[0]. */
+template <class M, int METHOD>
+__global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) {
+  constexpr int NC = M::N;
+  constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
+  constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
+  constexpr int OMAX = M::N_OUT > 0 ? M::N_OUT : (M::N_OUT == 0 ? 1 : DDE_DYN_MAXOUT);
+  constexpr int ORDER = METHOD == 0 ? 5 : 8;
+  const int n = NC > 0 ? NC : a.n;
+  const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
+  const int n_out = M::N_OUT == 0 ? 0 : a.n_out;
+  const int s = threadIdx.x;
+  if (threadIdx.x == 0) {
+    s_lag_u.sign = a.sign;
+    s_lag_u.cap = a.n_history;
+    s_lag_u.n = n;
+    s_lag_u.hl = ORDER * n + 2;
+    s_lag_u.order = ORDER;
+    s_lag_u.staged = 0;
+  }
+  __syncthreads();
+  const long long traj = blockIdx.x * (long long) DDE_TPB + threadIdx.x;
+  if (traj >= a.n_traj) {
+    return;
+  }
+  const double sign = a.sign, atol = a.atol, rtol = a.rtol;
+  const int nt = a.return_initial ? a.n_times : a.n_times - 1;
+  double p[PMAX], y[NMAX], k1[NMAX];
+#pragma unroll
+  for (int i = 0; i < PMAX; ++i) {
+    if (i < n_parms) {
+      p[i] = a.parms[traj * a.parms_stride + i];
+    }
+  }
+  const double *y0 = a.y0 + traj * n;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    y[i] = y0[i];
+  }
+  const double t = a.times[0];
+  s_ring[s] = a.ring;
+  s_y0[s] = y0;
+  s_t0[s] = sign * t;
+  s_count[s] = 0;
+  s_head[s] = 0;
+  s_code[s] = 0;
+  s_error[s] = 0;
+  lag_window_reset(s);
+  if (a.return_initial) { /* src/dopri.c:320-327 */
+    double *yo = a.y_out + (size_t) traj * (size_t) nt * (size_t) n;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      yo[i] = y[i];
+    }
+    if (n_out > 0) {
+      double *oo = a.out + (size_t) traj * (size_t) nt * (size_t) n_out;
+      double o[OMAX];
+      M::output((size_t) n, t, y, (size_t) n_out, o, p);
+#pragma unroll
+      for (int i = 0; i < OMAX; ++i) {
+        if (i < n_out) {
+          oo[i] = o[i];
+        }
+      }
+    }
+  }
+  int n_eval = 0;
+  double h = 0.0;
+  int code = 0;
+  M::deriv((size_t) n, t, y, k1, p); /* src/dopri.c:329 */
+  ++n_eval;
+  bool finite0 = true;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    finite0 = finite0 && isfinite(k1[i]);
+  }
+  if (!finite0) {
+    code = -8; /* DDE_ERR_NONFINITE_DERIV, src/dopri.c:331-336 */
+  } else if (a.step_size_initial > 0.0) {
+    h = a.step_size_initial; /* src/dopri.c:528-530 */
+  } else {
+    /* dopri_h_init, src/dopri.c:527-572 */
+    double norm_f = 0.0, norm_y = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double sk = atol + rtol * fabs(y[i]);
+      norm_f += sq(k1[i] / sk);
+      norm_y += sq(y[i] / sk);
+    }
+    h = (norm_f <= 1e-10 || norm_y <= 1e-10) ? 1e-6 : sqrt(norm_y / norm_f) * 0.01;
+    h = copysign(fmin(h, a.step_size_max), sign);
+    double f1[NMAX], ye[NMAX];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      ye[i] = y[i] + h * k1[i];
+    }
+    M::deriv((size_t) n, t + h, ye, f1, p);
+    ++n_eval;
+    double der2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double sk = atol + rtol * fabs(y[i]);
+      der2 += sq((f1[i] - k1[i]) / sk);
+    }
+    der2 = sqrt(der2) / h;
+    const double der12 = fmax(fabs(der2), sqrt(norm_f));
+    const double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3)
+                                       : dde_pow(0.01 / der12, 1.0 / ORDER);
+    h = fmin(fmin(100 * fabs(h), h1), a.step_size_max);
+    h = copysign(h, sign);
+  }
+  if (code == 0 && s_error[s]) {
+    code = s_code[s];
+  }
+  double *k0 = a.init_k1 + traj * n;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    k0[i] = k1[i];
+  }
+  a.init_h[traj] = h;
+  a.stats[4 * traj + 0] = n_eval;
+  a.code[traj] = code;
 }
 
 } /* namespace dde */

@@ -36,7 +36,10 @@
 #ifndef DDE_TPB
 #define DDE_TPB 128 /* threads per block of the thread-per-trajectory kernels */
 #endif
-#define DDE_WIN_EMPTY 0xffffffffu
+#define DDE_WIN 4 /* entries in a thread's staged lag window (power of two) */
+/* shared memory a block may spend on staged coefficients; above this the
+   window keeps only step times and sizes and coefficients are read from HBM */
+#define DDE_WIN_COEF_BUDGET (72 * 1024)
 
 namespace dde {
 
@@ -47,6 +50,7 @@ struct LagUniform {
   int n;         /* number of equations */
   int hl;        /* entry length in doubles: order*n + 2, or 1 + n + n_out */
   int order;     /* 5 or 8 (dopri); 0 for difeq */
+  int staged;    /* window coefficients live in shared memory */
 };
 
 __shared__ LagUniform s_lag_u;
@@ -56,24 +60,48 @@ __shared__ const double *s_y0[DDE_TPB];    /* pre-history state (src/dopri.c:777
 __shared__ double s_t0[DDE_TPB];           /* sign * start time (src/dopri.c:186) */
 __shared__ unsigned s_count[DDE_TPB];      /* entries committed so far */
 __shared__ int s_head[DDE_TPB];            /* slot the next commit goes to */
-__shared__ unsigned s_hint[DDE_TPB];       /* logical index the last search found */
-/* Staged bracket of the lag window: two adjacent committed entries a = s_win
- * and b = a + 1 with their sign-adjusted start times, the (exclusive) upper
- * bound of b, and their step sizes.  A query that falls in [ta, tc) needs no
- * search and no dependent load: slot and theta come from shared memory while
- * the coefficient loads from the ring are already in flight. */
-__shared__ unsigned s_win[DDE_TPB];        /* logical index of a; DDE_WIN_EMPTY = none */
-__shared__ double s_win_ta[DDE_TPB], s_win_tb[DDE_TPB], s_win_tc[DDE_TPB];
-__shared__ double s_win_ha[DDE_TPB], s_win_hb[DDE_TPB];
 __shared__ int s_code[DDE_TPB];            /* obj->code */
 __shared__ int s_error[DDE_TPB];           /* obj->error */
 __shared__ long long s_step[DDE_TPB];      /* difeq: obj->step */
 __shared__ long long s_step0[DDE_TPB];     /* difeq: obj->step0 */
 
+/* The staged lag window ("shared-memory staging of the bracketing history
+ * steps"): DDE_WIN consecutive committed entries base .. base + wn - 1 of the
+ * thread's ring, held in shared memory -- sign-adjusted start time and step
+ * size always, the dense-output coefficients too when they fit -- entry
+ * `idx` in slot idx % DDE_WIN.  wtop is the (exclusive) upper end of the
+ * window: the start time of entry base + wn, or +inf while the window's last
+ * entry is the newest committed one (a query beyond it extrapolates that
+ * entry's polynomial).  Unused slots hold +inf as
+ * start time so that the look-up needs no bounds.  A query inside
+ * [wt[base], wtop) is served without touching HBM and without a search.
+ *
+ * The window follows the lag by itself: the integrator tops it up once per
+ * step attempt (lag_window_ensure), while all lanes of a warp are in step, up
+ * to the highest time the previous attempts queried relative to the end of
+ * the step (dq_hi, learnt from misses); newly committed entries are appended
+ * straight from registers when the window sits at the head of the ring.  A
+ * query outside the window takes the slow path: bisection over the step
+ * times stored in the ring (the search path is free, only its result is
+ * defined: src/dopri.c:742-769), then a reload of the
+ * window at the entry found. */
+__shared__ double s_wt[DDE_WIN][DDE_TPB];
+__shared__ double s_wh[DDE_WIN][DDE_TPB];
+__shared__ double s_wtop[DDE_TPB];
+__shared__ unsigned s_wbase[DDE_TPB];
+__shared__ unsigned s_wn[DDE_TPB];
+__shared__ double s_att_hi[DDE_TPB]; /* sign * (t + h) of the attempt in progress */
+__shared__ double s_dq_hi[DDE_TPB];  /* highest query seen, relative to s_att_hi; -inf: none yet */
+extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
+
 __device__ __forceinline__ double na_real() {
   /* R's NA_real_ (quiet NaN, low word 1954); payloads do not survive device
      arithmetic, parity treats every NaN alike */
   return __longlong_as_double(0x7FF00000000007A2LL);
+}
+
+__device__ __forceinline__ double pos_inf() {
+  return __longlong_as_double(0x7ff0000000000000LL);
 }
 
 /* slot of the entry committed `back` commits ago (back = 1: most recent) */
@@ -82,87 +110,173 @@ __device__ __forceinline__ int ring_slot_back(int head, int back, int cap) {
   return slot < 0 ? slot + cap : slot;
 }
 
+/* ring slot of logical entry idx (0 = first entry ever committed) */
+__device__ __forceinline__ const double *ring_entry(int s, unsigned idx) {
+  const int slot = ring_slot_back(s_head[s], (int) (s_count[s] - idx), s_lag_u.cap);
+  return s_ring[s] + (size_t) slot * (size_t) s_lag_u.hl;
+}
+
+__device__ __forceinline__ void lag_window_reset(int s) {
+#pragma unroll
+  for (int k = 0; k < DDE_WIN; ++k) {
+    s_wt[k][s] = pos_inf();
+  }
+  s_wtop[s] = pos_inf();
+  s_wbase[s] = 0;
+  s_wn[s] = 0;
+  s_att_hi[s] = 0.0;
+  s_dq_hi[s] = -pos_inf();
+}
+
+/* Copy committed entry idx from the ring into its window slot.  Returns the
+ * sign-adjusted start time of the entry after it, +inf if there is none. */
+__device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
+  const int hl = s_lag_u.hl;
+  const int nc = hl - 2;
+  const double sign = s_lag_u.sign;
+  const unsigned count = s_count[s];
+  const double *e = ring_entry(s, idx);
+  const int w = (int) (idx & (DDE_WIN - 1));
+  double top = pos_inf();
+  if (idx + 1 < count) {
+    top = sign * ring_entry(s, idx + 1)[nc];
+  }
+  s_wt[w][s] = sign * e[nc];
+  s_wh[w][s] = e[nc + 1];
+  if (s_lag_u.staged) {
+    double *dst = s_wc + (size_t) w * nc * DDE_TPB + s;
+    for (int c = 0; c < nc; ++c) {
+      dst[(size_t) c * DDE_TPB] = e[c];
+    }
+  }
+  return top;
+}
+
+/* Once per step attempt, all lanes together: extend the window upwards until
+ * it covers sign * (t + h) + dq_hi, dropping entries from its lower end as
+ * needed.  Purely a prefetch: any query it fails to anticipate still finds
+ * its entry through the slow path. */
+__device__ __forceinline__ void lag_window_ensure(int s, double att_hi) {
+  s_att_hi[s] = att_hi;
+  const double need = att_hi + s_dq_hi[s];
+#pragma unroll 1
+  for (int it = 0; it < DDE_WIN; ++it) {
+    unsigned wn = s_wn[s];
+    if (!(wn > 0 && need >= s_wtop[s])) {
+      break;
+    }
+    unsigned base = s_wbase[s];
+    if (wn == DDE_WIN) {
+      ++base;
+      --wn;
+    }
+    const double top = lag_window_load(s, base + wn); /* overwrites the dropped slot */
+    s_wbase[s] = base;
+    s_wn[s] = wn + 1;
+    s_wtop[s] = top;
+  }
+}
+
 /* Bookkeeping after the integrating thread has written the head entry to
- * its slot: advance the ring (ring_buffer_head_advance, src/dopri.c:460) and
- * drop the staged bracket if the commit changes what it stands for -- its
- * upper bound was open (b or b's successor did not exist yet), or the
- * overwrite policy just recycled one of its slots. */
-__device__ __forceinline__ void ring_advance(int s, int cap) {
+ * its ring slot: advance the ring (ring_buffer_head_advance, src/dopri.c:460)
+ * and keep the window consistent -- drop an entry the overwrite policy just
+ * recycled, append the new entry if the window ends at the head of the ring.
+ * hd: the new entry's coefficients (order * n, in registers), then its start
+ * time and step size. */
+template <int NCOEF_MAX>
+__device__ __forceinline__ void ring_advance(int s, int cap, const double *hd, int nc,
+                                             double t_old, double h) {
   int head = s_head[s];
   head = head + 1 == cap ? 0 : head + 1;
   s_head[s] = head;
   const unsigned count = s_count[s] + 1;
   s_count[s] = count;
-  const unsigned win = s_win[s];
-  if (win != DDE_WIN_EMPTY) {
-    const bool open_top = win + 3 >= count;                /* a + 2 was not committed before */
-    const bool recycled = count > (unsigned) cap && win < count - (unsigned) cap;
-    if (open_top || recycled) {
-      s_win[s] = DDE_WIN_EMPTY;
+  const unsigned newest = count - 1;
+  unsigned wn = s_wn[s], base = s_wbase[s];
+  const unsigned tail = count > (unsigned) cap ? count - (unsigned) cap : 0u;
+  if (wn > 0 && base < tail) {
+    s_wt[base & (DDE_WIN - 1)][s] = pos_inf();
+    ++base;
+    --wn;
+    s_wbase[s] = base;
+    s_wn[s] = wn;
+  }
+  const double st_old = s_lag_u.sign * t_old;
+  bool append = false;
+  if (wn == 0) {
+    base = newest;
+    s_wbase[s] = base;
+    append = true;
+  } else if (base + wn == newest) {
+    if (wn < DDE_WIN) {
+      append = true;
+    } else {
+      s_wtop[s] = st_old;
     }
+  }
+  if (append) {
+    const int w = (int) (newest & (DDE_WIN - 1));
+    s_wt[w][s] = st_old;
+    s_wh[w][s] = h;
+    if (s_lag_u.staged) {
+      double *dst = s_wc + (size_t) w * nc * DDE_TPB + s;
+#pragma unroll
+      for (int c = 0; c < NCOEF_MAX; ++c) {
+        if (c < nc) {
+          dst[(size_t) c * DDE_TPB] = hd[c];
+        }
+      }
+    }
+    s_wn[s] = wn + 1;
+    s_wtop[s] = pos_inf();
   }
 }
 
 struct LagHit {
-  const double *entry; /* NULL: no entry (error already recorded) */
-  double t_old, h;     /* the entry's start time and step */
+  bool ok;         /* false: no entry (ERR_YLAG_FAIL recorded) */
+  unsigned idx;    /* logical index of the entry */
+  double t_old, h; /* its start time and step */
 };
 
-/* The last committed entry whose time is <= t (>= t when integrating
- * backwards), src/dopri.c:742-769.  On failure obj->error / ERR_YLAG_FAIL
- * are set and entry is NULL. */
-__device__ __forceinline__ LagHit find_time(int s, double t) {
+/* Slow path of the look-up: the last committed entry whose time is <= t
+ * (>= t when integrating backwards), src/dopri.c:742-769, by bisection over
+ * the ring, then the window is reloaded starting at that entry.  Returns
+ * false after recording ERR_YLAG_FAIL when there is no such entry. */
+static __device__ __noinline__ bool lag_window_miss(int s, double st) {
   const int cap = s_lag_u.cap;
-  const int hl = s_lag_u.hl;
+  const int idx_t = s_lag_u.hl - 2;
   const double sign = s_lag_u.sign;
-  const double st = sign * t; /* entries are ordered by sign * time */
   const unsigned count = s_count[s];
-  const int head = s_head[s];
-  const double *ring = s_ring[s];
-  LagHit hit;
-  /* fast path: the staged bracket */
-  const unsigned win = s_win[s];
-  if (win != DDE_WIN_EMPTY && st >= s_win_ta[s] && st < s_win_tc[s]) {
-    const bool second = st >= s_win_tb[s];
-    const unsigned idx = win + (second ? 1u : 0u);
-    hit.entry = ring + (size_t) ring_slot_back(head, (int) (count - idx), cap) * hl;
-    hit.t_old = sign * (second ? s_win_tb[s] : s_win_ta[s]);
-    hit.h = second ? s_win_hb[s] : s_win_ha[s];
-    return hit;
-  }
-  /* slow path: bisection over the stored step times, started from the last
-     result (the search path is free, only its result is defined) */
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
-  const int idx_t = hl - 2;
-#define DDE_ENTRY(j) (ring + (size_t) ring_slot_back(head, (int) (count - (j)), cap) * hl)
-#define DDE_PRED(j) (sign * DDE_ENTRY(j)[idx_t] <= st)
+#define DDE_PRED(j) (sign * ring_entry(s, (j))[idx_t] <= st)
   unsigned lo = count - used, hi = count; /* want: pred(lo) holds, pred(hi) fails */
-  bool ok = used > 0;
-  if (ok) {
-    const unsigned h = s_hint[s];
-    if (h >= lo && h < hi && DDE_PRED(h)) {
-      lo = h;
-      if (h + 1 < hi) {
-        if (DDE_PRED(h + 1)) {
-          lo = h + 1;
-        } else {
-          hi = h + 1;
-        }
-      }
-    } else {
-      ok = DDE_PRED(lo);
-      if (h > lo && h < hi) {
-        hi = h;
-      }
-    }
-  }
-  if (!ok) {
+  if (used == 0 || !DDE_PRED(lo)) {
     s_error[s] = 1;
     s_code[s] = -6; /* ERR_YLAG_FAIL */
-    hit.entry = nullptr;
-    hit.t_old = 0.0;
-    hit.h = 1.0;
-    return hit;
+    return false;
+  }
+  /* start from the window: the entry wanted is usually next to it */
+  const unsigned wn = s_wn[s];
+  if (wn > 0) {
+    const unsigned base = s_wbase[s];
+    if (st >= s_wtop[s]) {
+      const unsigned g = base + wn; /* exists: wtop is finite */
+      if (g > lo && g < hi) {
+        lo = g; /* its start time is wtop <= st */
+        if (g + 1 < hi) {
+          if (DDE_PRED(g + 1)) {
+            lo = g + 1;
+          } else {
+            hi = g + 1;
+          }
+        }
+      }
+    } else if (base > lo && base < hi) {
+      hi = base; /* st < wt[base] */
+      if (DDE_PRED(base - 1)) {
+        lo = base - 1;
+      }
+    }
   }
   while (hi - lo > 1) {
     const unsigned mid = lo + (hi - lo) / 2;
@@ -172,36 +286,57 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
       hi = mid;
     }
   }
-  s_hint[s] = lo;
-  /* stage the bracket [lo, lo + 1] */
-  const double *ea = DDE_ENTRY(lo);
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const double ta = ea[idx_t], ha = ea[idx_t + 1];
-  double tb = inf, tc = inf, hb = 1.0;
-  if (lo + 1 < count) {
-    const double *eb = DDE_ENTRY(lo + 1);
-    tb = sign * eb[idx_t];
-    hb = eb[idx_t + 1];
-    if (lo + 2 < count) {
-      tc = sign * DDE_ENTRY(lo + 2)[idx_t];
+#undef DDE_PRED
+  /* remember how far above the end of the step this query reached */
+  if (st - s_att_hi[s] > s_dq_hi[s]) {
+    s_dq_hi[s] = st - s_att_hi[s];
+  }
+  /* reload the window: entries lo .. lo + DDE_WIN - 1 as far as committed */
+  double top = pos_inf();
+  unsigned k = 0;
+#pragma unroll 1
+  for (int j = 0; j < DDE_WIN; ++j) {
+    if (lo + j < count) {
+      top = lag_window_load(s, lo + j);
+      k = j + 1;
+    } else {
+      s_wt[(lo + j) & (DDE_WIN - 1)][s] = pos_inf();
     }
   }
-#undef DDE_PRED
-#undef DDE_ENTRY
-  s_win[s] = lo;
-  s_win_ta[s] = sign * ta;
-  s_win_tb[s] = tb;
-  s_win_tc[s] = tc;
-  s_win_ha[s] = ha;
-  s_win_hb[s] = hb;
-  hit.entry = ea;
-  hit.t_old = ta;
-  hit.h = ha;
+  s_wbase[s] = lo;
+  s_wn[s] = k;
+  s_wtop[s] = top;
+  return true;
+}
+
+/* The entry a lag query at time t reads, src/dopri.c:742-769.  On failure
+ * obj->error / ERR_YLAG_FAIL are set and ok is false. */
+__device__ __forceinline__ LagHit find_time(int s, double t) {
+  const double sign = s_lag_u.sign;
+  const double st = sign * t; /* entries are ordered by sign * time */
+  LagHit hit;
+  unsigned base = s_wbase[s];
+  hit.ok = true;
+  if (!(s_wn[s] > 0 && st >= s_wt[base & (DDE_WIN - 1)][s] && st < s_wtop[s])) {
+    hit.ok = lag_window_miss(s, st);
+    base = s_wbase[s];
+  }
+  /* unused slots hold +inf, so this counts the entries that start at or before st */
+  unsigned j = 0;
+#pragma unroll
+  for (int k = 1; k < DDE_WIN; ++k) {
+    j += st >= s_wt[(base + k) & (DDE_WIN - 1)][s] ? 1u : 0u;
+  }
+  hit.idx = base + j;
+  const int w = (int) (hit.idx & (DDE_WIN - 1));
+  hit.t_old = sign * s_wt[w][s];
+  hit.h = s_wh[w][s];
   return hit;
 }
 
 /* Dense-output polynomial of one component; c points at the component's
- * first coefficient, coefficients are n apart. */
+ * first coefficient, coefficients are `n` doubles apart
+ * (src/dopri_5.c:120-127, src/dopri_853.c:369-380). */
 __device__ __forceinline__ double interp5(int n, double theta, double theta1,
                                           const double *c) {
   return c[0] + theta * (c[n] + theta1 * (c[2 * n] + theta * (c[3 * n] + theta1 * c[4 * n])));
@@ -213,9 +348,34 @@ __device__ __forceinline__ double interp853(int n, double theta, double theta1,
   return c[0] + theta * (c[n] + theta1 * (c[2 * n] + theta * (c[3 * n] + theta1 * tmp)));
 }
 
-__device__ __forceinline__ double interp_entry(const double *e, int order, int n,
-                                               double theta, double theta1, size_t i) {
-  return order == 5 ? interp5(n, theta, theta1, e + i) : interp853(n, theta, theta1, e + i);
+__device__ __forceinline__ double interp_entry(const double *c, int order, int stride,
+                                               double theta, double theta1) {
+  return order == 5 ? interp5(stride, theta, theta1, c) : interp853(stride, theta, theta1, c);
+}
+
+/* Components idx[0..nidx) (NULL: 0..nidx-1) of the dense output of the entry
+ * `hit` at time t, src/dopri.c:582-666.  Two copies so that the staged
+ * window is read with shared-memory loads and the ring with global ones. */
+template <class Index>
+__device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, const Index *idx,
+                                         size_t nidx, double *y) {
+  const int n = s_lag_u.n, order = s_lag_u.order;
+  const double theta = (t - hit.t_old) / hit.h;
+  const double theta1 = 1 - theta;
+  if (s_lag_u.staged) {
+    const int w = (int) (hit.idx & (DDE_WIN - 1));
+    const double *c = s_wc + (size_t) w * (order * n) * DDE_TPB + s;
+    for (size_t i = 0; i < nidx; ++i) {
+      const size_t comp = idx ? (size_t) idx[i] : i;
+      y[i] = interp_entry(c + comp * DDE_TPB, order, n * DDE_TPB, theta, theta1);
+    }
+  } else {
+    const double *c = ring_entry(s, hit.idx);
+    for (size_t i = 0; i < nidx; ++i) {
+      const size_t comp = idx ? (size_t) idx[i] : i;
+      y[i] = interp_entry(c + comp, order, n, theta, theta1);
+    }
+  }
 }
 
 } /* namespace dde */
@@ -228,13 +388,12 @@ static __device__ __forceinline__ double ylag_1(double t, size_t i) {
     return dde::s_y0[s][i];
   }
   const dde::LagHit hit = dde::find_time(s, t);
-  if (hit.entry == nullptr) {
+  if (!hit.ok) {
     return dde::na_real();
   }
-  const int n = dde::s_lag_u.n, order = dde::s_lag_u.order;
-  const double theta = (t - hit.t_old) / hit.h;
-  const double theta1 = 1 - theta;
-  return dde::interp_entry(hit.entry, order, n, theta, theta1, i);
+  double y;
+  dde::lag_eval<size_t>(s, hit, t, &i, 1, &y);
+  return y;
 }
 
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
@@ -247,13 +406,8 @@ static __device__ __forceinline__ void ylag_all(double t, double *y) {
     return;
   }
   const dde::LagHit hit = dde::find_time(s, t);
-  if (hit.entry != nullptr) {
-    const int order = dde::s_lag_u.order;
-    const double theta = (t - hit.t_old) / hit.h;
-    const double theta1 = 1 - theta;
-    for (int i = 0; i < n; ++i) {
-      y[i] = dde::interp_entry(hit.entry, order, n, theta, theta1, (size_t) i);
-    }
+  if (hit.ok) {
+    dde::lag_eval<size_t>(s, hit, t, nullptr, (size_t) n, y);
   }
 }
 
@@ -268,13 +422,8 @@ static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *i
     return;
   }
   const dde::LagHit hit = dde::find_time(s, t);
-  if (hit.entry != nullptr) {
-    const int n = dde::s_lag_u.n, order = dde::s_lag_u.order;
-    const double theta = (t - hit.t_old) / hit.h;
-    const double theta1 = 1 - theta;
-    for (size_t i = 0; i < nidx; ++i) {
-      y[i] = dde::interp_entry(hit.entry, order, n, theta, theta1, (size_t) idx[i]);
-    }
+  if (hit.ok) {
+    dde::lag_eval<Index>(s, hit, t, idx, nidx, y);
   }
 }
 

@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+# usage: tools/gpu_variants.sh tag lib1.so lib2.so ... : short bench of each library variant
+tag=$1; shift
+mkdir -p gpurun_out
+for lib in "$@"; do
+  echo "== $lib" >> gpurun_out/variants_$tag.log
+  DDE_B200_LIB=$PWD/$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline >> gpurun_out/variants_$tag.log 2>&1
+done
