@@ -80,6 +80,10 @@ SYMBOLS = [
     ("dde_difeq_batch_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     ("dde_difeq_batch_last_ms", C.c_double, [C.c_void_p]),
+    ("dde_device_count", C.c_int, []),
+    ("dde_dopri_batch_sharded", C.c_int, _DOPRI_BATCH_ARGS + [c_int32_p, _SZ]),
+    ("dde_difeq_batch_sharded", C.c_int, _DIFEQ_BATCH_ARGS + [c_int32_p, _SZ]),
+    ("dde_shard_range", None, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("dde_host_alloc", C.c_void_p, [_SZ]),
     ("dde_host_free", None, [C.c_void_p]),
     ("dde_pow_host", C.c_double, [C.c_double, C.c_double]),

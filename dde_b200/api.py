@@ -120,6 +120,18 @@ class DopriBatchResult:
         return strerror(self.code[j], self.t_last[j], self.n_history)
 
 
+def _device_list(devices):
+    """"all" -> None (every visible device); else an int32 array of indices."""
+    if isinstance(devices, str):
+        if devices != "all":
+            raise DdeError("'devices' must be None, \"all\" or a list of device indices")
+        return None
+    dev = np.ascontiguousarray(np.atleast_1d(devices), dtype=np.int32)
+    if dev.shape[0] == 0:
+        raise DdeError("'devices' must not be empty")
+    return dev
+
+
 def _prep_batch_inputs(y, parms, n_traj_hint=None):
     y = _f64(y, "y")
     if y.ndim == 1:
@@ -146,11 +158,13 @@ def _prep_batch_inputs(y, parms, n_traj_hint=None):
 def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_size_min=0.0,
                 step_size_max=math.inf, step_size_initial=0.0, step_max_n=100000,
                 step_size_min_allow=False, tcrit=None, method="dopri5", stiff_check=0,
-                n_history=0, grow_history=False, return_initial=True):
+                n_history=0, grow_history=False, return_initial=True, devices=None):
     """Integrate n_traj independent trajectories of one compiled model.
 
     One call == the reference's `dopri()` run once per row of `y` (and per row
     of `parms`), concurrently on the GPU.  Arguments as R/dopri.R:293-310.
+    `devices`: None = the current device; "all" or a list of device indices =
+    shard the trajectories over those GPUs (dde_dopri_batch_sharded).
     """
     lib = _lib.load()
     y, parms_arr, n_traj, n, n_parms, stride = _prep_batch_inputs(y, parms)
@@ -167,11 +181,15 @@ def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, st
     code = np.empty((n_traj,), dtype=np.int32)
     t_last = np.empty((n_traj,), dtype=np.float64)
     step_size = np.empty((n_traj,), dtype=np.float64)
-    rc = lib.dde_dopri_batch(func.encode(), C.byref(ctl), n, n_out, n_traj, _dp(y),
-                             _dp(parms_arr) if n_parms else None, n_parms, stride, _dp(times),
-                             times.shape[0], _dp(tc), 0 if tc is None else tc.shape[0],
-                             _dp(y_out), _dp(out), _ip(stats), _ip(code), _dp(t_last),
-                             _dp(step_size))
+    args = [func.encode(), C.byref(ctl), n, n_out, n_traj, _dp(y),
+            _dp(parms_arr) if n_parms else None, n_parms, stride, _dp(times), times.shape[0],
+            _dp(tc), 0 if tc is None else tc.shape[0], _dp(y_out), _dp(out), _ip(stats),
+            _ip(code), _dp(t_last), _dp(step_size)]
+    if devices is None:
+        rc = lib.dde_dopri_batch(*args)
+    else:
+        dev = _device_list(devices)
+        rc = lib.dde_dopri_batch_sharded(*args, _ip(dev), 0 if dev is None else dev.shape[0])
     if rc != 0:
         raise DdeError(_lib.last_error())
     return DopriBatchResult(y_out, out, stats, code, t_last, step_size, times, int(n_history))
@@ -359,7 +377,8 @@ def _steps(steps):
     return np.ascontiguousarray(steps, dtype=np.uint64)
 
 
-def _difeq_call(y2d, steps, target, parms_arr, n_parms, stride, n_out, n_history, return_initial):
+def _difeq_call(y2d, steps, target, parms_arr, n_parms, stride, n_out, n_history, return_initial,
+                devices=None):
     lib = _lib.load()
     n_rep, n = y2d.shape
     if n_history > 0 and n_history < 2:
@@ -369,11 +388,14 @@ def _difeq_call(y2d, steps, target, parms_arr, n_parms, stride, n_out, n_history
     out = np.empty((n_rep, nt, n_out)) if n_out > 0 else None
     code = np.empty((n_rep,), dtype=np.int32)
     y_final = np.empty((n_rep, n))
-    rc = lib.dde_difeq_batch(target.encode(), n, n_out, n_rep, _dp(y2d),
-                             _dp(parms_arr) if n_parms else None, n_parms, stride,
-                             steps.ctypes.data_as(c_uint64_p), steps.shape[0], int(n_history),
-                             int(bool(return_initial)), _dp(y_out), _dp(out), _ip(code),
-                             _dp(y_final))
+    args = [target.encode(), n, n_out, n_rep, _dp(y2d), _dp(parms_arr) if n_parms else None,
+            n_parms, stride, steps.ctypes.data_as(c_uint64_p), steps.shape[0], int(n_history),
+            int(bool(return_initial)), _dp(y_out), _dp(out), _ip(code), _dp(y_final)]
+    if devices is None:
+        rc = lib.dde_difeq_batch(*args)
+    else:
+        dev = _device_list(devices)
+        rc = lib.dde_difeq_batch_sharded(*args, _ip(dev), 0 if dev is None else dev.shape[0])
     if rc != 0:
         raise DdeError(_lib.last_error())
     return y_out, out, code, y_final
@@ -406,7 +428,7 @@ def difeq(y, steps, target, parms=None, *, n_out=0, n_history=0, grow_history=Fa
 
 def difeq_replicate(n, y, steps, target, parms=None, *, n_out=0, n_history=0, grow_history=False,
                     return_by_column=True, return_initial=True, return_step=True,
-                    return_output_with_y=True, return_minimal=False):
+                    return_output_with_y=True, return_minimal=False, devices=None):
     """Replicated difference-equation runs; R/difeq_replicate.R:47-152.
 
     `y` is one initial state (used for all n replicates), or [n, n_eq] with one
@@ -435,7 +457,7 @@ def difeq_replicate(n, y, steps, target, parms=None, *, n_out=0, n_history=0, gr
     st = _steps(steps)
     y2d, parms_arr, _, n_eq, n_parms, stride = _prep_batch_inputs(y2d, parms)
     y_out, out, code, _ = _difeq_call(y2d, st, target, parms_arr, n_parms, stride, n_out,
-                                      n_history, return_initial)
+                                      n_history, return_initial, devices)
     blocks = []
     if return_step:
         s = (st if return_initial else st[1:]).astype(np.float64)

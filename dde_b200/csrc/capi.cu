@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1184,6 +1185,134 @@ int dde_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep, con
   rc = rc ? rc : dde_difeq_batch_download(b, y_out, out, code, y_final);
   dde_difeq_batch_free(b);
   return rc;
+}
+
+/* ---- multi-GPU sharding ------------------------------------------------------------ */
+
+int dde_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    (void) cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+void dde_shard_range(size_t n_total, size_t world, size_t rank, size_t *first, size_t *count) {
+  if (world == 0) {
+    world = 1;
+  }
+  const size_t base = n_total / world, extra = n_total % world;
+  const size_t f = rank * base + (rank < extra ? rank : extra);
+  if (first) *first = f;
+  if (count) *count = base + (rank < extra ? 1 : 0);
+}
+
+} /* extern "C" */
+
+namespace {
+
+/* Run `work(shard, first, count)` for every non-empty shard on its own thread
+   with that shard's device current; collect the first failure. */
+template <class Work>
+int run_sharded(size_t n_total, const int32_t *devices, size_t n_devices, Work work) {
+  std::vector<int> devs;
+  if (devices != nullptr && n_devices > 0) {
+    devs.assign(devices, devices + n_devices);
+  } else {
+    const int count = dde_device_count();
+    for (int d = 0; d < count; ++d) {
+      devs.push_back(d);
+    }
+  }
+  if (devs.empty()) {
+    return fail("no CUDA device available: dde_b200 has no CPU fallback");
+  }
+  const int visible = dde_device_count();
+  for (int d : devs) {
+    if (d < 0 || d >= visible) {
+      return fail("device %d is not visible (%d devices)", d, visible);
+    }
+  }
+  const size_t world = devs.size();
+  std::vector<int> rc(world, 0);
+  std::vector<std::string> msg(world);
+  std::vector<std::thread> threads;
+  for (size_t r = 0; r < world; ++r) {
+    size_t first = 0, count = 0;
+    dde_shard_range(n_total, world, r, &first, &count);
+    if (count == 0) {
+      continue;
+    }
+    threads.emplace_back([&, r, first, count]() {
+      if (cudaSetDevice(devs[r]) != cudaSuccess) {
+        (void) cudaGetLastError();
+        rc[r] = 1;
+        msg[r] = "cudaSetDevice failed";
+        return;
+      }
+      rc[r] = work(first, count);
+      if (rc[r] != 0) {
+        msg[r] = g_last_error; /* thread-local */
+      }
+    });
+  }
+  for (std::thread &t : threads) {
+    t.join();
+  }
+  for (size_t r = 0; r < world; ++r) {
+    if (rc[r] != 0) {
+      return fail("shard %zu (device %d): %s", r, devs[r], msg[r].c_str());
+    }
+  }
+  return 0;
+}
+
+template <class T>
+T *offset(T *p, size_t k) {
+  return p == nullptr ? nullptr : p + k;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int dde_dopri_batch_sharded(const char *model, const dde_dopri_control *ctl, size_t n,
+                            size_t n_out, size_t n_traj, const double *y0, const double *parms,
+                            size_t n_parms, size_t parms_stride, const double *times,
+                            size_t n_times, const double *tcrit, size_t n_tcrit, double *y_out,
+                            double *out, int32_t *stats, int32_t *code, double *t_last,
+                            double *step_size, const int32_t *devices, size_t n_devices) {
+  if (ctl == nullptr || n_times < 2) {
+    return fail("ctl must not be NULL and at least two times must be given");
+  }
+  const size_t nt = ctl->return_initial ? n_times : n_times - 1;
+  return run_sharded(n_traj, devices, n_devices, [&](size_t first, size_t count) {
+    return dde_dopri_batch(model, ctl, n, n_out, count, offset(y0, first * n),
+                           offset(parms, first * parms_stride), n_parms, parms_stride, times,
+                           n_times, tcrit, n_tcrit, offset(y_out, first * n * nt),
+                           offset(out, first * n_out * nt), offset(stats, first * 4),
+                           offset(code, first), offset(t_last, first), offset(step_size, first));
+  });
+}
+
+int dde_difeq_batch_sharded(const char *model, size_t n, size_t n_out, size_t n_rep,
+                            const double *y0, const double *parms, size_t n_parms,
+                            size_t parms_stride, const uint64_t *steps, size_t n_steps,
+                            size_t n_history, int32_t return_initial, double *y_out, double *out,
+                            int32_t *code, double *y_final, const int32_t *devices,
+                            size_t n_devices) {
+  if (n_steps < 2) {
+    return fail("At least two steps must be given");
+  }
+  const size_t nt = return_initial ? n_steps : n_steps - 1;
+  return run_sharded(n_rep, devices, n_devices, [&](size_t first, size_t count) {
+    return dde_difeq_batch(model, n, n_out, count, offset(y0, first * n),
+                           offset(parms, first * parms_stride), n_parms, parms_stride, steps,
+                           n_steps, n_history, return_initial, offset(y_out, first * n * nt),
+                           offset(out, first * n_out * nt), offset(code, first),
+                           offset(y_final, first * n));
+  });
 }
 
 } /* extern "C" */

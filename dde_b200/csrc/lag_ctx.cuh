@@ -94,6 +94,15 @@ __shared__ double s_att_hi[DDE_TPB]; /* sign * (t + h) of the attempt in progres
 __shared__ double s_dq_hi[DDE_TPB];  /* highest query seen, relative to s_att_hi; -inf: none yet */
 extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
 
+#ifdef DDE_LAG_STATS
+/* debug build only: [0] misses above, [1] misses below, [2] misses on an empty
+   window, [3] entries appended by lag_window_ensure, [4] failures, [5] bisection probes */
+static __device__ unsigned long long dde_lag_stats[8];
+#define DDE_LAG_COUNT(i) atomicAdd(&dde_lag_stats[i], 1ULL)
+#else
+#define DDE_LAG_COUNT(i) ((void) 0)
+#endif
+
 __device__ __forceinline__ double na_real() {
   /* R's NA_real_ (quiet NaN, low word 1954); payloads do not survive device
      arithmetic, parity treats every NaN alike */
@@ -170,6 +179,7 @@ __device__ __forceinline__ void lag_window_ensure(int s, double att_hi) {
       ++base;
       --wn;
     }
+    DDE_LAG_COUNT(3);
     const double top = lag_window_load(s, base + wn); /* overwrites the dropped slot */
     s_wbase[s] = base;
     s_wn[s] = wn + 1;
@@ -251,14 +261,19 @@ static __device__ __noinline__ bool lag_window_miss(int s, double st) {
 #define DDE_PRED(j) (sign * ring_entry(s, (j))[idx_t] <= st)
   unsigned lo = count - used, hi = count; /* want: pred(lo) holds, pred(hi) fails */
   if (used == 0 || !DDE_PRED(lo)) {
+    DDE_LAG_COUNT(4);
     s_error[s] = 1;
     s_code[s] = -6; /* ERR_YLAG_FAIL */
     return false;
   }
   /* start from the window: the entry wanted is usually next to it */
   const unsigned wn = s_wn[s];
+  if (wn == 0) {
+    DDE_LAG_COUNT(2);
+  }
   if (wn > 0) {
     const unsigned base = s_wbase[s];
+    DDE_LAG_COUNT(st >= s_wtop[s] ? 0 : 1);
     if (st >= s_wtop[s]) {
       const unsigned g = base + wn; /* exists: wtop is finite */
       if (g > lo && g < hi) {
@@ -280,6 +295,7 @@ static __device__ __noinline__ bool lag_window_miss(int s, double st) {
   }
   while (hi - lo > 1) {
     const unsigned mid = lo + (hi - lo) / 2;
+    DDE_LAG_COUNT(5);
     if (DDE_PRED(mid)) {
       lo = mid;
     } else {

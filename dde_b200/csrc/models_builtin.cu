@@ -30,3 +30,12 @@ DDE_REGISTER_DIFEQ(additive,  additive,  0, -1,     -1)
 DDE_REGISTER_DIFEQ(fibonacci, fibonacci, 5, -1,     0)
 DDE_REGISTER_DIFEQ(fib_out,   fib_out,   1, -1,     1)
 DDE_REGISTER_DIFEQ(sir_delay, sir_delay, 3, 2,      0)
+
+#ifdef DDE_LAG_STATS
+/* debug build only: read and clear the lag-window counters of this module */
+extern "C" void dde_debug_lag_stats(unsigned long long *out) {
+  unsigned long long zero[8] = {0};
+  cudaMemcpyFromSymbol(out, dde::dde_lag_stats, sizeof zero);
+  cudaMemcpyToSymbol(dde::dde_lag_stats, zero, sizeof zero);
+}
+#endif

@@ -230,6 +230,38 @@ int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
                              int32_t *code, double *y_final);
 double dde_difeq_batch_last_ms(dde_difeq_batch_t *b);
 
+/* ---- multi-GPU ---------------------------------------------------------------- */
+
+/* Trajectories are independent, so a batch shards over the GPUs of one box
+ * with no communication between them: contiguous blocks of trajectory
+ * indices, one host thread and one stream per device, every device copying
+ * its results straight into its slice of the caller's arrays (layouts above,
+ * so concatenation is free).  devices == NULL: all visible devices.  Same
+ * arguments and semantics as dde_dopri_batch / dde_difeq_batch otherwise; the
+ * serial loop they replace is src/r_difeq.c:94-103. */
+int dde_device_count(void);
+int dde_dopri_batch_sharded(const char *model, const dde_dopri_control *ctl,
+                            size_t n, size_t n_out, size_t n_traj,
+                            const double *y0, const double *parms,
+                            size_t n_parms, size_t parms_stride,
+                            const double *times, size_t n_times,
+                            const double *tcrit, size_t n_tcrit, double *y_out,
+                            double *out, int32_t *stats, int32_t *code,
+                            double *t_last, double *step_size,
+                            const int32_t *devices, size_t n_devices);
+int dde_difeq_batch_sharded(const char *model, size_t n, size_t n_out,
+                            size_t n_rep, const double *y0,
+                            const double *parms, size_t n_parms,
+                            size_t parms_stride, const uint64_t *steps,
+                            size_t n_steps, size_t n_history,
+                            int32_t return_initial, double *y_out, double *out,
+                            int32_t *code, double *y_final,
+                            const int32_t *devices, size_t n_devices);
+/* The block of a batch of n_total that shard `rank` of `world` owns:
+ * [*first, *first + *count).  Blocks differ in size by at most one. */
+void dde_shard_range(size_t n_total, size_t world, size_t rank, size_t *first,
+                     size_t *count);
+
 /* ---- host memory ------------------------------------------------------------ */
 
 /* Page-locked host buffers (cudaHostAlloc) so the upload/download calls above

@@ -1,0 +1,117 @@
+"""The C-ABI shared library: it loads, exports every symbol include/dde_b200.h
+declares, its host-only entry points behave like the reference's glue, and
+without a GPU every solver entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import dde_b200
+from dde_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    text = (ROOT / "include" / "dde_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dde_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), "libdde_b200.so does not export %s" % name
+    # and the ctypes table binds exactly the header's list
+    assert sorted(n for n, _, _ in _lib.SYMBOLS) == names
+
+
+def test_model_header_is_source_compatible():
+    # the eight history functions of inst/include/dde/dde.h:3-13, same signatures
+    text = (ROOT / "include" / "dde" / "dde.h").read_text()
+    for proto in ("double ylag_1(double t, size_t i);", "void ylag_all(double t, double *y);",
+                  "void ylag_vec(double t, const size_t *idx, size_t nidx, double *y);",
+                  "void ylag_vec_int(double t, const int *idx, size_t nidx, double *y);",
+                  "double yprev_1(int step, size_t i);", "void yprev_all(int step, double *y);",
+                  "void yprev_vec(int step, const size_t *idx, size_t nidx, double *y);",
+                  "void yprev_vec_int(int step, const int *idx, size_t nidx, double *y);"):
+        assert proto in text
+
+
+def test_control_defaults():
+    lib = _lib.load()
+    for method, name in ((0, "dopri5"), (1, "dopri853")):
+        ctl = _lib.DopriControl()
+        lib.dde_dopri_control_default(C.byref(ctl), method)
+        # src/dopri.c:64-87, R/dopri.R:293-310
+        assert (ctl.atol, ctl.rtol) == (1e-6, 1e-6)
+        assert ctl.step_max_n == 100000 and ctl.stiff_check == 0 and ctl.n_history == 0
+        assert ctl.method == method and ctl.return_initial == 1 and ctl.grow_history == 0
+        assert ctl.step_size_initial == 0.0 and ctl.step_size_min_allow == 0
+
+
+def test_error_strings_are_the_reference_ones():
+    # src/r_dopri.c:264-297
+    assert dde_b200.strerror(-1) == "Initialisation failure: Beginning and end times are the same"
+    assert dde_b200.strerror(-2) == "Initialisation failure: Times have inconsistent sign"
+    assert dde_b200.strerror(-3, 1.5) == "Integration failure: too many steps (at t = 1.50000)"
+    assert dde_b200.strerror(-4, 2.0) == "Integration failure: step size too small (at t = 2.00000)"
+    assert dde_b200.strerror(-5, 2.0) == "Integration failure: step size vanished (at t = 2.00000)"
+    assert dde_b200.strerror(-6, 3.0, 0) == \
+        "Integration failure: can't use ylag in model with no history"
+    assert dde_b200.strerror(-6, 3.0, 10) == \
+        "Integration failure: did not find time in history (at t = 3.00000)"
+    assert dde_b200.strerror(-7, 0.25) == "Integration failure: problem became stiff (at t = 0.25000)"
+    assert dde_b200.strerror(-8) == "non-finite derivative at initial time"  # src/dopri.c:333
+    assert "did not find step" in dde_b200.strerror(-9)  # src/difeq.c:268
+    assert dde_b200.strerror(1) == "OK"
+
+
+def test_model_registry():
+    names = dde_b200.models()
+    for m in ("lorenz", "rossler", "mackey_glass", "seir", "seir_int", "exponential",
+              "delayed_growth", "logistic", "fibonacci", "sir_delay"):
+        assert m in names
+    lib = _lib.load()
+    kind, n, npar, nout = C.c_int32(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert lib.dde_model_info(b"mackey_glass", C.byref(kind), C.byref(n), C.byref(npar),
+                              C.byref(nout)) == 0
+    assert (kind.value & 1) and n.value == 1 and npar.value == 3
+    assert lib.dde_model_info(b"no_such_model", None, None, None, None) != 0
+    assert "unknown model" in _lib.last_error()
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(dde_b200.DdeError, match="no CUDA device|CUDA"):
+        dde_b200.dopri_batch([[10.0, 1.0, 1.0]], [0.0, 1.0], "lorenz", [10.0, 28.0, 8.0 / 3.0])
+    with pytest.raises(dde_b200.DdeError, match="no CUDA device|CUDA"):
+        dde_b200.difeq([0.1], 5, "logistic", [1.5])
+
+
+def test_argument_validation_matches_the_reference():
+    # these are rejected before any device work
+    with pytest.raises(dde_b200.DdeError, match="At least two times"):
+        dde_b200.dopri_batch([[1.0]], [0.0], "exponential", [[1.0]])
+    with pytest.raises(dde_b200.DdeError, match="must be one of"):
+        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[1.0]], method="rk4")
+    with pytest.raises(dde_b200.DdeError, match="n_history must be at least 2"):
+        dde_b200.difeq([1.0], 5, "fib_out", None, n_out=1, n_history=1)
+    with pytest.raises(dde_b200.DdeError, match="steps must be positive"):
+        dde_b200.difeq([0.1], [-1, 3], "logistic", [1.5])
+    with pytest.raises(dde_b200.DdeError):
+        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "no_such_model", [[1.0]])
+    with pytest.raises(dde_b200.DdeError, match="grow_history"):
+        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[1.0]], grow_history=True)

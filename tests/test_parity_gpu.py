@@ -259,3 +259,25 @@ def test_c4_delayed_sir(backend):
     single = dde_b200.difeq(y0[5], [0, 2000], model, parms[5], n_history=16)
     many = dde_b200.difeq_replicate(2048, y0, [0, 2000], model, parms, n_history=16)
     assert_bits_equal(np.asarray(single), np.asarray(many)[:, :, 5], "replicate slice")
+
+
+# ---- multi-GPU sharding ---------------------------------------------------------
+
+
+def test_sharded_equals_single_device(backend):
+    # dde_dopri_batch_sharded / dde_difeq_batch_sharded over every visible GPU
+    # (one here, eight on a full box): same results as one device, row for row
+    model, y0, parms, times, kw = workloads.mackey_glass(1000)
+    one = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+    for devices in ([0], "all"):
+        many = dde_b200.dopri_batch(y0, times, model, parms, devices=devices, **kw)
+        np.testing.assert_array_equal(one.statistics, many.statistics)
+        np.testing.assert_array_equal(one.code, many.code)
+        assert_bits_equal(one.y, many.y, "y")
+    model, y0, parms, steps, kw = workloads.sir_delay(500, n_steps=300)
+    a = dde_b200.difeq_replicate(500, y0, steps, model, parms, **kw)
+    b = dde_b200.difeq_replicate(500, y0, steps, model, parms, devices="all", **kw)
+    assert_bits_equal(np.asarray(a), np.asarray(b), "difeq")
+    with pytest.raises(dde_b200.DdeError, match="not visible"):
+        dde_b200.dopri_batch(y0[:, :1], times, "mackey_glass", parms[:, :1].repeat(3, 1),
+                             devices=[99], method="dopri853", n_history=8)
