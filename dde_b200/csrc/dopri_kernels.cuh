@@ -47,7 +47,11 @@
 namespace dde {
 
 #ifndef DDE_MIN_BLOCKS
-#define DDE_MIN_BLOCKS 1 /* resident blocks per SM the register allocation must allow */
+/* Resident blocks per SM the register allocation of a scalar model (n = 1)
+   must allow: 3 x 128 threads at <= 168 registers; the staged window
+   (DDE_WIN 6) is sized to the shared memory that leaves per block.  Larger
+   compile-time n keep their whole state in registers instead (1 block). */
+#define DDE_MIN_BLOCKS 3
 #endif
 #ifndef DDE_DYN_MAXN
 #define DDE_DYN_MAXN 16 /* largest n of a model compiled with runtime n */
@@ -93,7 +97,7 @@ struct DopriArgs {
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 template <class M, int METHOD>
-__global__ void __launch_bounds__(DDE_TPB, DDE_MIN_BLOCKS) dopri_tpt_kernel(const DopriArgs a) {
+__global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dopri_tpt_kernel(const DopriArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE_MIN_BLOCKS) dopri_tpt_kernel(cons
       ++n_step;
       if (a.n_history > 0) {
         /* top up the staged lag window while the warp is in step */
-        lag_window_ensure(s, sign * (t + h));
+        lag_window_ensure<ORDER * NMAX>(s, sign * t, sign * (t + h));
       }
     }
 
@@ -456,6 +460,9 @@ __global__ void __launch_bounds__(DDE_TPB, DDE_MIN_BLOCKS) dopri_tpt_kernel(cons
       }
 
       /* -- 2. dopri_eval, src/dopri.c:831-835: the one hot copy of the model -- */
+      if (a.n_history > 0) {
+        s_tt[s] = sign * tt; /* lag look-ups learn their offset from it */
+      }
       M::deriv((size_t) n, tt, yin, kt, p);
       ++n_eval;
 

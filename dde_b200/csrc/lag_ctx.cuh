@@ -30,13 +30,18 @@
 #define DDE_LAG_CTX_CUH
 
 #include <stdint.h>
+#ifdef DDE_LAG_STATS
+#include <stdio.h>
+#endif
 
 #include "dde_math.h"
 
 #ifndef DDE_TPB
 #define DDE_TPB 128 /* threads per block of the thread-per-trajectory kernels */
 #endif
-#define DDE_WIN 4 /* entries in a thread's staged lag window (power of two) */
+#ifndef DDE_WIN
+#define DDE_WIN 6 /* entries in a thread's staged lag window */
+#endif
 /* shared memory a block may spend on staged coefficients; above this the
    window keeps only step times and sizes and coefficients are read from HBM */
 #define DDE_WIN_COEF_BUDGET (72 * 1024)
@@ -66,9 +71,9 @@ __shared__ long long s_step[DDE_TPB];      /* difeq: obj->step */
 __shared__ long long s_step0[DDE_TPB];     /* difeq: obj->step0 */
 
 /* The staged lag window ("shared-memory staging of the bracketing history
- * steps"): DDE_WIN consecutive committed entries base .. base + wn - 1 of the
- * thread's ring, held in shared memory -- sign-adjusted start time and step
- * size always, the dense-output coefficients too when they fit -- entry
+ * steps"): up to DDE_WIN consecutive committed entries base .. base + wn - 1
+ * of the thread's ring, held in shared memory -- sign-adjusted start time and
+ * step size always, the dense-output coefficients too when they fit -- entry
  * `idx` in slot idx % DDE_WIN.  wtop is the (exclusive) upper end of the
  * window: the start time of entry base + wn, or +inf while the window's last
  * entry is the newest committed one (a query beyond it extrapolates that
@@ -76,30 +81,40 @@ __shared__ long long s_step0[DDE_TPB];     /* difeq: obj->step0 */
  * start time so that the look-up needs no bounds.  A query inside
  * [wt[base], wtop) is served without touching HBM and without a search.
  *
- * The window follows the lag by itself: the integrator tops it up once per
- * step attempt (lag_window_ensure), while all lanes of a warp are in step, up
- * to the highest time the previous attempts queried relative to the end of
- * the step (dq_hi, learnt from misses); newly committed entries are appended
- * straight from registers when the window sits at the head of the ring.  A
- * query outside the window takes the slow path: bisection over the step
- * times stored in the ring (the search path is free, only its result is
- * defined: src/dopri.c:742-769), then a reload of the
- * window at the entry found. */
+ * The window follows the lag by itself.  The integrator tops it up once per
+ * step attempt (lag_window_ensure), while all lanes of a warp are in step,
+ * so that it covers [sign t + dq_lo, sign (t + h) + dq_hi], where dq_lo and
+ * dq_hi bound the offsets (query time - evaluation time) seen so far (learnt
+ * from misses; for a constant lag tau both are -tau after the first miss).  Newly committed entries are appended straight from registers when
+ * the window sits at the head of the ring.  A query outside the window takes
+ * the slow path (lag_window_miss): the entry is found by bisection over the
+ * step times stored in the ring, starting next to the window (the search
+ * path is free, only its result is defined: src/dopri.c:742-769, SURVEY.md
+ * A.2#11); the window then moves by one entry if it can, restarts at the
+ * entry if it was far away, or stays put while the query is answered from the
+ * ring directly (a range wider than the window would otherwise thrash it). */
 __shared__ double s_wt[DDE_WIN][DDE_TPB];
 __shared__ double s_wh[DDE_WIN][DDE_TPB];
 __shared__ double s_wtop[DDE_TPB];
 __shared__ unsigned s_wbase[DDE_TPB];
 __shared__ unsigned s_wn[DDE_TPB];
+__shared__ double s_att_lo[DDE_TPB]; /* sign * t of the attempt in progress */
 __shared__ double s_att_hi[DDE_TPB]; /* sign * (t + h) of the attempt in progress */
-__shared__ double s_dq_hi[DDE_TPB];  /* highest query seen, relative to s_att_hi; -inf: none yet */
+__shared__ unsigned s_hint[DDE_TPB]; /* entry the last search ended at */
+__shared__ double s_tt[DDE_TPB];     /* sign * time of the RHS evaluation in progress */
+__shared__ double s_dq_lo[DDE_TPB];  /* lowest / highest query seen, relative to the time of the */
+__shared__ double s_dq_hi[DDE_TPB];  /* evaluation that made it (+inf / -inf: none yet) */
 extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
 
 #ifdef DDE_LAG_STATS
 /* debug build only: [0] misses above, [1] misses below, [2] misses on an empty
-   window, [3] entries appended by lag_window_ensure, [4] failures, [5] bisection probes */
+   window, [3] entries appended by lag_window_ensure, [4] failures, [5] ring
+   probes of the search, [6] queries answered from the ring directly */
 static __device__ unsigned long long dde_lag_stats[8];
 #define DDE_LAG_COUNT(i) atomicAdd(&dde_lag_stats[i], 1ULL)
+#define DDE_LAG_TRACE(...) ((void) 0)
 #else
+#define DDE_LAG_TRACE(...) ((void) 0)
 #define DDE_LAG_COUNT(i) ((void) 0)
 #endif
 
@@ -133,58 +148,117 @@ __device__ __forceinline__ void lag_window_reset(int s) {
   s_wtop[s] = pos_inf();
   s_wbase[s] = 0;
   s_wn[s] = 0;
+  s_hint[s] = 0;
+  s_att_lo[s] = 0.0;
   s_att_hi[s] = 0.0;
+  s_tt[s] = 0.0;
+  s_dq_lo[s] = pos_inf();
   s_dq_hi[s] = -pos_inf();
 }
 
-/* Copy committed entry idx from the ring into its window slot.  Returns the
- * sign-adjusted start time of the entry after it, +inf if there is none. */
+/* Copy committed entry idx from the ring into its window slot: all loads are
+ * issued before the first store, one round trip.  Returns the sign-adjusted
+ * start time of the entry after it, +inf if there is none. */
+template <int NCOEF_MAX>
 __device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
   const int hl = s_lag_u.hl;
   const int nc = hl - 2;
   const double sign = s_lag_u.sign;
   const unsigned count = s_count[s];
   const double *e = ring_entry(s, idx);
-  const int w = (int) (idx & (DDE_WIN - 1));
+  const int w = (int) (idx % DDE_WIN);
   double top = pos_inf();
   if (idx + 1 < count) {
     top = sign * ring_entry(s, idx + 1)[nc];
   }
-  s_wt[w][s] = sign * e[nc];
-  s_wh[w][s] = e[nc + 1];
+  const double te = e[nc], he = e[nc + 1];
   if (s_lag_u.staged) {
     double *dst = s_wc + (size_t) w * nc * DDE_TPB + s;
-    for (int c = 0; c < nc; ++c) {
-      dst[(size_t) c * DDE_TPB] = e[c];
+    if (NCOEF_MAX > 0) {
+      double c[NCOEF_MAX > 0 ? NCOEF_MAX : 1];
+#pragma unroll
+      for (int k = 0; k < NCOEF_MAX; ++k) {
+        if (k < nc) {
+          c[k] = e[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NCOEF_MAX; ++k) {
+        if (k < nc) {
+          dst[(size_t) k * DDE_TPB] = c[k];
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < nc; ++k) {
+        dst[(size_t) k * DDE_TPB] = e[k];
+      }
     }
   }
+  s_wt[w][s] = sign * te;
+  s_wh[w][s] = he;
   return top;
 }
 
-/* Once per step attempt, all lanes together: extend the window upwards until
- * it covers sign * (t + h) + dq_hi, dropping entries from its lower end as
- * needed.  Purely a prefetch: any query it fails to anticipate still finds
- * its entry through the slow path. */
-__device__ __forceinline__ void lag_window_ensure(int s, double att_hi) {
+/* drop the window's lowest entry */
+__device__ __forceinline__ void lag_window_evict(int s, unsigned &base, unsigned &wn) {
+  s_wt[base % DDE_WIN][s] = pos_inf();
+  ++base;
+  --wn;
+}
+
+/* Once per step attempt, all lanes together: slide the window so that it
+ * starts at the entry holding the lowest query expected and reaches the
+ * highest one (or is full).  Purely a prefetch: any query it fails to
+ * anticipate still finds its entry through the slow path. */
+template <int NCOEF_MAX>
+__device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double att_hi) {
+  s_att_lo[s] = att_lo;
   s_att_hi[s] = att_hi;
-  const double need = att_hi + s_dq_hi[s];
+  const double need_hi = att_hi + s_dq_hi[s];
+  const double need_lo = att_lo + s_dq_lo[s];
+  if (!(need_lo <= need_hi)) {
+    return; /* nothing learnt yet */
+  }
+  unsigned wn = s_wn[s];
+  if (wn == 0) {
+    return;
+  }
+  unsigned base = s_wbase[s];
+  /* 1. drop the entries no query of this step reaches (an entry ends where the
+        next one starts); shared memory only */
 #pragma unroll 1
-  for (int it = 0; it < DDE_WIN; ++it) {
-    unsigned wn = s_wn[s];
-    if (!(wn > 0 && need >= s_wtop[s])) {
-      break;
-    }
-    unsigned base = s_wbase[s];
+  while (wn > 1 && s_wt[(base + 1) % DDE_WIN][s] <= need_lo) {
+    lag_window_evict(s, base, wn);
+  }
+  /* 2. extend upwards; lanes load in the same iterations */
+  double wtop = s_wtop[s];
+#pragma unroll 1
+  while (need_hi >= wtop && wn < DDE_WIN) {
+    DDE_LAG_COUNT(3);
+    wtop = lag_window_load<NCOEF_MAX>(s, base + wn);
+    ++wn;
+  }
+  /* 3. the window starts too late (a restart, a step back): make room at the
+        top and extend downwards */
+  const unsigned count = s_count[s];
+  const unsigned tail = count > (unsigned) s_lag_u.cap ? count - (unsigned) s_lag_u.cap : 0u;
+#pragma unroll 1
+  for (int it = 0; it < DDE_WIN && need_lo < s_wt[base % DDE_WIN][s] && base > tail; ++it) {
     if (wn == DDE_WIN) {
-      ++base;
+      const int top_slot = (int) ((base + wn - 1) % DDE_WIN);
+      wtop = s_wt[top_slot][s];
+      s_wt[top_slot][s] = pos_inf();
       --wn;
     }
     DDE_LAG_COUNT(3);
-    const double top = lag_window_load(s, base + wn); /* overwrites the dropped slot */
-    s_wbase[s] = base;
-    s_wn[s] = wn + 1;
-    s_wtop[s] = top;
+    --base;
+    (void) lag_window_load<NCOEF_MAX>(s, base);
+    ++wn;
   }
+  s_wbase[s] = base;
+  s_wn[s] = wn;
+  s_wtop[s] = wtop;
 }
 
 /* Bookkeeping after the integrating thread has written the head entry to
@@ -205,9 +279,7 @@ __device__ __forceinline__ void ring_advance(int s, int cap, const double *hd, i
   unsigned wn = s_wn[s], base = s_wbase[s];
   const unsigned tail = count > (unsigned) cap ? count - (unsigned) cap : 0u;
   if (wn > 0 && base < tail) {
-    s_wt[base & (DDE_WIN - 1)][s] = pos_inf();
-    ++base;
-    --wn;
+    lag_window_evict(s, base, wn);
     s_wbase[s] = base;
     s_wn[s] = wn;
   }
@@ -225,7 +297,7 @@ __device__ __forceinline__ void ring_advance(int s, int cap, const double *hd, i
     }
   }
   if (append) {
-    const int w = (int) (newest & (DDE_WIN - 1));
+    const int w = (int) (newest % DDE_WIN);
     s_wt[w][s] = st_old;
     s_wh[w][s] = h;
     if (s_lag_u.staged) {
@@ -244,85 +316,122 @@ __device__ __forceinline__ void ring_advance(int s, int cap, const double *hd, i
 
 struct LagHit {
   bool ok;         /* false: no entry (ERR_YLAG_FAIL recorded) */
+  bool from_ring;  /* read the coefficients from the ring, not from the window */
   unsigned idx;    /* logical index of the entry */
   double t_old, h; /* its start time and step */
 };
 
-/* Slow path of the look-up: the last committed entry whose time is <= t
- * (>= t when integrating backwards), src/dopri.c:742-769, by bisection over
- * the ring, then the window is reloaded starting at that entry.  Returns
- * false after recording ERR_YLAG_FAIL when there is no such entry. */
-static __device__ __noinline__ bool lag_window_miss(int s, double st) {
+/* Slow path of the look-up, for a query outside the window: the last
+ * committed entry whose time is <= t (>= t when integrating backwards),
+ * src/dopri.c:742-769.  Returns its logical index, or records ERR_YLAG_FAIL
+ * and returns 0xffffffff when there is no such entry.  *from_ring tells
+ * whether the window now holds the entry.  The window moves only by one
+ * entry at its ends (or starts, if empty); a query further away is answered
+ * from the ring and leaves the window to lag_window_ensure. */
+static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *from_ring) {
   const int cap = s_lag_u.cap;
   const int idx_t = s_lag_u.hl - 2;
   const double sign = s_lag_u.sign;
   const unsigned count = s_count[s];
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
-#define DDE_PRED(j) (sign * ring_entry(s, (j))[idx_t] <= st)
-  unsigned lo = count - used, hi = count; /* want: pred(lo) holds, pred(hi) fails */
-  if (used == 0 || !DDE_PRED(lo)) {
+  const unsigned tail = count - used;
+  unsigned wn = s_wn[s], base = s_wbase[s];
+  /* remember the lag of this query */
+  const double dq = st - s_tt[s];
+  if (dq > s_dq_hi[s]) {
+    s_dq_hi[s] = dq;
+  }
+  if (dq < s_dq_lo[s]) {
+    s_dq_lo[s] = dq;
+  }
+#define DDE_TIME(j) (DDE_LAG_COUNT(5), sign * ring_entry(s, (j))[idx_t])
+  /* bracket: pred(lo) holds, pred(hi) fails, pred(j) := time(j) <= st */
+  unsigned lo = tail, hi = count;
+  const bool above = wn > 0 && st >= s_wtop[s];
+  bool lo_known = false; /* pred(lo) already established */
+  if (wn == 0) {
+    DDE_LAG_COUNT(2);
+  } else if (above) {
+    DDE_LAG_COUNT(0);
+    lo = base + wn; /* exists (wtop is finite) and starts at wtop <= st */
+    lo_known = true;
+  } else {
+    DDE_LAG_COUNT(1);
+    hi = base; /* st < wt[base] */
+  }
+  if (used == 0 || lo >= hi) {
+    lo_known = false;
+    hi = lo; /* empty bracket: fails below */
+  } else {
+    /* try next to where the last search ended: two independent loads */
+    unsigned g = s_hint[s];
+    g = g < lo ? lo : (g >= hi ? hi - 1 : g);
+    const double tg = DDE_TIME(g);
+    const double tg1 = g + 1 < hi ? DDE_TIME(g + 1) : pos_inf();
+    if (tg <= st) {
+      lo = g;
+      lo_known = true;
+      if (g + 1 < hi) {
+        if (tg1 <= st) {
+          lo = g + 1;
+        } else {
+          hi = g + 1;
+        }
+      }
+    } else {
+      hi = g;
+    }
+  }
+  if (!lo_known && !(lo < hi && DDE_TIME(lo) <= st)) {
     DDE_LAG_COUNT(4);
     s_error[s] = 1;
     s_code[s] = -6; /* ERR_YLAG_FAIL */
-    return false;
-  }
-  /* start from the window: the entry wanted is usually next to it */
-  const unsigned wn = s_wn[s];
-  if (wn == 0) {
-    DDE_LAG_COUNT(2);
-  }
-  if (wn > 0) {
-    const unsigned base = s_wbase[s];
-    DDE_LAG_COUNT(st >= s_wtop[s] ? 0 : 1);
-    if (st >= s_wtop[s]) {
-      const unsigned g = base + wn; /* exists: wtop is finite */
-      if (g > lo && g < hi) {
-        lo = g; /* its start time is wtop <= st */
-        if (g + 1 < hi) {
-          if (DDE_PRED(g + 1)) {
-            lo = g + 1;
-          } else {
-            hi = g + 1;
-          }
-        }
-      }
-    } else if (base > lo && base < hi) {
-      hi = base; /* st < wt[base] */
-      if (DDE_PRED(base - 1)) {
-        lo = base - 1;
-      }
-    }
+    return 0xffffffffu;
   }
   while (hi - lo > 1) {
     const unsigned mid = lo + (hi - lo) / 2;
-    DDE_LAG_COUNT(5);
-    if (DDE_PRED(mid)) {
+    if (DDE_TIME(mid) <= st) {
       lo = mid;
     } else {
       hi = mid;
     }
   }
-#undef DDE_PRED
-  /* remember how far above the end of the step this query reached */
-  if (st - s_att_hi[s] > s_dq_hi[s]) {
-    s_dq_hi[s] = st - s_att_hi[s];
-  }
-  /* reload the window: entries lo .. lo + DDE_WIN - 1 as far as committed */
-  double top = pos_inf();
-  unsigned k = 0;
-#pragma unroll 1
-  for (int j = 0; j < DDE_WIN; ++j) {
-    if (lo + j < count) {
-      top = lag_window_load(s, lo + j);
-      k = j + 1;
-    } else {
-      s_wt[(lo + j) & (DDE_WIN - 1)][s] = pos_inf();
+#undef DDE_TIME
+  s_hint[s] = lo;
+  DDE_LAG_TRACE("miss thr %d st %.6f tt %.6f att [%.6f %.6f] dq [%.3f %.3f] base %u wn %u wt0 %.6f wtop %.6f -> idx %u\n", s, st, s_tt[s], s_att_lo[s], s_att_hi[s], s_dq_lo[s], s_dq_hi[s], base, wn,
+                s_wt[base % DDE_WIN][s], s_wtop[s], lo);
+  *from_ring = false;
+  if (wn == 0) {
+    /* start the window at the entry */
+    s_wtop[s] = lag_window_load<0>(s, lo);
+    s_wbase[s] = lo;
+    s_wn[s] = 1;
+  } else if (lo == base + wn) {
+    /* next above: append, dropping the lowest entry if no query of this step
+       can reach it */
+    const double need_lo = s_att_lo[s] + s_dq_lo[s];
+    if (wn == DDE_WIN && s_wt[(base + 1) % DDE_WIN][s] <= need_lo) {
+      lag_window_evict(s, base, wn);
     }
+    if (wn < DDE_WIN) {
+      s_wtop[s] = lag_window_load<0>(s, lo);
+      s_wbase[s] = base;
+      s_wn[s] = wn + 1;
+    } else {
+      *from_ring = true;
+    }
+  } else if (lo + 1 == base && wn < DDE_WIN) {
+    /* next below, and its slot is free: prepend */
+    (void) lag_window_load<0>(s, lo);
+    s_wbase[s] = lo;
+    s_wn[s] = wn + 1;
+  } else {
+    *from_ring = true;
   }
-  s_wbase[s] = lo;
-  s_wn[s] = k;
-  s_wtop[s] = top;
-  return true;
+  if (*from_ring) {
+    DDE_LAG_COUNT(6);
+  }
+  return lo;
 }
 
 /* The entry a lag query at time t reads, src/dopri.c:742-769.  On failure
@@ -331,22 +440,41 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
   const double sign = s_lag_u.sign;
   const double st = sign * t; /* entries are ordered by sign * time */
   LagHit hit;
-  unsigned base = s_wbase[s];
+  const unsigned base = s_wbase[s];
   hit.ok = true;
-  if (!(s_wn[s] > 0 && st >= s_wt[base & (DDE_WIN - 1)][s] && st < s_wtop[s])) {
-    hit.ok = lag_window_miss(s, st);
-    base = s_wbase[s];
-  }
-  /* unused slots hold +inf, so this counts the entries that start at or before st */
-  unsigned j = 0;
+  hit.from_ring = s_lag_u.staged == 0;
+  if (s_wn[s] > 0 && st >= s_wt[base % DDE_WIN][s] && st < s_wtop[s]) {
+    /* unused slots hold +inf, so this counts the entries that start at or before st */
+    unsigned j = 0;
 #pragma unroll
-  for (int k = 1; k < DDE_WIN; ++k) {
-    j += st >= s_wt[(base + k) & (DDE_WIN - 1)][s] ? 1u : 0u;
+    for (int k = 1; k < DDE_WIN; ++k) {
+      j += st >= s_wt[(base + k) % DDE_WIN][s] ? 1u : 0u;
+    }
+    hit.idx = base + j;
+    const int w = (int) (hit.idx % DDE_WIN);
+    hit.t_old = sign * s_wt[w][s];
+    hit.h = s_wh[w][s];
+    return hit;
   }
-  hit.idx = base + j;
-  const int w = (int) (hit.idx & (DDE_WIN - 1));
-  hit.t_old = sign * s_wt[w][s];
-  hit.h = s_wh[w][s];
+  bool from_ring = false;
+  hit.idx = lag_window_miss(s, st, &from_ring);
+  if (hit.idx == 0xffffffffu) {
+    hit.ok = false;
+    hit.t_old = 0.0;
+    hit.h = 1.0;
+    return hit;
+  }
+  if (from_ring) {
+    hit.from_ring = true;
+    const double *e = ring_entry(s, hit.idx);
+    const int idx_t = s_lag_u.hl - 2;
+    hit.t_old = e[idx_t];
+    hit.h = e[idx_t + 1];
+  } else {
+    const int w = (int) (hit.idx % DDE_WIN);
+    hit.t_old = sign * s_wt[w][s];
+    hit.h = s_wh[w][s];
+  }
   return hit;
 }
 
@@ -378,8 +506,8 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
   const int n = s_lag_u.n, order = s_lag_u.order;
   const double theta = (t - hit.t_old) / hit.h;
   const double theta1 = 1 - theta;
-  if (s_lag_u.staged) {
-    const int w = (int) (hit.idx & (DDE_WIN - 1));
+  if (!hit.from_ring) {
+    const int w = (int) (hit.idx % DDE_WIN);
     const double *c = s_wc + (size_t) w * (order * n) * DDE_TPB + s;
     for (size_t i = 0; i < nidx; ++i) {
       const size_t comp = idx ? (size_t) idx[i] : i;

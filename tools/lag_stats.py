@@ -13,7 +13,7 @@ out = (C.c_ulonglong * 8)()
 lib.dde_debug_lag_stats(out)
 r = dde_b200.dopri_batch(y0, times, model, parms, **kw)
 lib.dde_debug_lag_stats(out)
-names = ["miss_above", "miss_below", "miss_empty", "ensure_appends", "failures", "bisect_probes"]
+names = ["miss_above", "miss_below", "miss_empty", "ensure_appends", "failures", "ring_probes", "answered_from_ring", "above_but_predicted"]
 st = r.statistics.sum(axis=0)
 print("per trajectory: evals %.1f steps %.1f accepts %.1f" % tuple(st[:3] / n))
 for k, v in zip(names, out):
