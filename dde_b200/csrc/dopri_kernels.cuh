@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
 
       /* -- 2. dopri_eval, src/dopri.c:831-835: the one hot copy of the model -- */
       if (a.n_history > 0) {
-        s_tt[s] = sign * tt; /* lag look-ups learn their offset from it */
+        s_tt[s] = tt; /* lag look-ups learn their offset from it */
       }
       M::deriv((size_t) n, tt, yin, kt, p);
       ++n_eval;

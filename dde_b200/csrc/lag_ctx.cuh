@@ -101,7 +101,7 @@ __shared__ unsigned s_wn[DDE_TPB];
 __shared__ double s_att_lo[DDE_TPB]; /* sign * t of the attempt in progress */
 __shared__ double s_att_hi[DDE_TPB]; /* sign * (t + h) of the attempt in progress */
 __shared__ unsigned s_hint[DDE_TPB]; /* entry the last search ended at */
-__shared__ double s_tt[DDE_TPB];     /* sign * time of the RHS evaluation in progress */
+__shared__ double s_tt[DDE_TPB];     /* time of the RHS evaluation in progress */
 __shared__ double s_dq_lo[DDE_TPB];  /* lowest / highest query seen, relative to the time of the */
 __shared__ double s_dq_hi[DDE_TPB];  /* evaluation that made it (+inf / -inf: none yet) */
 extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
@@ -318,6 +318,7 @@ struct LagHit {
   bool ok;         /* false: no entry (ERR_YLAG_FAIL recorded) */
   bool from_ring;  /* read the coefficients from the ring, not from the window */
   unsigned idx;    /* logical index of the entry */
+  int slot;        /* its window slot */
   double t_old, h; /* its start time and step */
 };
 
@@ -337,7 +338,7 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
   const unsigned tail = count - used;
   unsigned wn = s_wn[s], base = s_wbase[s];
   /* remember the lag of this query */
-  const double dq = st - s_tt[s];
+  const double dq = st - sign * s_tt[s];
   if (dq > s_dq_hi[s]) {
     s_dq_hi[s] = dq;
   }
@@ -440,24 +441,26 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
   const double sign = s_lag_u.sign;
   const double st = sign * t; /* entries are ordered by sign * time */
   LagHit hit;
-  const unsigned base = s_wbase[s];
   hit.ok = true;
   hit.from_ring = s_lag_u.staged == 0;
-  if (s_wn[s] > 0 && st >= s_wt[base % DDE_WIN][s] && st < s_wtop[s]) {
-    /* unused slots hold +inf, so this counts the entries that start at or before st */
-    unsigned j = 0;
+  /* Entries in the window are consecutive and unused slots hold +inf, so the
+     number of slots (in any order) that start at or before st locates the
+     entry: no search, no slot arithmetic. */
+  unsigned below = 0;
 #pragma unroll
-    for (int k = 1; k < DDE_WIN; ++k) {
-      j += st >= s_wt[(base + k) % DDE_WIN][s] ? 1u : 0u;
-    }
-    hit.idx = base + j;
-    const int w = (int) (hit.idx % DDE_WIN);
-    hit.t_old = sign * s_wt[w][s];
-    hit.h = s_wh[w][s];
+  for (int k = 0; k < DDE_WIN; ++k) {
+    below += st >= s_wt[k][s] ? 1u : 0u;
+  }
+  if (below > 0 && st < s_wtop[s]) {
+    hit.idx = s_wbase[s] + below - 1;
+    hit.slot = (int) (hit.idx % DDE_WIN);
+    hit.t_old = sign * s_wt[hit.slot][s];
+    hit.h = s_wh[hit.slot][s];
     return hit;
   }
   bool from_ring = false;
   hit.idx = lag_window_miss(s, st, &from_ring);
+  hit.slot = (int) (hit.idx % DDE_WIN);
   if (hit.idx == 0xffffffffu) {
     hit.ok = false;
     hit.t_old = 0.0;
@@ -471,9 +474,8 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
     hit.t_old = e[idx_t];
     hit.h = e[idx_t + 1];
   } else {
-    const int w = (int) (hit.idx % DDE_WIN);
-    hit.t_old = sign * s_wt[w][s];
-    hit.h = s_wh[w][s];
+    hit.t_old = sign * s_wt[hit.slot][s];
+    hit.h = s_wh[hit.slot][s];
   }
   return hit;
 }
@@ -507,8 +509,7 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
   const double theta = (t - hit.t_old) / hit.h;
   const double theta1 = 1 - theta;
   if (!hit.from_ring) {
-    const int w = (int) (hit.idx % DDE_WIN);
-    const double *c = s_wc + (size_t) w * (order * n) * DDE_TPB + s;
+    const double *c = s_wc + (size_t) hit.slot * (order * n) * DDE_TPB + s;
     for (size_t i = 0; i < nidx; ++i) {
       const size_t comp = idx ? (size_t) idx[i] : i;
       y[i] = interp_entry(c + comp * DDE_TPB, order, n * DDE_TPB, theta, theta1);
