@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs[0], [2], [3]) on one GPU,
+device-resident, timed with the handle's CUDA events.  Not the headline bench
+(bench.py is configs[1]); prints one JSON line per workload.
+
+usage: tools/bench_configs.py [--c3-traj N] [--c3-times N] [--c4-rep N] [--c4-steps N]
+"""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import dde_b200  # noqa: E402
+from dde_b200 import workloads  # noqa: E402
+
+
+def time_dopri(model, y0, parms, times, kw, n, reps=3):
+    b = dde_b200.DopriBatch(model, n, y0.shape[0], n_parms=parms.shape[1], **kw)
+    b.set_times(times)
+    b.upload(y0, parms)
+    b.run()
+    b.sync()
+    ms = []
+    for _ in range(reps):
+        b.run()
+        b.sync()
+        ms.append(b.last_ms())
+    stats = np.empty((y0.shape[0], 4), dtype=np.int32)
+    code = np.empty((y0.shape[0],), dtype=np.int32)
+    b.download_into(None, None, stats, code, None, None)
+    b.close()
+    return float(np.median(ms)), stats, code
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--c3-traj", type=int, default=1 << 22)
+    ap.add_argument("--c3-times", type=int, default=1001)
+    ap.add_argument("--c4-rep", type=int, default=1 << 20)
+    ap.add_argument("--c4-steps", type=int, default=10000)
+    args = ap.parse_args()
+
+    # C1: one Lorenz trajectory, t = 0..100 (latency, not throughput)
+    y0 = np.array([[10.0, 1.0, 1.0]])
+    p = np.array([[10.0, 28.0, 8.0 / 3.0]])
+    ms, stats, code = time_dopri("lorenz", y0, p, np.linspace(0, 100, 1001), dict(method="dopri5"), 3)
+    print(json.dumps({"workload": "C1 lorenz dopri5 single trajectory t=0..100", "ms": ms,
+                      "statistics": stats[0].tolist(), "code": int(code[0]),
+                      "accepted_steps_per_s": stats[0, 2] / (ms * 1e-3)}))
+
+    # C3: Lorenz / Roessler dopri5 sweeps, dense output at c3_times - 1 times
+    for gen in (workloads.lorenz_sweep, workloads.rossler_sweep):
+        n_traj = args.c3_traj // 2
+        model, y0, parms, times, kw = gen(n_traj, n_times=args.c3_times)
+        out_bytes = n_traj * (args.c3_times - 1) * 3 * 8
+        ms, stats, code = time_dopri(model, y0, parms, times, kw, 3, reps=2)
+        S, A, E = (stats[:, k].astype(np.float64).sum() for k in (1, 2, 0))
+        frhs = 9 if model == "lorenz" else 7
+        flops = 3 * (76 * S + 6 * A + 8 * n_traj * (args.c3_times - 1)) + E * frhs
+        print(json.dumps({"workload": "C3 %s dopri5 sweep" % model, "n_traj": n_traj,
+                          "n_out_times": args.c3_times - 1, "ms": ms,
+                          "trajectories_per_s": n_traj / (ms * 1e-3),
+                          "accepted_steps_per_s": A / (ms * 1e-3),
+                          "output_GB": out_bytes / 1e9, "output_GBps": out_bytes / (ms * 1e-3) / 1e9,
+                          "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                          "failed": int((code != 1).sum())}))
+
+    # C4: delayed SIR map through difeq_replicate
+    model, y0, parms, steps, kw = workloads.sir_delay(args.c4_rep, n_steps=args.c4_steps)
+    b = dde_b200.DifeqBatch(model, 3, args.c4_rep, n_parms=2, n_history=kw["n_history"])
+    b.upload(y0, parms)
+    b.set_steps(steps, kw["return_initial"])
+    b.run()
+    b.sync()
+    ms = []
+    for _ in range(3):
+        b.run()
+        b.sync()
+        ms.append(b.last_ms())
+    ms = float(np.median(ms))
+    y, _, code, _ = b.download()
+    b.close()
+    n_steps_total = float(args.c4_rep) * args.c4_steps
+    print(json.dumps({"workload": "C4 delayed SIR difeq_replicate", "n_rep": args.c4_rep,
+                      "n_steps": args.c4_steps, "ms": ms, "steps_per_s": n_steps_total / (ms * 1e-3),
+                      "replicates_per_s": args.c4_rep / (ms * 1e-3),
+                      "ring_GBps": n_steps_total * 40 / (ms * 1e-3) / 1e9,
+                      "failed": int((code != 1).sum()), "checksum": float(y.sum())}))
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    main()
+    print("elapsed %.1f s" % (time.time() - t0), file=sys.stderr)
