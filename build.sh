@@ -11,12 +11,14 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 OUT=${DDE_OUT:-dde_b200/libdde_b200.so}
 TAG=${DDE_TAG:-}
 mkdir -p build
-rm -f build/capi$TAG.o build/models_builtin$TAG.o
+rm -f build/capi$TAG.o build/models_builtin$TAG.o build/models_coop$TAG.o
 "$NVCC" "${FLAGS[@]}" -c dde_b200/csrc/capi.cu -o build/capi$TAG.o 2> build/nvcc_capi$TAG.log &
 "$NVCC" "${FLAGS[@]}" -Xptxas -v -c dde_b200/csrc/models_builtin.cu -o build/models_builtin$TAG.o 2> build/ptxas_models$TAG.log &
+"$NVCC" "${FLAGS[@]}" -Xptxas -v -c dde_b200/csrc/models_coop.cu -o build/models_coop$TAG.o 2> build/ptxas_coop$TAG.log &
 wait
 grep -v "offline compilation" build/nvcc_capi$TAG.log | grep -i -B2 -A6 "error\|warning" || true
 grep -i -B2 -A6 "error" build/ptxas_models$TAG.log || true
-test -f build/capi$TAG.o -a -f build/models_builtin$TAG.o || { echo "build failed" >&2; exit 1; }
-"$NVCC" -shared -o "$OUT" build/capi$TAG.o build/models_builtin$TAG.o -lcudart
+grep -i -B2 -A6 "error" build/ptxas_coop$TAG.log || true
+test -f build/capi$TAG.o -a -f build/models_builtin$TAG.o -a -f build/models_coop$TAG.o || { echo "build failed" >&2; exit 1; }
+"$NVCC" -shared -o "$OUT" build/capi$TAG.o build/models_builtin$TAG.o build/models_coop$TAG.o -lcudart
 echo "built $OUT"

@@ -1,0 +1,53 @@
+/* dopri_args.h -- kernel arguments of the dopri kernels: the per-batch
+ * constants of dopri_data (/root/reference/src/dopri.h:55-161) plus array
+ * bases.  Shared by the thread-per-trajectory kernels (dopri_kernels.cuh), the
+ * block-per-trajectory kernel (dopri_coop_kernel.cuh) and the host layer. */
+#ifndef DDE_DOPRI_ARGS_H
+#define DDE_DOPRI_ARGS_H
+
+namespace dde {
+
+#ifndef DDE_DYN_MAXN
+#define DDE_DYN_MAXN 16 /* largest n of a model compiled with runtime n */
+#endif
+#ifndef DDE_DYN_MAXP
+#define DDE_DYN_MAXP 16
+#endif
+#ifndef DDE_DYN_MAXOUT
+#define DDE_DYN_MAXOUT 8
+#endif
+
+/* Kernel arguments: the per-batch constants of dopri_data plus array bases. */
+struct DopriArgs {
+  /* problem */
+  long long n_traj;
+  int n, n_out, n_parms;
+  long long parms_stride;
+  const double *y0;    /* [n x n_traj] */
+  const double *parms; /* [n_parms x n_traj] or one shared vector */
+  const double *times; /* [n_times] */
+  const double *tcrit; /* [n_tcrit] */
+  int n_times, n_tcrit, tcrit_idx0;
+  /* controls (src/dopri.h:133-146) */
+  double atol, rtol, step_size_min, step_size_max, step_size_initial;
+  unsigned long long step_max_n, stiff_check;
+  int n_history, step_size_min_allow, return_initial;
+  double sign; /* src/dopri.c:173 */
+  /* results */
+  double *y_out, *out;
+  int *stats, *code;
+  double *t_last, *step_size;
+  /* start-up values from dopri_init_kernel */
+  double *init_k1; /* [n x n_traj] f(t0, y0) */
+  double *init_h;  /* [n_traj] first step size */
+  /* history */
+  double *ring;          /* [n_traj][n_history][order*n + 2] */
+  unsigned *ring_count;  /* [n_traj] entries committed (for export) */
+  int win_staged;        /* lag-window coefficients in (dynamic) shared memory */
+  /* work distribution: next trajectory index to hand out */
+  unsigned long long *next_traj;
+};
+
+} /* namespace dde */
+
+#endif /* DDE_DOPRI_ARGS_H */

@@ -29,3 +29,26 @@ DDE_MODEL_FN void delayed_growth(size_t n, double t, const double *y,
     dydt[i] = r[i] * ylag_1(t - 1.0, i);
   }
 }
+
+/* The same two models written for wide state vectors with the cooperative
+ * macros of <dde/dde.h> (any n; the lagged state is fetched whole with
+ * ylag_all). */
+DDE_MODEL_FN void exponential_wide(size_t n, double t, const double *y,
+                                   double *dydt, const void *data) {
+  const double *r = (const double *) data;
+  DDE_FOR(i, 0, n) {
+    dydt[i] = -y[i] * r[i];
+  }
+}
+
+#define DDE_GROWTH_WIDE_MAX 128
+DDE_MODEL_FN void delayed_growth_wide(size_t n, double t, const double *y,
+                                      double *dydt, const void *data) {
+  const double *r = (const double *) data;
+  DDE_SCRATCH_BEGIN();
+  DDE_SCRATCH(double, ylag, DDE_GROWTH_WIDE_MAX);
+  ylag_all(t - 1.0, ylag);
+  DDE_FOR(i, 0, n) {
+    dydt[i] = r[i] * ylag[i];
+  }
+}

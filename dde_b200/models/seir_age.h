@@ -4,7 +4,8 @@
  * Rates scaled from the reference's SEIR example
  * (/root/reference/inst/examples/seir.c:8-10).
  *
- *   lambda_a(t) = beta / N * sum_{|d| <= 4} w_|d| I_{a+d}(t)      banded contacts
+ *   lambda_a(t) = beta sum_{|d| <= 4} w_|d| I_{a+d}(t) / (N_a sum w)   banded contacts,
+ *                                                       N_a = N / 128 per class
  *   new_inf_a   = S_a lambda_a
  *   lag_inf_a   = S_a(t - 14) lambda_a(t - 14) exp(-14 b)          latent period 14
  *   waning_a    = delta R_a + sigma I_a(t - 21) exp(-21 b) / 8     loss of immunity, lag 21
@@ -14,7 +15,9 @@
  *   R_a' = sigma I_a - b R_a - waning_a
  *
  * The S and I blocks at t - 14 and the I block at t - 21 are fetched with
- * ylag_vec_int (src/dopri.c:816-828). */
+ * ylag_vec_int (src/dopri.c:816-828).  Written with the cooperative macros of
+ * <dde/dde.h>: sequential C for the reference solver, one age class per
+ * thread when a thread block integrates the trajectory. */
 #include <dde/dde.h>
 
 #define SEIR_AGE_CLASSES 128
@@ -30,22 +33,25 @@ DDE_MODEL_FN void seir_age(size_t n, double t, const double *y, double *dydt,
   const double w[SEIR_AGE_BAND + 1] = {1.0, 0.5, 0.25, 0.125, 0.0625};
   const int A = SEIR_AGE_CLASSES;
 
-  int idx14[2 * SEIR_AGE_CLASSES];
-  int idx21[SEIR_AGE_CLASSES];
-  double lag14[2 * SEIR_AGE_CLASSES];
-  double lag21[SEIR_AGE_CLASSES];
-  for (int a = 0; a < A; ++a) {
+  DDE_SCRATCH_BEGIN();
+  DDE_SCRATCH(int, idx14, 2 * SEIR_AGE_CLASSES);
+  DDE_SCRATCH(int, idx21, SEIR_AGE_CLASSES);
+  DDE_SCRATCH(double, lag14, 2 * SEIR_AGE_CLASSES);
+  DDE_SCRATCH(double, lag21, SEIR_AGE_CLASSES);
+  DDE_FOR(a, 0, A) {
     idx14[a] = a;             /* S block */
     idx14[A + a] = 2 * A + a; /* I block */
     idx21[a] = 2 * A + a;
   }
+  DDE_SYNC();
   ylag_vec_int(t - 14.0, idx14, 2 * SEIR_AGE_CLASSES, lag14);
   ylag_vec_int(t - 21.0, idx21, SEIR_AGE_CLASSES, lag21);
 
   const double *S = y, *E = y + A, *I = y + 2 * A, *R = y + 3 * A;
   const double *S14 = lag14, *I14 = lag14 + A;
   const double births = b * N / SEIR_AGE_CLASSES;
-  for (int a = 0; a < A; ++a) {
+  const double scale = N / SEIR_AGE_CLASSES * 2.875; /* class size x sum of the weights */
+  DDE_FOR(a, 0, A) {
     double force = 0.0, force14 = 0.0;
     for (int d = -SEIR_AGE_BAND; d <= SEIR_AGE_BAND; ++d) {
       const int c = a + d;
@@ -55,8 +61,8 @@ DDE_MODEL_FN void seir_age(size_t n, double t, const double *y, double *dydt,
         force14 += wd * I14[c];
       }
     }
-    const double new_inf = S[a] * (beta * force / N);
-    const double lag_inf = S14[a] * (beta * force14 / N) * surv14;
+    const double new_inf = S[a] * (beta * force / scale);
+    const double lag_inf = S14[a] * (beta * force14 / scale) * surv14;
     const double waning = delta * R[a] + sigma * lag21[a] * surv21 / 8.0;
     dydt[a] = births - b * S[a] - new_inf + waning;
     dydt[A + a] = new_inf - lag_inf - b * E[a];

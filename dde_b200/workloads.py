@@ -64,3 +64,21 @@ def sir_delay(n_rep, first=0, n_steps=10000):
     steps = np.array([0, n_steps], dtype=np.uint64)
     kwargs = dict(n_history=16, return_initial=False)
     return "sir_delay", y0, np.ascontiguousarray(parms), steps, kwargs
+
+
+def seir_age(n_traj, first=0, t_end=200.0, n_times=21):
+    """C5: age-structured SEIR, 128 age classes x (S, E, I, R) = 512 states, lags 14 and 21;
+    beta = 8 + 4u, sigma = 1 / (2 + 2u), delta = 1 / (14 + 14u); y0: the population of 1e7
+    spread evenly over the age classes, all susceptible but one infective in class 0;
+    dop853, rtol = atol = 1e-6, n_history = 128, times 0 .. t_end."""
+    u = splitmix64_uniform(3 * n_traj, start=3 * first).reshape(n_traj, 3)
+    parms = np.stack([8.0 + 4.0 * u[:, 0], 1.0 / (2.0 + 2.0 * u[:, 1]),
+                      1.0 / (14.0 + 14.0 * u[:, 2])], axis=1)
+    A = 128
+    y0 = np.zeros((n_traj, 4 * A))
+    y0[:, :A] = 1e7 / A
+    y0[:, 0] -= 1.0
+    y0[:, 2 * A] = 1.0
+    times = np.linspace(0.0, t_end, n_times)
+    kwargs = dict(method="dopri853", rtol=1e-6, atol=1e-6, n_history=128)
+    return "seir_age", y0, np.ascontiguousarray(parms), times, kwargs

@@ -30,6 +30,43 @@
 #include <math.h>
 #include <stddef.h>
 
+/* ---- large models: cooperative evaluation (an extension, optional) --------
+ *
+ * A model with hundreds of equations is integrated by a whole thread block
+ * per trajectory (dde_b200/csrc/dopri_coop_kernel.cuh), and its deriv() is
+ * then called by all threads of the block at once.  Written with the three
+ * macros below the same source still compiles as plain sequential C (for the
+ * reference solver / the oracle) and as a thread-per-trajectory device
+ * function:
+ *
+ *   DDE_FOR(i, lo, hi) { ... }   independent iterations i = lo .. hi-1; the
+ *                                block's threads take them in strides
+ *   DDE_SCRATCH_BEGIN();          once, before the first DDE_SCRATCH
+ *   DDE_SCRATCH(type, name, len); an array all threads share (a local array
+ *                                in sequential code)
+ *   DDE_SYNC();                   all writes before it are visible to all
+ *                                threads after it (nothing in sequential code)
+ *
+ * y, dydt and data are shared by the block; ylag_vec / ylag_vec_int / ylag_all
+ * are collective (every thread calls them with the same arguments, index and
+ * result arrays are shared, the results are visible on return).
+ */
+#if defined(__CUDACC__) && defined(DDE_COOPERATIVE)
+#define DDE_FOR(i, lo, hi) \
+  for (int i = (int) (lo) + (int) threadIdx.x; i < (int) (hi); i += (int) blockDim.x)
+#define DDE_SYNC() __syncthreads()
+#define DDE_SCRATCH_BEGIN() size_t dde_scratch_offset_ = 0
+#define DDE_SCRATCH(type, name, len)                                       \
+  type *name = (type *) (dde_coop_scratch() + dde_scratch_offset_);        \
+  dde_scratch_offset_ += (sizeof(type) * (size_t) (len) + 15) & ~(size_t) 15
+static __device__ char *dde_coop_scratch(void);
+#else
+#define DDE_FOR(i, lo, hi) for (int i = (int) (lo); i < (int) (hi); ++i)
+#define DDE_SYNC() ((void) 0)
+#define DDE_SCRATCH_BEGIN() ((void) 0)
+#define DDE_SCRATCH(type, name, len) type name[len]
+#endif
+
 #if defined(__CUDACC__)
 
 #define DDE_MODEL_FN static __device__ __forceinline__

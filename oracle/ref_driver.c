@@ -154,6 +154,8 @@ static const model_entry models[] = {
     {"exponential", exponential, NULL, NULL},
     {"linear", linear, NULL, NULL},
     {"delayed_growth", delayed_growth, NULL, NULL},
+    {"exponential_wide", exponential_wide, NULL, NULL},
+    {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
     {"seir_age", seir_age, NULL, NULL},
     {"logistic", NULL, NULL, logistic},
     {"additive", NULL, NULL, additive},

@@ -83,6 +83,13 @@ def main():
     dopri_case("stiff", "exponential", [[1.0]], [0.0, 10.0], [[1e5]], stiff_check=1)
     dopri_case("delayed_growth", "delayed_growth", [[1.0, 2.0, 0.5]], np.linspace(0, 3, 13),
                [[0.5, 0.25, 1.0]], method="dopri853", n_history=200)
+    # BASELINE.json configs[4], reduced: two trajectories of the n = 512 model
+    model, y0, parms, times, kw = workloads.seir_age(2)
+    dopri_case("c5_seir_age", model, y0, times, parms, **kw)
+    rng = np.random.default_rng(70)
+    dopri_case("delayed_growth_wide", "delayed_growth_wide", rng.uniform(0.5, 2.0, (3, 70)),
+               np.linspace(0, 3, 13), rng.uniform(0.1, 1.0, (3, 70)), method="dopri5",
+               n_history=200)
     # difeq
     difeq_case("logistic", "logistic", [[0.1]], np.arange(21), [[1.5]])
     difeq_case("fibonacci", "fibonacci", [[1.0] * 5], np.arange(11), None, n_history=2)
