@@ -59,16 +59,49 @@ struct LagUniform {
 };
 
 __shared__ LagUniform s_lag_u;
-/* per-thread part, structure of arrays: conflict-free LDS/STS */
-__shared__ double *s_ring[DDE_TPB];        /* this trajectory's ring base */
-__shared__ const double *s_y0[DDE_TPB];    /* pre-history state (src/dopri.c:777-778) */
-__shared__ double s_t0[DDE_TPB];           /* sign * start time (src/dopri.c:186) */
-__shared__ unsigned s_count[DDE_TPB];      /* entries committed so far */
-__shared__ int s_head[DDE_TPB];            /* slot the next commit goes to */
-__shared__ int s_code[DDE_TPB];            /* obj->code */
-__shared__ int s_error[DDE_TPB];           /* obj->error */
-__shared__ long long s_step[DDE_TPB];      /* difeq: obj->step */
-__shared__ long long s_step0[DDE_TPB];     /* difeq: obj->step0 */
+
+/* The per-thread part: ONE structure-of-arrays block, [field][thread], so that
+ * every access is one thread-dependent base register plus an immediate offset
+ * (conflict-free LDS/STS, no per-array address arithmetic).  64-bit fields: */
+enum {
+  DDE_F_RING = 0, /* double *: this trajectory's ring base */
+  DDE_F_Y0,       /* const double *: pre-history state (src/dopri.c:777-778) */
+  DDE_F_T0,       /* sign * start time (src/dopri.c:186) */
+  DDE_F_WTOP,     /* the staged lag window, see below */
+  DDE_F_ATT_LO,
+  DDE_F_ATT_HI,
+  DDE_F_TT,
+  DDE_F_DQ_LO,
+  DDE_F_DQ_HI,
+  DDE_F_WT,       /* DDE_WIN rows */
+  DDE_F_WH = DDE_F_WT + DDE_WIN,
+  DDE_F_COUNT64 = DDE_F_WH + DDE_WIN,
+  /* difeq has no lag window: obj->step, obj->step0 share its fields */
+  DDE_F_STEP = DDE_F_ATT_LO,
+  DDE_F_STEP0 = DDE_F_ATT_HI
+};
+/* 32-bit fields: */
+enum {
+  DDE_FI_COUNT = 0, /* entries committed so far */
+  DDE_FI_HEAD,      /* slot the next commit goes to */
+  DDE_FI_CODE,      /* obj->code */
+  DDE_FI_ERROR,     /* obj->error */
+  DDE_FI_WBASE,
+  DDE_FI_WN,
+  DDE_FI_HINT,
+  DDE_FI_COUNT32
+};
+__shared__ double s_ctx64[DDE_F_COUNT64][DDE_TPB];
+__shared__ int s_ctx32[DDE_FI_COUNT32][DDE_TPB];
+#define s_ring ((double **) ::dde::s_ctx64[::dde::DDE_F_RING])
+#define s_y0 ((const double **) ::dde::s_ctx64[::dde::DDE_F_Y0])
+#define s_t0 (::dde::s_ctx64[::dde::DDE_F_T0])
+#define s_step ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP])
+#define s_step0 ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP0])
+#define s_count ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_COUNT])
+#define s_head (::dde::s_ctx32[::dde::DDE_FI_HEAD])
+#define s_code (::dde::s_ctx32[::dde::DDE_FI_CODE])
+#define s_error (::dde::s_ctx32[::dde::DDE_FI_ERROR])
 
 /* The staged lag window ("shared-memory staging of the bracketing history
  * steps"): up to DDE_WIN consecutive committed entries base .. base + wn - 1
@@ -93,17 +126,17 @@ __shared__ long long s_step0[DDE_TPB];     /* difeq: obj->step0 */
  * A.2#11); the window then moves by one entry if it can, restarts at the
  * entry if it was far away, or stays put while the query is answered from the
  * ring directly (a range wider than the window would otherwise thrash it). */
-__shared__ double s_wt[DDE_WIN][DDE_TPB];
-__shared__ double s_wh[DDE_WIN][DDE_TPB];
-__shared__ double s_wtop[DDE_TPB];
-__shared__ unsigned s_wbase[DDE_TPB];
-__shared__ unsigned s_wn[DDE_TPB];
-__shared__ double s_att_lo[DDE_TPB]; /* sign * t of the attempt in progress */
-__shared__ double s_att_hi[DDE_TPB]; /* sign * (t + h) of the attempt in progress */
-__shared__ unsigned s_hint[DDE_TPB]; /* entry the last search ended at */
-__shared__ double s_tt[DDE_TPB];     /* time of the RHS evaluation in progress */
-__shared__ double s_dq_lo[DDE_TPB];  /* lowest / highest query seen, relative to the time of the */
-__shared__ double s_dq_hi[DDE_TPB];  /* evaluation that made it (+inf / -inf: none yet) */
+#define s_wt (&::dde::s_ctx64[::dde::DDE_F_WT])      /* [DDE_WIN][thread] sign-adjusted start times */
+#define s_wh (&::dde::s_ctx64[::dde::DDE_F_WH])      /* [DDE_WIN][thread] step sizes */
+#define s_wtop (::dde::s_ctx64[::dde::DDE_F_WTOP])
+#define s_wbase ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_WBASE])
+#define s_wn ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_WN])
+#define s_att_lo (::dde::s_ctx64[::dde::DDE_F_ATT_LO]) /* sign * t of the attempt in progress */
+#define s_att_hi (::dde::s_ctx64[::dde::DDE_F_ATT_HI]) /* sign * (t + h) of the attempt in progress */
+#define s_hint ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_HINT]) /* entry the last search ended at */
+#define s_tt (::dde::s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
+#define s_dq_lo (::dde::s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
+#define s_dq_hi (::dde::s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
 extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
 
 #ifdef DDE_LAG_STATS
@@ -529,8 +562,8 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
-  if (dde::s_lag_u.sign * t <= dde::s_t0[s]) {
-    return dde::s_y0[s][i];
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
+    return s_y0[s][i];
   }
   const dde::LagHit hit = dde::find_time(s, t);
   if (!hit.ok) {
@@ -544,9 +577,9 @@ static __device__ __forceinline__ double ylag_1(double t, size_t i) {
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
-  if (dde::s_lag_u.sign * t <= dde::s_t0[s]) {
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
     for (int i = 0; i < n; ++i) {
-      y[i] = dde::s_y0[s][i];
+      y[i] = s_y0[s][i];
     }
     return;
   }
@@ -560,9 +593,9 @@ template <class Index>
 static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *idx,
                                                         size_t nidx, double *y) {
   const int s = threadIdx.x;
-  if (dde::s_lag_u.sign * t <= dde::s_t0[s]) {
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
     for (size_t i = 0; i < nidx; ++i) {
-      y[i] = dde::s_y0[s][idx[i]];
+      y[i] = s_y0[s][idx[i]];
     }
     return;
   }
@@ -585,23 +618,23 @@ static __device__ __forceinline__ void ylag_vec_int(double t, const int *idx, si
 /* difeq: the y block of the entry for `step`, or NULL + error
  * (src/difeq.c:261-272).  Entry = {step, y[n], out[n_out]}. */
 static __device__ __forceinline__ const double *dde_find_step(int s, int step) {
-  const int offset = (int) dde::s_step[s] - step;
+  const int offset = (int) s_step[s] - step;
   const int cap = dde::s_lag_u.cap;
-  const unsigned count = dde::s_count[s];
+  const unsigned count = s_count[s];
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   if (cap == 0 || offset < 0 || (unsigned) offset >= used) {
-    dde::s_error[s] = 1;
-    dde::s_code[s] = -9; /* DDE_ERR_DIFEQ_HISTORY */
+    s_error[s] = 1;
+    s_code[s] = -9; /* DDE_ERR_DIFEQ_HISTORY */
     return nullptr;
   }
-  const int slot = dde::ring_slot_back(dde::s_head[s], offset + 1, cap);
-  return dde::s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
+  const int slot = dde::ring_slot_back(s_head[s], offset + 1, cap);
+  return s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
 }
 
 static __device__ __forceinline__ double yprev_1(int step, size_t i) {
   const int s = threadIdx.x;
-  if (step <= (int) dde::s_step0[s]) {
-    return dde::s_y0[s][i];
+  if (step <= (int) s_step0[s]) {
+    return s_y0[s][i];
   }
   const double *e = dde_find_step(s, step);
   return e == nullptr ? dde::na_real() : e[i];
@@ -610,9 +643,9 @@ static __device__ __forceinline__ double yprev_1(int step, size_t i) {
 static __device__ __forceinline__ void yprev_all(int step, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
-  if (step <= (int) dde::s_step0[s]) {
+  if (step <= (int) s_step0[s]) {
     for (int i = 0; i < n; ++i) {
-      y[i] = dde::s_y0[s][i];
+      y[i] = s_y0[s][i];
     }
     return;
   }
@@ -628,9 +661,9 @@ template <class Index>
 static __device__ __forceinline__ void dde_yprev_indexed(int step, const Index *idx,
                                                          size_t nidx, double *y) {
   const int s = threadIdx.x;
-  if (step <= (int) dde::s_step0[s]) {
+  if (step <= (int) s_step0[s]) {
     for (size_t i = 0; i < nidx; ++i) {
-      y[i] = dde::s_y0[s][idx[i]];
+      y[i] = s_y0[s][idx[i]];
     }
     return;
   }

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--c3-times", type=int, default=1001)
     ap.add_argument("--c4-rep", type=int, default=1 << 20)
     ap.add_argument("--c4-steps", type=int, default=10000)
+    ap.add_argument("--c5-traj", type=int, default=4096)
     args = ap.parse_args()
 
     # C1: one Lorenz trajectory, t = 0..100 (latency, not throughput)
@@ -93,7 +94,29 @@ def main():
                       "failed": int((code != 1).sum()), "checksum": float(y.sum())}))
 
 
+def c5(n_traj):
+    # C5: age-structured SEIR, n = 512, block per trajectory; the ring is
+    # n_traj x 128 x 32.8 KB, so one GPU holds ~32k trajectories (65536 shard over 8)
+    model, y0, parms, times, kw = workloads.seir_age(n_traj)
+    ms, stats, code = time_dopri(model, y0, parms, times, kw, 512, reps=2)
+    S, A, E = (stats[:, k].astype(np.float64).sum() for k in (1, 2, 0))
+    n = 512
+    frhs = 128 * (2 * 9 * 2 + 22) + 384 * 17  # band sums + rates, lag interpolation
+    flops = n * (158 * S + 153 * A + 14 * n_traj * 20) + E * frhs
+    ring_bytes = 8.0 * (8 * n + 2) * A + 8.0 * 8 * 384 * E
+    print(json.dumps({"workload": "C5 seir_age dop853 n=512 block-per-trajectory", "n_traj": n_traj,
+                      "ms": ms, "trajectories_per_s": n_traj / (ms * 1e-3),
+                      "accepted_steps_per_s": A / (ms * 1e-3),
+                      "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                      "ring_GBps_algorithmic": ring_bytes / (ms * 1e-3) / 1e9,
+                      "failed": int((code != 1).sum())}))
+
+
 if __name__ == "__main__":
     t0 = time.time()
     main()
+    if "--c5-traj" in " ".join(sys.argv) or True:
+        ap = argparse.ArgumentParser()
+        ap.add_argument("--c5-traj", type=int, default=4096)
+        c5(ap.parse_known_args()[0].c5_traj)
     print("elapsed %.1f s" % (time.time() - t0), file=sys.stderr)
