@@ -238,12 +238,22 @@ DDE_HD int dde_pow_zeroinfnan(uint64_t i) {
   return 2 * i - 1 >= 2 * 0x7ff0000000000000ULL - 1;
 }
 
-/* Everything outside "x positive normal, 2^-65 <= |y| < 2^63".  Returns 1
- * with the result in *res, or 0 with (*ix, *sign_bias) adjusted so the main
- * path can continue. */
-DDE_HD_NOINLINE int dde_pow_special(double x, double y, uint64_t *pix, uint32_t *psign_bias,
-                                    double *res) {
-  uint64_t ix = *pix;
+/* x^y for the normalised bit pattern ix of |x| (the common path): log in
+ * double-double, product, exp. */
+DDE_HD double dde_pow_main(uint64_t ix, double y, uint32_t sign_bias) {
+  double lo;
+  const double hi = dde_pow_log_inline(ix, &lo);
+  const double ehi = y * hi;
+  const double elo = DDE_FMA(y, lo, DDE_FMA(hi, y, -ehi));
+  return dde_exp_inline(ehi, elo, sign_bias, 1);
+}
+
+/* Everything outside "x positive normal, 2^-65 <= |y| < 2^63": zeros,
+ * infinities, NaNs, negative and subnormal bases, tiny and huge exponents.
+ * Out of line (and by value, so the caller keeps nothing on the stack). */
+DDE_HD_NOINLINE double dde_pow_slow(double x, double y) {
+  uint32_t sign_bias = 0;
+  uint64_t ix = dde_asuint64(x);
   const uint64_t iy = dde_asuint64(y);
   uint32_t topx = dde_top12(x);
   const uint32_t topy = dde_top12(y);
@@ -251,46 +261,38 @@ DDE_HD_NOINLINE int dde_pow_special(double x, double y, uint64_t *pix, uint32_t 
   const uint64_t inf_bits = 0x7ff0000000000000ULL;
   if (dde_pow_zeroinfnan(iy)) {
     if (2 * iy == 0) {
-      *res = 1.0;
-      return 1;
+      return 1.0;
     }
     if (ix == one_bits) {
-      *res = 1.0;
-      return 1;
+      return 1.0;
     }
     if (2 * ix > 2 * inf_bits || 2 * iy > 2 * inf_bits) {
-      *res = x + y;
-      return 1;
+      return x + y;
     }
     if (2 * ix == 2 * one_bits) {
-      *res = 1.0;
-      return 1;
+      return 1.0;
     }
     if ((2 * ix < 2 * one_bits) == !(iy >> 63)) {
-      *res = 0.0; /* |x| < 1 && y == inf, or |x| > 1 && y == -inf */
-      return 1;
+      return 0.0; /* |x| < 1 && y == inf, or |x| > 1 && y == -inf */
     }
-    *res = y * y;
-    return 1;
+    return y * y;
   }
   if (dde_pow_zeroinfnan(ix)) {
     double x2 = x * x;
     if ((ix >> 63) && dde_pow_checkint(iy) == 1) {
       x2 = -x2;
     }
-    *res = (iy >> 63) ? 1 / x2 : x2;
-    return 1;
+    return (iy >> 63) ? 1 / x2 : x2;
   }
   /* x and y are non-zero finite */
   if (ix >> 63) {
     /* finite x < 0 */
     const int yint = dde_pow_checkint(iy);
     if (yint == 0) {
-      *res = (x - x) / (x - x); /* invalid: NaN */
-      return 1;
+      return (x - x) / (x - x); /* invalid: NaN */
     }
     if (yint == 1) {
-      *psign_bias = 0x800u << 7;
+      sign_bias = 0x800u << 7;
     }
     ix &= 0x7fffffffffffffffULL;
     topx &= 0x7ff;
@@ -298,16 +300,13 @@ DDE_HD_NOINLINE int dde_pow_special(double x, double y, uint64_t *pix, uint32_t 
   if ((topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu) {
     /* sign_bias == 0 here because y is not odd */
     if (ix == one_bits) {
-      *res = 1.0;
-      return 1;
+      return 1.0;
     }
     if ((topy & 0x7ff) < 0x3be) {
       /* |y| < 2^-65: x^y ~= 1 + y log(x) */
-      *res = ix > one_bits ? 1.0 + y : 1.0 - y;
-      return 1;
+      return ix > one_bits ? 1.0 + y : 1.0 - y;
     }
-    *res = ((ix > one_bits) == (topy < 0x800)) ? HUGE_VAL : 0.0;
-    return 1;
+    return ((ix > one_bits) == (topy < 0x800)) ? HUGE_VAL : 0.0;
   }
   if (topx == 0) {
     /* normalise subnormal x so the exponent becomes negative */
@@ -315,26 +314,16 @@ DDE_HD_NOINLINE int dde_pow_special(double x, double y, uint64_t *pix, uint32_t 
     ix &= 0x7fffffffffffffffULL;
     ix -= 52ULL << 52;
   }
-  *pix = ix;
-  return 0;
+  return dde_pow_main(ix, y, sign_bias);
 }
 
 DDE_HD double dde_pow(double x, double y) {
-  uint32_t sign_bias = 0;
-  uint64_t ix = dde_asuint64(x);
   const uint32_t topx = dde_top12(x);
   const uint32_t topy = dde_top12(y);
   if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu) {
-    double res;
-    if (dde_pow_special(x, y, &ix, &sign_bias, &res)) {
-      return res;
-    }
+    return dde_pow_slow(x, y);
   }
-  double lo;
-  const double hi = dde_pow_log_inline(ix, &lo);
-  const double ehi = y * hi;
-  const double elo = DDE_FMA(y, lo, DDE_FMA(hi, y, -ehi));
-  return dde_exp_inline(ehi, elo, sign_bias, 1);
+  return dde_pow_main(dde_asuint64(x), y, 0);
 }
 
 #endif /* DDE_MATH_H */

@@ -67,6 +67,8 @@ enum {
   DDE_F_RING = 0, /* double *: this trajectory's ring base */
   DDE_F_Y0,       /* const double *: pre-history state (src/dopri.c:777-778) */
   DDE_F_T0,       /* sign * start time (src/dopri.c:186) */
+  DDE_F_SIGN,     /* per-thread copy of the batch-uniform sign: the hot path reads
+                     it at base + offset like everything else */
   DDE_F_WTOP,     /* the staged lag window, see below */
   DDE_F_ATT_LO,
   DDE_F_ATT_HI,
@@ -89,6 +91,7 @@ enum {
   DDE_FI_WBASE,
   DDE_FI_WN,
   DDE_FI_HINT,
+  DDE_FI_CFG,       /* per-thread copy of n | order << 16 | staged << 24 */
   DDE_FI_COUNT32
 };
 __shared__ double s_ctx64[DDE_F_COUNT64][DDE_TPB];
@@ -96,6 +99,8 @@ __shared__ int s_ctx32[DDE_FI_COUNT32][DDE_TPB];
 #define s_ring ((double **) ::dde::s_ctx64[::dde::DDE_F_RING])
 #define s_y0 ((const double **) ::dde::s_ctx64[::dde::DDE_F_Y0])
 #define s_t0 (::dde::s_ctx64[::dde::DDE_F_T0])
+#define s_sign (::dde::s_ctx64[::dde::DDE_F_SIGN])
+#define s_cfg (::dde::s_ctx32[::dde::DDE_FI_CFG])
 #define s_step ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP])
 #define s_step0 ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP0])
 #define s_count ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_COUNT])
@@ -174,6 +179,8 @@ __device__ __forceinline__ const double *ring_entry(int s, unsigned idx) {
 }
 
 __device__ __forceinline__ void lag_window_reset(int s) {
+  s_sign[s] = s_lag_u.sign;
+  s_cfg[s] = s_lag_u.n | (s_lag_u.order << 16) | (s_lag_u.staged << 24);
 #pragma unroll
   for (int k = 0; k < DDE_WIN; ++k) {
     s_wt[k][s] = pos_inf();
@@ -471,11 +478,11 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
 /* The entry a lag query at time t reads, src/dopri.c:742-769.  On failure
  * obj->error / ERR_YLAG_FAIL are set and ok is false. */
 __device__ __forceinline__ LagHit find_time(int s, double t) {
-  const double sign = s_lag_u.sign;
+  const double sign = s_sign[s];
   const double st = sign * t; /* entries are ordered by sign * time */
   LagHit hit;
   hit.ok = true;
-  hit.from_ring = s_lag_u.staged == 0;
+  hit.from_ring = (s_cfg[s] >> 24) == 0;
   /* Entries in the window are consecutive and unused slots hold +inf, so the
      number of slots (in any order) that start at or before st locates the
      entry: no search, no slot arithmetic. */
@@ -538,7 +545,8 @@ __device__ __forceinline__ double interp_entry(const double *c, int order, int s
 template <class Index>
 __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, const Index *idx,
                                          size_t nidx, double *y) {
-  const int n = s_lag_u.n, order = s_lag_u.order;
+  const int cfg = s_cfg[s];
+  const int n = cfg & 0xffff, order = (cfg >> 16) & 0xff;
   const double theta = (t - hit.t_old) / hit.h;
   const double theta1 = 1 - theta;
   if (!hit.from_ring) {
@@ -562,7 +570,7 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
-  if (dde::s_lag_u.sign * t <= s_t0[s]) {
+  if (s_sign[s] * t <= s_t0[s]) {
     return s_y0[s][i];
   }
   const dde::LagHit hit = dde::find_time(s, t);
@@ -577,7 +585,7 @@ static __device__ __forceinline__ double ylag_1(double t, size_t i) {
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
-  if (dde::s_lag_u.sign * t <= s_t0[s]) {
+  if (s_sign[s] * t <= s_t0[s]) {
     for (int i = 0; i < n; ++i) {
       y[i] = s_y0[s][i];
     }
@@ -593,7 +601,7 @@ template <class Index>
 static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *idx,
                                                         size_t nidx, double *y) {
   const int s = threadIdx.x;
-  if (dde::s_lag_u.sign * t <= s_t0[s]) {
+  if (s_sign[s] * t <= s_t0[s]) {
     for (size_t i = 0; i < nidx; ++i) {
       y[i] = s_y0[s][idx[i]];
     }
