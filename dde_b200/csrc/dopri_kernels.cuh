@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
      src/dopri_853.c:304,330-347) */
   constexpr int NST_STEP = METHOD == 0 ? 6 : 11;
   constexpr int NST = METHOD == 0 ? 6 : 16;
+  /* window coefficients staged in shared memory (decided by the shape alone) */
+  constexpr bool STAGED =
+      NC > 0 && sizeof(double) * DDE_WIN * ORDER * NC * DDE_TPB <= DDE_WIN_COEF_BUDGET;
   const int n = NC > 0 ? NC : a.n;
   const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
   const int n_out = M::N_OUT == 0 ? 0 : a.n_out; /* 0 = output function not requested */
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
     s_lag_u.n = n;
     s_lag_u.hl = hl;
     s_lag_u.order = ORDER;
-    s_lag_u.staged = a.win_staged;
+    s_lag_u.staged = NC > 0 ? (STAGED ? 1 : 0) : a.win_staged;
   }
   __syncthreads();
 
@@ -422,6 +425,11 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       /* -- 2. dopri_eval, src/dopri.c:831-835: the one hot copy of the model -- */
       if (a.n_history > 0) {
         s_tt[s] = tt; /* lag look-ups learn their offset from it */
+      }
+      if (NC > 0) {
+        /* the lag functions read the method / width / staging flags from the
+           thread's context: tell the optimiser what they will find */
+        __builtin_assume(s_cfg[s] == (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24)));
       }
       M::deriv((size_t) n, tt, yin, kt, p);
       ++n_eval;

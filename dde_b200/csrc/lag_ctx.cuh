@@ -359,6 +359,7 @@ struct LagHit {
   bool from_ring;  /* read the coefficients from the ring, not from the window */
   unsigned idx;    /* logical index of the entry */
   int slot;        /* its window slot */
+  int cfg;         /* n | order << 16 | staged << 24, read before any call */
   double t_old, h; /* its start time and step */
 };
 
@@ -482,7 +483,8 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
   const double st = sign * t; /* entries are ordered by sign * time */
   LagHit hit;
   hit.ok = true;
-  hit.from_ring = (s_cfg[s] >> 24) == 0;
+  hit.cfg = s_cfg[s];
+  hit.from_ring = (hit.cfg >> 24) == 0;
   /* Entries in the window are consecutive and unused slots hold +inf, so the
      number of slots (in any order) that start at or before st locates the
      entry: no search, no slot arithmetic. */
@@ -545,8 +547,7 @@ __device__ __forceinline__ double interp_entry(const double *c, int order, int s
 template <class Index>
 __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, const Index *idx,
                                          size_t nidx, double *y) {
-  const int cfg = s_cfg[s];
-  const int n = cfg & 0xffff, order = (cfg >> 16) & 0xff;
+  const int n = hit.cfg & 0xffff, order = (hit.cfg >> 16) & 0xff;
   const double theta = (t - hit.t_old) / hit.h;
   const double theta1 = 1 - theta;
   if (!hit.from_ring) {
