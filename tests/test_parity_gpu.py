@@ -281,3 +281,54 @@ def test_sharded_equals_single_device(backend):
     with pytest.raises(dde_b200.DdeError, match="not visible"):
         dde_b200.dopri_batch(y0[:, :1], times, "mackey_glass", parms[:, :1].repeat(3, 1),
                              devices=[99], method="dopri853", n_history=8)
+
+
+# ---- the staged lag window under stress -------------------------------------------
+
+
+@pytest.mark.parametrize("n_history", [3, 5, 8, 16, 33])
+def test_mackey_glass_small_rings(backend, n_history):
+    # the ring recycles entries the window still holds; look-ups that reach
+    # behind the tail must fail exactly where the reference's do
+    model, y0, parms, times, kw = workloads.mackey_glass(768, first=2048)
+    kw["n_history"] = n_history
+    got, _ = check_dopri(backend, model, y0, times, parms, **kw)
+    if n_history <= 8:
+        assert (got.code == -6).sum() > 0
+
+
+@pytest.mark.parametrize("method,rtol", [("dopri5", 1e-6), ("dopri853", 1e-9), ("dopri853", 1e-3),
+                                         ("dopri5", 1e-4)])
+def test_mackey_glass_methods_and_tolerances(backend, method, rtol):
+    model, y0, parms, times, kw = workloads.mackey_glass(512, first=9000)
+    kw.update(method=method, rtol=rtol, atol=rtol, n_history=200)
+    check_dopri(backend, model, y0, times, parms, **kw)
+
+
+def test_mackey_glass_dense_output_and_tcrit(backend):
+    # many output rows per step and critical times at the lag's discontinuities
+    model, y0, parms, _, kw = workloads.mackey_glass(256, first=123)
+    times = np.linspace(0, 120, 481)
+    check_dopri(backend, model, y0, times, parms, tcrit=[17.0, 34.0, 51.0, 68.0], **kw)
+
+
+def test_backward_delay_queries_ahead_of_history(backend):
+    # integrating backwards, t - 1 lies AHEAD of the solver: every query either
+    # extrapolates the newest entry or, on the first step, fails
+    rng = np.random.default_rng(11)
+    y0 = rng.uniform(0.5, 2.0, size=(5, 2))
+    r = rng.uniform(0.1, 1.0, size=(5, 2))
+    for method in ("dopri5", "dopri853"):
+        check_dopri(backend, "delayed_growth", y0, -np.linspace(0, 3, 13), r, method=method,
+                    n_history=50)
+
+
+def test_seir_many_parameter_free_replicates_and_long_lag(backend):
+    # n = 4, two components lagged: window holds times only (coefficients from
+    # the ring), long horizon so the window slides through hundreds of entries
+    y0 = np.tile([1e7 - 1, 0.0, 1.0, 0.0], (6, 1))
+    y0[:, 2] = np.arange(1, 7)
+    y0[:, 0] = 1e7 - y0[:, 2]
+    for method in ("dopri5", "dopri853"):
+        check_dopri(backend, "seir", y0, np.linspace(0, 400, 41), None, n_out=1, method=method,
+                    n_history=40)
