@@ -37,6 +37,11 @@
 #define pow(x, y) dde_pow((x), (y))
 #define exp(x) dde_exp((x))
 
+/* shared memory a block may spend on an on-chip difeq history */
+#ifndef DDE_DIFEQ_STAGE_BUDGET
+#define DDE_DIFEQ_STAGE_BUDGET (56 * 1024)
+#endif
+
 namespace dde {
 
 template <class Kernel>
@@ -97,10 +102,27 @@ cudaError_t launch_dopri_model(int method, const DopriArgs &args, int device_sms
 }
 
 template <class M>
-cudaError_t launch_difeq_model(const DifeqArgs &args, int device_sms, cudaStream_t stream,
+cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStream_t stream,
                                int *n_launches) {
-  const int grid = persistent_grid(difeq_tpt_kernel<M>, args.n_rep, device_sms);
-  difeq_tpt_kernel<M><<<grid, DDE_TPB, 0, stream>>>(args);
+  DifeqArgs a = args_in;
+  /* keep the history on chip when it fits: [slot][component][thread] doubles */
+  size_t dyn = 0;
+  a.staged = 0;
+  if (a.n_history > 0) {
+    const size_t bytes = sizeof(double) * (size_t) a.n_history * (size_t) a.n * DDE_TPB;
+    if (bytes <= DDE_DIFEQ_STAGE_BUDGET) {
+      dyn = bytes;
+      a.staged = 1;
+    }
+  }
+  auto kernel = difeq_tpt_kernel<M>;
+  cudaError_t err =
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
+  if (err != cudaSuccess) {
+    return err;
+  }
+  const int grid = persistent_grid(kernel, a.n_rep, device_sms, dyn);
+  kernel<<<grid, DDE_TPB, dyn, stream>>>(a);
   *n_launches = 1;
   return cudaGetLastError();
 }

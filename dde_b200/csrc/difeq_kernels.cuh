@@ -46,6 +46,7 @@ struct DifeqArgs {
   int *code;       /* [n_rep] */
   double *y_final; /* [n x n_rep], obj->y1 (src/difeq.c:244) */
   double *ring;    /* [n_rep][n_history][1 + n + n_out] */
+  int staged;      /* history in (dynamic) shared memory instead */
   unsigned long long *next_rep;
 };
 
@@ -68,8 +69,10 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     s_lag_u.n = n;
     s_lag_u.hl = hl;
     s_lag_u.order = 0;
+    s_lag_u.staged = a.staged;
   }
   __syncthreads();
+  const int cfg = n | (a.staged << 24);
 
   const int n_steps = a.n_steps;
   const int nt = a.return_initial ? n_steps : n_steps - 1;
@@ -107,19 +110,28 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     s_head[s] = 0;
     s_code[s] = 0;
     s_error[s] = 0;
+    s_cfg[s] = cfg;
 
     int head = 0;
     unsigned count = 0;
 #define DDE_DIFEQ_COMMIT(yy)                                  \
   do {                                                        \
     if (cap > 0) {                                            \
-      double *dst = ring + (size_t) head * (size_t) hl;       \
-      dst[0] = (double) step; /* src/difeq.c:327-330 */       \
-      _Pragma("unroll") for (int i = 0; i < n; ++i) {         \
-        dst[1 + i] = (yy)[i];                                 \
-      }                                                       \
-      for (int i = 0; i < n_out; ++i) {                       \
-        dst[1 + n + i] = na_real();                           \
+      if (a.staged) {                                         \
+        /* on-chip history: only y is ever read back */       \
+        double *dst = s_wc + (size_t) head * n * DDE_TPB + s; \
+        _Pragma("unroll") for (int i = 0; i < n; ++i) {       \
+          dst[(size_t) i * DDE_TPB] = (yy)[i];                \
+        }                                                     \
+      } else {                                                \
+        double *dst = ring + (size_t) head * (size_t) hl;     \
+        dst[0] = (double) step; /* src/difeq.c:327-330 */     \
+        _Pragma("unroll") for (int i = 0; i < n; ++i) {       \
+          dst[1 + i] = (yy)[i];                               \
+        }                                                     \
+        for (int i = 0; i < n_out; ++i) {                     \
+          dst[1 + n + i] = na_real();                         \
+        }                                                     \
       }                                                       \
       head = head + 1 == cap ? 0 : head + 1;                  \
       ++count;                                                \
@@ -146,6 +158,9 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     bool failed = false;
     for (;;) {
       s_step[s] = (long long) step;
+      if (NC > 0) { /* what yprev_* will read: lets the optimiser drop the other path */
+        __builtin_assume(s_cfg[s] == cfg);
+      }
       M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
       if (s_error[s]) {
         failed = true; /* Rf_error in difeq_find_step, src/difeq.c:267-270 */

@@ -624,29 +624,66 @@ static __device__ __forceinline__ void ylag_vec_int(double t, const int *idx, si
   dde_ylag_indexed<int>(t, idx, nidx, y);
 }
 
-/* difeq: the y block of the entry for `step`, or NULL + error
- * (src/difeq.c:261-272).  Entry = {step, y[n], out[n_out]}. */
-static __device__ __forceinline__ const double *dde_find_step(int s, int step) {
+/* difeq: where the state of `step` is stored, or failure (src/difeq.c:261-272).
+ * The history of a difference equation is a handful of short entries that
+ * every step reads and writes, so when it fits it lives in shared memory
+ * ([slot][component][thread], conflict-free) and never travels to HBM; a
+ * longer one is a ring {step, y[n], out[n_out]} per replicate in HBM. */
+struct PrevHit {
+  bool ok;
+  bool staged;
+  const double *e; /* component i at e[i * stride] */
+  int stride;
+};
+
+static __device__ __forceinline__ PrevHit dde_find_step(int s, int step) {
+  PrevHit hit;
+  const int cfg = s_cfg[s];
   const int offset = (int) s_step[s] - step;
   const int cap = dde::s_lag_u.cap;
   const unsigned count = s_count[s];
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
-  if (cap == 0 || offset < 0 || (unsigned) offset >= used) {
+  hit.staged = (cfg >> 24) != 0;
+  hit.ok = !(cap == 0 || offset < 0 || (unsigned) offset >= used);
+  hit.e = nullptr;
+  hit.stride = 1;
+  if (!hit.ok) {
     s_error[s] = 1;
     s_code[s] = -9; /* DDE_ERR_DIFEQ_HISTORY */
-    return nullptr;
+    return hit;
   }
   const int slot = dde::ring_slot_back(s_head[s], offset + 1, cap);
-  return s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
+  if (hit.staged) {
+    hit.e = dde::s_wc + (size_t) slot * (cfg & 0xffff) * DDE_TPB + s;
+    hit.stride = DDE_TPB;
+  } else {
+    hit.e = s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
+  }
+  return hit;
 }
+
+/* two copies of each read so the staged history is read with shared-memory
+   loads and the ring with global ones */
+#define DDE_PREV_READ(dst, hit, comp)                              \
+  do {                                                             \
+    if ((hit).staged) {                                            \
+      (dst) = (hit).e[(size_t) (comp) * DDE_TPB];                  \
+    } else {                                                       \
+      (dst) = (hit).e[(comp)];                                     \
+    }                                                              \
+  } while (0)
 
 static __device__ __forceinline__ double yprev_1(int step, size_t i) {
   const int s = threadIdx.x;
   if (step <= (int) s_step0[s]) {
     return s_y0[s][i];
   }
-  const double *e = dde_find_step(s, step);
-  return e == nullptr ? dde::na_real() : e[i];
+  const PrevHit hit = dde_find_step(s, step);
+  double ret = dde::na_real();
+  if (hit.ok) {
+    DDE_PREV_READ(ret, hit, i);
+  }
+  return ret;
 }
 
 static __device__ __forceinline__ void yprev_all(int step, double *y) {
@@ -658,10 +695,10 @@ static __device__ __forceinline__ void yprev_all(int step, double *y) {
     }
     return;
   }
-  const double *e = dde_find_step(s, step);
-  if (e != nullptr) {
+  const PrevHit hit = dde_find_step(s, step);
+  if (hit.ok) {
     for (int i = 0; i < n; ++i) {
-      y[i] = e[i];
+      DDE_PREV_READ(y[i], hit, i);
     }
   }
 }
@@ -676,10 +713,10 @@ static __device__ __forceinline__ void dde_yprev_indexed(int step, const Index *
     }
     return;
   }
-  const double *e = dde_find_step(s, step);
-  if (e != nullptr) {
+  const PrevHit hit = dde_find_step(s, step);
+  if (hit.ok) {
     for (size_t i = 0; i < nidx; ++i) {
-      y[i] = e[idx[i]];
+      DDE_PREV_READ(y[i], hit, idx[i]);
     }
   }
 }
