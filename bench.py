@@ -278,6 +278,14 @@ def main():
             hbm_peak = 6650.0
             peak_src = "fallback (B200_PROFILING.md)"
         achieved_gbs = bytes_ / (ms_kernel * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of the stepping kernel from the
+        # committed ncu --set full capture of this command (profiles/), if it matches
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            tj = json.loads(tpath.read_text())
+            if tj.get("n_traj_per_gpu") == n_traj:
+                traffic = tj.get("dram_bytes_per_launch")
         fp64 = measure_fp64_peaks(torch)
         achieved_tflops = flops / (ms_kernel * 1e-3) / 1e12
         line = {
@@ -296,7 +304,7 @@ def main():
             "failed_trajectories": int((code != 1).sum()),
             "roofline": {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "kernel is FP64-issue bound, not HBM bound: see fp64",
                 "fp64": {"achieved_tflops": achieved_tflops,
                          "peak_nofma_tflops": fp64["nofma"], "peak_fma_tflops": fp64["fma"],
@@ -311,9 +319,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            n1 = args.cpu_sample or 4096
+            n1 = args.cpu_sample or 8192
             backend, r1 = cpu_reference_run(n1, 0, 0)
-            nN = max(n1, 1024 * cores)
+            nN = max(n1, 4096 * cores)
             _, rN = cpu_reference_run(nN, 0, cores)
             # parity spot check on the sample the baseline just integrated
             same = bool(np.array_equal(r1.statistics, stats[:n1]) and

@@ -105,13 +105,11 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
   bool done = false;   /* ... whose integration has ended */
   double p[PMAX];
   double y[NMAX], k1[NMAX];
-  double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0, t_stop = t_end;
-  double step_size_exit = 0.0;
+  double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
   bool stop = false, last = false, reject = false;
   int times_idx = 1, tcrit_idx = 0;
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
-  double *yo = nullptr, *oo = nullptr;
 
   for (;;) {
     if (!active) {
@@ -153,17 +151,6 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       fac_old = 1e-4;
       stop = last = reject = false;
       h_save = 0.0;
-      step_size_exit = a.step_size_initial;
-      t_stop = t_end;
-      if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
-        t_stop = a.tcrit[tcrit_idx];
-      }
-      yo = a.y_out + (size_t) traj * (size_t) nt * (size_t) n;
-      oo = n_out > 0 ? a.out + (size_t) traj * (size_t) nt * (size_t) n_out : nullptr;
-      if (a.return_initial) { /* row 0 was written by dopri_init_kernel */
-        yo += n;
-        oo += n_out;
-      }
       /* k1 = f(t0, y0) and the first step size come from dopri_init_kernel */
       const double *k0 = a.init_k1 + traj * n;
 #pragma unroll
@@ -207,6 +194,12 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       run = !done;
     }
     if (run) {
+      /* the next stop: a critical time before the end, else the end
+         (src/dopri.c:305-311,484-490; recomputed, not carried) */
+      double t_stop = t_end;
+      if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
+        t_stop = a.tcrit[tcrit_idx];
+      }
       if ((t + 1.01 * h - t_stop) * sign > 0.0) {
         h = t_stop - t;
         stop = true;
@@ -228,7 +221,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
        `ysti`, dop853's last y1).  hd: dense-output coefficients of this
        step, i.e. the ring's head entry, in registers until committed. */
     double k2[NMAX], k3[NMAX], k4[NMAX], k5[NMAX], k6[NMAX], k7[NMAX], k8[NMAX], k9[NMAX],
-        k10[NMAX], ysave[NMAX], hd[ORDER * NMAX];
+        k10[NMAX], k14[NMAX], k15[NMAX], ysave[NMAX], hd[ORDER * NMAX];
     bool accepted = false;
     double h_new = 0.0;
 
@@ -406,7 +399,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
                                    DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
-                                   DP8_A1513 * k4[i] + DP8_A1514 * k10[i]);
+                                   DP8_A1513 * k4[i] + DP8_A1514 * k14[i]);
             }
             tt = t + DP8_C15 * h;
             break;
@@ -415,7 +408,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
                                    DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
-                                   DP8_A1614 * k10[i] + DP8_A1615 * k2[i]);
+                                   DP8_A1614 * k14[i] + DP8_A1615 * k15[i]);
             }
             tt = t + DP8_C16 * h;
             break;
@@ -522,50 +515,49 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
 #pragma unroll
             for (int i = 0; i < n; ++i) k4[i] = kt[i];
             break;
-          case 12: /* src/dopri_853.c:306-327 */
+          case 12: /* k4 = f(t + h, k5), src/dopri_853.c:304 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            break;
+          /* The reference stores the three extra stages over k10, k2, k3 and
+             therefore forms half of each dense coefficient before them
+             (src/dopri_853.c:315-326,350-363).  Here they get registers of
+             their own, so all eight coefficients are formed in one place after
+             the last stage, from the same operands in the same order. */
+          case 13:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k14[i] = kt[i];
+            break;
+          case 14:
+#pragma unroll
+            for (int i = 0; i < n; ++i) k15[i] = kt[i];
+            break;
+          default: /* 15, src/dopri_853.c:306-327,350-366 */
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              k4[i] = kt[i];
+              const double k16 = kt[i];
               const double ydiff = k5[i] - y[i];
               const double bspl = h * k1[i] - ydiff;
               hd[i] = y[i];
               hd[n + i] = ydiff;
               hd[2 * n + i] = bspl;
               hd[3 * n + i] = ydiff - h * k4[i] - bspl;
-              hd[4 * n + i] = DP8_D41 * k1[i] + DP8_D46 * k6[i] + DP8_D47 * k7[i] +
-                              DP8_D48 * k8[i] + DP8_D49 * k9[i] + DP8_D410 * k10[i] +
-                              DP8_D411 * k2[i] + DP8_D412 * k3[i];
-              hd[5 * n + i] = DP8_D51 * k1[i] + DP8_D56 * k6[i] + DP8_D57 * k7[i] +
-                              DP8_D58 * k8[i] + DP8_D59 * k9[i] + DP8_D510 * k10[i] +
-                              DP8_D511 * k2[i] + DP8_D512 * k3[i];
-              hd[6 * n + i] = DP8_D61 * k1[i] + DP8_D66 * k6[i] + DP8_D67 * k7[i] +
-                              DP8_D68 * k8[i] + DP8_D69 * k9[i] + DP8_D610 * k10[i] +
-                              DP8_D611 * k2[i] + DP8_D612 * k3[i];
-              hd[7 * n + i] = DP8_D71 * k1[i] + DP8_D76 * k6[i] + DP8_D77 * k7[i] +
-                              DP8_D78 * k8[i] + DP8_D79 * k9[i] + DP8_D710 * k10[i] +
-                              DP8_D711 * k2[i] + DP8_D712 * k3[i];
-            }
-            break;
-          case 13:
-#pragma unroll
-            for (int i = 0; i < n; ++i) k10[i] = kt[i];
-            break;
-          case 14:
-#pragma unroll
-            for (int i = 0; i < n; ++i) k2[i] = kt[i];
-            break;
-          default: /* 15, src/dopri_853.c:350-366 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              k3[i] = kt[i];
-              hd[4 * n + i] = h * (hd[4 * n + i] + DP8_D413 * k4[i] + DP8_D414 * k10[i] +
-                                   DP8_D415 * k2[i] + DP8_D416 * k3[i]);
-              hd[5 * n + i] = h * (hd[5 * n + i] + DP8_D513 * k4[i] + DP8_D514 * k10[i] +
-                                   DP8_D515 * k2[i] + DP8_D516 * k3[i]);
-              hd[6 * n + i] = h * (hd[6 * n + i] + DP8_D613 * k4[i] + DP8_D614 * k10[i] +
-                                   DP8_D615 * k2[i] + DP8_D616 * k3[i]);
-              hd[7 * n + i] = h * (hd[7 * n + i] + DP8_D713 * k4[i] + DP8_D714 * k10[i] +
-                                   DP8_D715 * k2[i] + DP8_D716 * k3[i]);
+              hd[4 * n + i] = h * (DP8_D41 * k1[i] + DP8_D46 * k6[i] + DP8_D47 * k7[i] +
+                                   DP8_D48 * k8[i] + DP8_D49 * k9[i] + DP8_D410 * k10[i] +
+                                   DP8_D411 * k2[i] + DP8_D412 * k3[i] + DP8_D413 * k4[i] +
+                                   DP8_D414 * k14[i] + DP8_D415 * k15[i] + DP8_D416 * k16);
+              hd[5 * n + i] = h * (DP8_D51 * k1[i] + DP8_D56 * k6[i] + DP8_D57 * k7[i] +
+                                   DP8_D58 * k8[i] + DP8_D59 * k9[i] + DP8_D510 * k10[i] +
+                                   DP8_D511 * k2[i] + DP8_D512 * k3[i] + DP8_D513 * k4[i] +
+                                   DP8_D514 * k14[i] + DP8_D515 * k15[i] + DP8_D516 * k16);
+              hd[6 * n + i] = h * (DP8_D61 * k1[i] + DP8_D66 * k6[i] + DP8_D67 * k7[i] +
+                                   DP8_D68 * k8[i] + DP8_D69 * k9[i] + DP8_D610 * k10[i] +
+                                   DP8_D611 * k2[i] + DP8_D612 * k3[i] + DP8_D613 * k4[i] +
+                                   DP8_D614 * k14[i] + DP8_D615 * k15[i] + DP8_D616 * k16);
+              hd[7 * n + i] = h * (DP8_D71 * k1[i] + DP8_D76 * k6[i] + DP8_D77 * k7[i] +
+                                   DP8_D78 * k8[i] + DP8_D79 * k9[i] + DP8_D710 * k10[i] +
+                                   DP8_D711 * k2[i] + DP8_D712 * k3[i] + DP8_D713 * k4[i] +
+                                   DP8_D714 * k14[i] + DP8_D715 * k15[i] + DP8_D716 * k16);
             }
             step_done = true;
             break;
@@ -718,6 +710,10 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
           const double theta = (tq - t_old) / h;
           const double theta1 = 1 - theta;
           double row[NMAX];
+          /* row of this time: times_idx, shifted by one without the initial row */
+          const size_t r = (size_t) traj * (size_t) nt +
+                           (size_t) (times_idx - (a.return_initial ? 0 : 1));
+          double *yo = a.y_out + r * (size_t) n;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
@@ -726,6 +722,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
           }
           if (n_out > 0) {
             double o[OMAX];
+            double *oo = a.out + r * (size_t) n_out;
             M::output((size_t) n, tq, row, (size_t) n_out, o, p);
 #pragma unroll
             for (int i = 0; i < OMAX; ++i) {
@@ -733,9 +730,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
                 oo[i] = o[i];
               }
             }
-            oo += n_out;
           }
-          yo += n;
           ++times_idx;
         }
 
@@ -753,7 +748,6 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
         }
 
         if (last) {
-          step_size_exit = h_save; /* src/dopri.c:463 */
           s_code[s] = 1;           /* OK_COMPLETE */
           done = true;
           run = false;
@@ -771,11 +765,6 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
           while (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] <= sign * t) {
             ++tcrit_idx;
           }
-          if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
-            t_stop = a.tcrit[tcrit_idx];
-          } else {
-            t_stop = t_end;
-          }
           stop = false;
         } else {
           h = h_new;
@@ -791,7 +780,8 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       a.stats[4 * traj + 3] = n_reject;
       a.code[traj] = s_code[s];
       a.t_last[traj] = t;
-      a.step_size[traj] = step_size_exit;
+      /* obj->step_size_initial on return: h_save once complete, src/dopri.c:463 */
+      a.step_size[traj] = s_code[s] == 1 ? h_save : a.step_size_initial;
       a.ring_count[traj] = s_count[s];
       active = false;
     }
