@@ -64,6 +64,32 @@ class DopriBatch:
     def run(self):
         self._check(self._lib.dde_dopri_batch_run(self._h))
 
+    def continue_(self, times, y=None, tcrit=None):
+        """dopri_continue (R/dopri.R:469-511): integrate on from where the last
+        run ended; `y` [n_traj, n] replaces the final states (and becomes the
+        pre-history), times[0] must be the time every trajectory stopped at."""
+        times = _f64(times, "times").ravel()
+        tc = None if tcrit is None else _f64(tcrit, "tcrit").ravel()
+        if y is not None and not hasattr(y, "data_ptr"):
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            if y.size != self.n * self.n_traj:
+                raise DdeError("Incorrect size 'y' on integration restart")  # src/r_dopri.c:203
+        self._check(self._lib.dde_dopri_batch_continue(
+            self._h, _ptr(y), times.ctypes.data_as(c_double_p), times.shape[0],
+            None if tc is None else tc.ctypes.data_as(c_double_p), 0 if tc is None else tc.shape[0]))
+        self.times = times
+        self.nt = times.shape[0] if self.return_initial else times.shape[0] - 1
+
+    def copy(self):
+        """dopri_data_copy (src/dopri.c:92-134): an independent handle with the same state."""
+        h = self._lib.dde_dopri_batch_copy(self._h)
+        if not h:
+            raise DdeError(_lib.last_error())
+        other = object.__new__(DopriBatch)
+        other.__dict__.update(self.__dict__)
+        other._h = h
+        return other
+
     def sync(self):
         self._check(self._lib.dde_dopri_batch_sync(self._h))
 

@@ -168,7 +168,7 @@ struct dde_dopri_batch_s {
   double *d_y_out = nullptr, *d_out = nullptr, *d_t_last = nullptr, *d_step_size = nullptr;
   int *d_stats = nullptr, *d_code = nullptr;
   double *d_ring = nullptr;
-  double *d_init_k1 = nullptr, *d_init_h = nullptr;
+  double *d_init_k1 = nullptr, *d_init_h = nullptr, *d_y_final = nullptr;
   unsigned *d_ring_count = nullptr;
   unsigned long long *d_next = nullptr;
 };
@@ -280,6 +280,9 @@ int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf, si
     case DDE_ERR_DIFEQ_HISTORY: /* src/difeq.c:268 */
       snprintf(buf, len, "difeq failure: did not find step in history");
       break;
+    case DDE_ERR_RESTART: /* src/r_dopri.c:216 */
+      snprintf(buf, len, "Incorrect initial time on integration restart");
+      break;
     case DDE_OK_COMPLETE:
     case DDE_OK_INTERRUPTED:
       snprintf(buf, len, "OK");
@@ -373,6 +376,7 @@ void dde_dopri_batch_free(dde_dopri_batch_t *b) {
   free_dev(b->d_ring);
   free_dev(b->d_init_k1);
   free_dev(b->d_init_h);
+  free_dev(b->d_y_final);
   free_dev(b->d_ring_count);
   free_dev(b->d_next);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -453,6 +457,7 @@ dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model, const dde_dopri_cont
   ok = ok && cudaMalloc(&b->d_ring_count, sizeof(unsigned) * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_init_k1, sizeof(double) * n * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_init_h, sizeof(double) * n_traj) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_y_final, sizeof(double) * n * n_traj) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_next, sizeof(unsigned long long)) == cudaSuccess;
   if (ok && ctl->n_history > 0) {
     const size_t bytes = sizeof(double) * hl * (size_t) ctl->n_history * n_traj;
@@ -574,7 +579,11 @@ int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times, size_t 
   return 0;
 }
 
-int dde_dopri_batch_run(dde_dopri_batch_t *b) {
+} /* extern "C" */
+
+namespace {
+
+int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
   if (b == nullptr) {
     return fail("NULL handle");
   }
@@ -593,9 +602,11 @@ int dde_dopri_batch_run(dde_dopri_batch_t *b) {
   if (b->reset_code != 0) {
     /* dopri_integrate returns right after reset, src/dopri.c:298-300 */
     DDE_CUDA(cudaMemsetAsync(b->d_stats, 0, sizeof(int) * 4 * b->n_traj, b->stream));
-    DDE_CUDA(cudaMemsetAsync(b->d_t_last, 0, sizeof(double) * b->n_traj, b->stream));
-    DDE_CUDA(cudaMemsetAsync(b->d_step_size, 0, sizeof(double) * b->n_traj, b->stream));
-    DDE_CUDA(cudaMemsetAsync(b->d_ring_count, 0, sizeof(unsigned) * b->n_traj, b->stream));
+    if (!restart) {
+      DDE_CUDA(cudaMemsetAsync(b->d_t_last, 0, sizeof(double) * b->n_traj, b->stream));
+      DDE_CUDA(cudaMemsetAsync(b->d_step_size, 0, sizeof(double) * b->n_traj, b->stream));
+      DDE_CUDA(cudaMemsetAsync(b->d_ring_count, 0, sizeof(unsigned) * b->n_traj, b->stream));
+    }
     const int threads = 256;
     const long long blocks = ((long long) b->n_traj + threads - 1) / threads;
     fill_int_kernel<<<(unsigned) blocks, threads, 0, b->stream>>>(b->d_code, (long long) b->n_traj,
@@ -639,6 +650,8 @@ int dde_dopri_batch_run(dde_dopri_batch_t *b) {
     a.init_k1 = b->d_init_k1;
     a.init_h = b->d_init_h;
     a.ring_count = b->d_ring_count;
+    a.restart = restart;
+    a.y_final = b->d_y_final;
     a.next_traj = b->d_next;
     int launches = 0;
     cudaError_t err = b->model->launch_dopri(b->ctl.method, a, b->device_sms, b->stream, &launches);
@@ -651,6 +664,114 @@ int dde_dopri_batch_run(dde_dopri_batch_t *b) {
   DDE_CUDA(cudaEventRecord(b->ev1, b->stream));
   b->ran = true;
   return 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int dde_dopri_batch_run(dde_dopri_batch_t *b) { return dopri_run_impl(b, 0); }
+
+/* dopri_continue, R/dopri.R:469-511 + src/r_dopri.c:193-262 */
+int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double *times,
+                             size_t n_times, const double *tcrit, size_t n_tcrit) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle: there is nothing to continue");
+  }
+  if (times == nullptr || n_times < 2) {
+    return fail("At least two times must be given"); /* src/r_dopri.c:211-213 */
+  }
+  if (b->reset_code == 0 && b->sign != copysign(1.0, times[n_times - 1] - times[0])) {
+    return fail("Incorrect sign for the times"); /* src/r_dopri.c:218-220 */
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y != nullptr) { /* a new state: it is also the pre-history from now on, src/dopri.c:157 */
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, y, sizeof(double) * b->n * b->n_traj,
+                             cudaMemcpyHostToDevice, b->stream));
+  } else {
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * b->n * b->n_traj,
+                             cudaMemcpyDeviceToDevice, b->stream));
+  }
+  const int rc = dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
+  if (rc != 0) {
+    return rc;
+  }
+  return dopri_run_impl(b, 1);
+}
+
+/* dopri_data_copy, src/dopri.c:92-134: an independent handle with the same
+   state (rings included), e.g. to continue one solve in two directions */
+dde_dopri_batch_t *dde_dopri_batch_copy(dde_dopri_batch_t *src) {
+  if (src == nullptr) {
+    fail("NULL handle");
+    return nullptr;
+  }
+  if (cudaSetDevice(src->device) != cudaSuccess || cudaStreamSynchronize(src->stream) != cudaSuccess) {
+    fail("CUDA error in dde_dopri_batch_copy");
+    (void) cudaGetLastError();
+    return nullptr;
+  }
+  dde_dopri_batch_t *b = dde_dopri_batch_alloc(src->model->name, &src->ctl, src->n, src->n_out,
+                                               src->n_parms, src->n_traj);
+  if (b == nullptr) {
+    return nullptr;
+  }
+  b->ctl = src->ctl; /* already clamped */
+  b->parms_stride = src->parms_stride;
+  b->have_y0 = src->have_y0;
+  b->sign = src->sign;
+  b->reset_code = src->reset_code;
+  const size_t nt = src->n_traj, n = src->n;
+  const size_t hl = (size_t) src->order * n + 2;
+  cudaError_t err = cudaSuccess;
+#define DDE_COPY(field, bytes)                                                              \
+  if (err == cudaSuccess && src->field != nullptr && (bytes) > 0) {                         \
+    err = cudaMemcpy(b->field, src->field, (bytes), cudaMemcpyDeviceToDevice);              \
+  }
+  DDE_COPY(d_y0, sizeof(double) * n * nt)
+  DDE_COPY(d_parms, sizeof(double) * (src->n_parms ? src->n_parms : 1) * nt)
+  DDE_COPY(d_y_final, sizeof(double) * n * nt)
+  DDE_COPY(d_t_last, sizeof(double) * nt)
+  DDE_COPY(d_step_size, sizeof(double) * nt)
+  DDE_COPY(d_stats, sizeof(int) * 4 * nt)
+  DDE_COPY(d_code, sizeof(int) * nt)
+  DDE_COPY(d_ring_count, sizeof(unsigned) * nt)
+  DDE_COPY(d_ring, sizeof(double) * hl * (size_t) src->ctl.n_history * nt)
+#undef DDE_COPY
+  if (err == cudaSuccess && src->have_times) {
+    /* results of the last run stay readable through the copy as well */
+    std::vector<double> times(src->n_times), tcrit(src->n_tcrit ? src->n_tcrit : 1);
+    err = cudaMemcpy(times.data(), src->d_times, sizeof(double) * src->n_times,
+                     cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && src->n_tcrit > 0) {
+      err = cudaMemcpy(tcrit.data(), src->d_tcrit, sizeof(double) * src->n_tcrit,
+                       cudaMemcpyDeviceToHost);
+    }
+    if (err == cudaSuccess &&
+        dde_dopri_batch_set_times(b, times.data(), src->n_times, tcrit.data(), src->n_tcrit) != 0) {
+      dde_dopri_batch_free(b);
+      return nullptr;
+    }
+    if (err == cudaSuccess) {
+      err = cudaMemcpy(b->d_y_out, src->d_y_out, sizeof(double) * n * src->nt * nt,
+                       cudaMemcpyDeviceToDevice);
+    }
+    if (err == cudaSuccess && src->n_out > 0) {
+      err = cudaMemcpy(b->d_out, src->d_out, sizeof(double) * src->n_out * src->nt * nt,
+                       cudaMemcpyDeviceToDevice);
+    }
+  }
+  if (err != cudaSuccess) {
+    fail("CUDA error in dde_dopri_batch_copy: %s", cudaGetErrorString(err));
+    (void) cudaGetLastError();
+    dde_dopri_batch_free(b);
+    return nullptr;
+  }
+  b->ran = src->ran;
+  return b;
 }
 
 int dde_dopri_batch_sync(dde_dopri_batch_t *b) {

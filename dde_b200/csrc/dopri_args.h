@@ -44,6 +44,10 @@ struct DopriArgs {
   double *ring;          /* [n_traj][n_history][order*n + 2] */
   unsigned *ring_count;  /* [n_traj] entries committed (for export) */
   int win_staged;        /* lag-window coefficients in (dynamic) shared memory */
+  /* restart (dopri_continue, src/r_dopri.c:193-262): the rings, ring_count,
+     code, t_last and step_size of the previous run are inputs */
+  int restart;
+  double *y_final;       /* [n x n_traj] obj->y on return */
   /* work distribution: next trajectory index to hand out */
   unsigned long long *next_traj;
 };

@@ -309,6 +309,18 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
     const double *p = a.parms + traj * a.parms_stride;
     const double *y0 = a.y0 + traj * n;
     double *ring = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) hl;
+    const bool cannot_restart =
+        a.restart && (a.code[traj] != 1 || a.t_last[traj] != a.times[0]);
+    const double ssi = a.restart ? a.step_size[traj] : a.step_size_initial;
+    __syncthreads(); /* everybody has read the previous run's code */
+    if (cannot_restart) { /* src/r_dopri.c:215-217 */
+      if (tid == 0) {
+        a.code[traj] = -10;
+        a.stats[4 * traj + 0] = a.stats[4 * traj + 1] = 0;
+        a.stats[4 * traj + 2] = a.stats[4 * traj + 3] = 0;
+      }
+      continue;
+    }
     if (tid == 0) { /* dopri_data_reset, src/dopri.c:138-219 */
       s_cc.sign = sign;
       s_cc.t0s = sign * a.times[0];
@@ -320,6 +332,16 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       s_cc.cap = a.n_history;
       s_cc.count = 0;
       s_cc.head = 0;
+      if (a.restart && a.n_history > 0) { /* the ring the last run left, src/dopri.c:185-191 */
+        const unsigned cap = (unsigned) a.n_history;
+        const unsigned count = a.ring_count[traj];
+        s_cc.count = count;
+        s_cc.head = (int) (count % cap);
+        if (count > 0) {
+          const unsigned used = count < cap ? count : cap;
+          s_cc.t0s = sign * ring[(size_t) ((count - used) % cap) * (size_t) hl + (hl - 2)];
+        }
+      }
       s_cc.error = 0;
       s_cc.code = 0;
       s_cc.c_valid = 0;
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
     int times_idx = 1, tcrit_idx = a.tcrit_idx0;
     int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
     unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
-    double fac_old = 1e-4, h_save = 0.0, step_size_exit = a.step_size_initial;
+    double fac_old = 1e-4, h_save = 0.0, step_size_exit = ssi;
     bool stop = false, last = false, reject = false;
     double t_stop = t_end;
     if (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] < sign * t_end) {
@@ -376,8 +398,8 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       }
     }
     if (!done) {
-      if (a.step_size_initial > 0.0) {
-        h = a.step_size_initial;
+      if (ssi > 0.0) {
+        h = ssi;
       } else {
         double term[2][CMAX];
         DDE_CLOOP(j, i) {
@@ -897,6 +919,9 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       a.t_last[traj] = t;
       a.step_size[traj] = step_size_exit;
       a.ring_count[traj] = s_cc.count;
+    }
+    if (a.y_final != nullptr) {
+      DDE_CLOOP(j, i) { a.y_final[traj * n + i] = y[j]; }
     }
 #undef DDE_COOP_EVAL
   }

@@ -56,6 +56,34 @@ namespace dde {
 #endif
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+/* Ring state a trajectory starts from: empty, or -- on a restart -- what the
+ * previous run left, in which case t0 is the oldest surviving entry's time
+ * (dopri_data_reset, src/dopri.c:185-191). */
+struct RingStart {
+  unsigned count;
+  int head;
+  double t0s; /* sign * t0 */
+};
+
+__device__ __forceinline__ RingStart ring_start(const DopriArgs &a, long long traj,
+                                                const double *ring, int hl) {
+  RingStart r;
+  r.count = 0;
+  r.head = 0;
+  r.t0s = a.sign * a.times[0];
+  if (a.restart && a.n_history > 0) {
+    const unsigned cap = (unsigned) a.n_history;
+    r.count = a.ring_count[traj];
+    r.head = (int) (r.count % cap);
+    if (r.count > 0) {
+      const unsigned used = r.count < cap ? r.count : cap;
+      const unsigned tail_slot = (r.count - used) % cap;
+      r.t0s = a.sign * ring[(size_t) tail_slot * (size_t) hl + (hl - 2)];
+    }
+  }
+  return r;
+}
+
 template <class M, int METHOD>
 __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dopri_tpt_kernel(const DopriArgs a) {
   constexpr int NC = M::N;
@@ -140,9 +168,10 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       stiff_n_stiff = stiff_n_nonstiff = 0;
       s_ring[s] = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) hl;
       s_y0[s] = y0;
-      s_t0[s] = sign * a.times[0];
-      s_count[s] = 0;
-      s_head[s] = 0;
+      const RingStart rs = ring_start(a, traj, s_ring[s], hl);
+      s_t0[s] = rs.t0s;
+      s_count[s] = rs.count;
+      s_head[s] = rs.head;
       lag_window_reset(s);
       s_code[s] = 0; /* NOT_SET */
       s_error[s] = 0;
@@ -160,7 +189,8 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       h = a.init_h[traj];
       n_eval = a.stats[4 * traj + 0];
       const int code0 = a.code[traj];
-      if (code0 == -8) { /* non-finite initial derivative, src/dopri.c:331-336 */
+      if (code0 == -8 || code0 == -10) { /* non-finite initial derivative, src/dopri.c:331-336;
+                                            or not restartable from times[0] */
         s_code[s] = code0;
         done = true;
       } else if (code0 != 0) { /* a lag look-up failed during start-up */
@@ -779,9 +809,20 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
       a.stats[4 * traj + 2] = n_accept;
       a.stats[4 * traj + 3] = n_reject;
       a.code[traj] = s_code[s];
-      a.t_last[traj] = t;
-      /* obj->step_size_initial on return: h_save once complete, src/dopri.c:463 */
-      a.step_size[traj] = s_code[s] == 1 ? h_save : a.step_size_initial;
+      if (s_code[s] == 1) {
+        a.step_size[traj] = h_save; /* obj->step_size_initial on return, src/dopri.c:463 */
+      } else if (!a.restart) {
+        a.step_size[traj] = a.step_size_initial;
+      }
+      if (s_code[s] != -10) { /* a trajectory that could not restart keeps its old state */
+        a.t_last[traj] = t;
+        if (a.y_final != nullptr) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            a.y_final[traj * n + i] = y[i];
+          }
+        }
+      }
       a.ring_count[traj] = s_count[s];
       active = false;
     }
@@ -820,6 +861,17 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
   if (traj >= a.n_traj) {
     return;
   }
+  if (a.restart && (a.code[traj] != 1 || a.t_last[traj] != a.times[0])) {
+    /* r_dopri_continue: "Incorrect initial time on integration restart"
+       (src/r_dopri.c:215-217); a failed solve has nothing to continue from */
+    a.code[traj] = -10;
+    a.stats[4 * traj + 0] = 0;
+    a.init_h[traj] = 0.0;
+    return;
+  }
+  /* obj->step_size_initial: on a restart the step the last run would have
+     taken next (src/dopri.c:463) */
+  const double ssi = a.restart ? a.step_size[traj] : a.step_size_initial;
   const double sign = a.sign, atol = a.atol, rtol = a.rtol;
   const int nt = a.return_initial ? a.n_times : a.n_times - 1;
   double p[PMAX], y[NMAX], k1[NMAX];
@@ -835,11 +887,12 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
     y[i] = y0[i];
   }
   const double t = a.times[0];
-  s_ring[s] = a.ring;
   s_y0[s] = y0;
-  s_t0[s] = sign * t;
-  s_count[s] = 0;
-  s_head[s] = 0;
+  s_ring[s] = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) (ORDER * n + 2);
+  const RingStart rs = ring_start(a, traj, s_ring[s], ORDER * n + 2);
+  s_t0[s] = rs.t0s;
+  s_count[s] = rs.count;
+  s_head[s] = rs.head;
   s_code[s] = 0;
   s_error[s] = 0;
   lag_window_reset(s);
@@ -873,8 +926,8 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
   }
   if (!finite0) {
     code = -8; /* DDE_ERR_NONFINITE_DERIV, src/dopri.c:331-336 */
-  } else if (a.step_size_initial > 0.0) {
-    h = a.step_size_initial; /* src/dopri.c:528-530 */
+  } else if (ssi > 0.0) {
+    h = ssi; /* src/dopri.c:528-530 */
   } else {
     /* dopri_h_init, src/dopri.c:527-572 */
     double norm_f = 0.0, norm_y = 0.0;

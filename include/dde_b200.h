@@ -53,6 +53,9 @@ extern "C" {
  * the solver; a batch needs a per-trajectory code instead. */
 #define DDE_ERR_NONFINITE_DERIV (-8) /* src/dopri.c:331-336 */
 #define DDE_ERR_DIFEQ_HISTORY (-9)   /* src/difeq.c:267-270 */
+/* dopri_continue from a time the trajectory did not stop at (or from a failed
+ * solve): "Incorrect initial time on integration restart", src/r_dopri.c:215-217 */
+#define DDE_ERR_RESTART (-10)
 
 /* index into stats[4 x n_traj]; order of the `statistics` attribute,
  * src/r_dopri.c:415-422 */
@@ -162,6 +165,21 @@ int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times,
 /* dopri_integrate for every trajectory, from the resident y0/parms.
  * Asynchronous on the handle's stream. */
 int dde_dopri_batch_run(dde_dopri_batch_t *b);
+/* dopri_continue (R/dopri.R:469-511, src/r_dopri.c:193-262): integrate on from
+ * where the last run of this handle ended -- the checkpoint/resume of the
+ * reference, which keeps the live solver object (`restartable = TRUE`).  The
+ * rings, the final states and the step sizes the last run would have taken
+ * next are resident; times[0] must equal the time each trajectory stopped at.
+ * y == NULL keeps the final states; a new y [n x n_traj] also becomes the
+ * pre-history (src/dopri.c:157).  A trajectory that did not complete, or
+ * stopped at another time, gets DDE_ERR_RESTART and keeps its state.
+ * Asynchronous like dde_dopri_batch_run; results through _download. */
+int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y,
+                             const double *times, size_t n_times,
+                             const double *tcrit, size_t n_tcrit);
+/* dopri_data_copy (src/dopri.c:92-134; Cdopri_copy): an independent handle
+ * with the same device state, rings included.  NULL on failure. */
+dde_dopri_batch_t *dde_dopri_batch_copy(dde_dopri_batch_t *b);
 /* Wait for the handle's stream. */
 int dde_dopri_batch_sync(dde_dopri_batch_t *b);
 /* Device -> host copy of results (any pointer may be NULL). Synchronises. */

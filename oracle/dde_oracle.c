@@ -580,7 +580,9 @@ static double integrate(solver *s, const double *y_init, const double *times, si
   s->error = 0;
   s->code = DDE_NOT_SET;
   memcpy(s->y0, y_init, n * sizeof(double));
-  memcpy(s->y, y_init, n * sizeof(double));
+  if (s->y != y_init) { /* on a restart the caller may pass the solver's own state */
+    memcpy(s->y, y_init, n * sizeof(double));
+  }
   if (times[n_times - 1] == times[0]) {
     s->error = 1;
     s->code = DDE_ERR_ZERO_TIME_DIFFERENCE;
@@ -594,10 +596,14 @@ static double integrate(solver *s, const double *y_init, const double *times, si
       return exit_step;
     }
   }
-  s->t0 = s->sign * times[0]; /* fresh object: the ring is empty */
+  /* an empty ring: a fresh start; otherwise a restart, whose pre-history ends
+     at the oldest surviving entry (src/dopri.c:185-191) */
+  s->t0 = s->history.used == 0
+              ? s->sign * times[0]
+              : s->sign * hist_slot(&s->history, 0)[(size_t) s->order * n];
   s->t = times[0];
   size_t i_time = 1, i_crit = 0;
-  while (i_crit < n_tcrit && s->sign * tcrit[i_crit] <= s->t0) {
+  while (i_crit < n_tcrit && s->sign * tcrit[i_crit] <= s->sign * times[0]) {
     i_crit++;
   }
   s->n_eval = s->n_step = s->n_accept = s->n_reject = 0;
@@ -840,6 +846,54 @@ int oracle_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n
               step_size ? step_size + j : NULL, NULL, 0, NULL);
   }
   last_seconds = now_seconds() - t_start;
+  free(scratch);
+  return 0;
+}
+
+/* dopri_continue, src/r_dopri.c:193-262: times1, then -- same solver object --
+ * times2; the outputs are those of the second segment (see ref_driver.c). */
+int oracle_dopri_batch_continue(const char *model, const dde_dopri_control *ctl, size_t n,
+                                size_t n_out, size_t n_traj, const double *y0,
+                                const double *parms, size_t n_parms, size_t parms_stride,
+                                const double *times1, size_t n_times1, const double *times2,
+                                size_t n_times2, const double *y_new, const double *tcrit2,
+                                size_t n_tcrit2, double *y_out, double *out, int32_t *stats,
+                                int32_t *code, double *t_last, double *step_size) {
+  const model_entry *m = find_model(model);
+  (void) n_parms;
+  if (m == NULL || m->deriv == NULL) {
+    return 1;
+  }
+  const size_t nt1 = ctl->return_initial ? n_times1 : n_times1 - 1;
+  const size_t nt2 = ctl->return_initial ? n_times2 : n_times2 - 1;
+  memset(y_out, 0, sizeof(double) * n * nt2 * n_traj);
+  if (out) {
+    memset(out, 0, sizeof(double) * n_out * nt2 * n_traj);
+  }
+  double *scratch = (double *) calloc(n * nt1 + n_out * nt1 + 1, sizeof(double));
+  for (size_t j = 0; j < n_traj; ++j) {
+    solver s;
+    solver_setup(&s, m, ctl, n, n_out, parms + j * parms_stride);
+    s.step_size_initial = integrate(&s, y0 + j * n, times1, n_times1, NULL, 0, scratch,
+                                    scratch + n * nt1, ctl->return_initial != 0);
+    if (s.code == DDE_OK_COMPLETE && times2[0] == s.t) {
+      s.step_size_initial =
+          integrate(&s, y_new ? y_new + j * n : s.y, times2, n_times2, tcrit2, n_tcrit2,
+                    y_out + j * n * nt2, out ? out + j * n_out * nt2 : NULL,
+                    ctl->return_initial != 0);
+    } else {
+      s.code = DDE_ERR_RESTART;
+      s.n_eval = s.n_step = s.n_accept = s.n_reject = 0;
+    }
+    stats[4 * j + DDE_STAT_N_EVAL] = (int32_t) s.n_eval;
+    stats[4 * j + DDE_STAT_N_STEP] = (int32_t) s.n_step;
+    stats[4 * j + DDE_STAT_N_ACCEPT] = (int32_t) s.n_accept;
+    stats[4 * j + DDE_STAT_N_REJECT] = (int32_t) s.n_reject;
+    code[j] = s.code;
+    t_last[j] = s.t;
+    step_size[j] = s.step_size_initial;
+    solver_release(&s);
+  }
   free(scratch);
   return 0;
 }

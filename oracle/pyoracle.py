@@ -141,6 +141,40 @@ def dopri_batch(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, n_
     return r
 
 
+def dopri_continue(backend, model, y, times1, times2, parms=None, *, y_new=None, n_out=0,
+                   tcrit2=None, **ctl_kwargs):
+    """dopri() over times1, then dopri_continue() over times2 on the same solver
+    object (src/r_dopri.c:193-262); the results are those of the second segment."""
+    lib = load(backend)
+    pre = "ref" if backend == "ref" else "oracle"
+    fn = getattr(lib, pre + "_dopri_batch_continue")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char_p, C.POINTER(Control), _SZ, _SZ, _SZ, c_double_p, c_double_p, _SZ,
+                   _SZ, c_double_p, _SZ, c_double_p, _SZ, c_double_p, c_double_p, _SZ, c_double_p,
+                   c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p]
+    ctl = control(**ctl_kwargs)
+    y, p, n_traj, n, n_parms, stride = _prep(y, parms)
+    t1 = np.ascontiguousarray(times1, dtype=np.float64)
+    t2 = np.ascontiguousarray(times2, dtype=np.float64)
+    tc = None if tcrit2 is None else np.ascontiguousarray(tcrit2, dtype=np.float64)
+    yn = None if y_new is None else np.ascontiguousarray(y_new, dtype=np.float64).reshape(n_traj, n)
+    nt = t2.shape[0] if ctl.return_initial else t2.shape[0] - 1
+    r = Result()
+    r.y = np.zeros((n_traj, nt, n))
+    r.output = np.zeros((n_traj, nt, n_out)) if n_out > 0 else None
+    r.statistics = np.zeros((n_traj, 4), dtype=np.int32)
+    r.code = np.zeros((n_traj,), dtype=np.int32)
+    r.t_last = np.zeros((n_traj,))
+    r.step_size = np.zeros((n_traj,))
+    rc = fn(model.encode(), C.byref(ctl), n, n_out, n_traj, _dp(y), _dp(p), n_parms, stride,
+            _dp(t1), t1.shape[0], _dp(t2), t2.shape[0], _dp(yn), _dp(tc),
+            0 if tc is None else tc.shape[0], _dp(r.y), _dp(r.output), _ip(r.statistics),
+            _ip(r.code), _dp(r.t_last), _dp(r.step_size))
+    if rc != 0:
+        raise RuntimeError(getattr(lib, pre + "_last_message")().decode())
+    return r
+
+
 def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, **ctl_kwargs):
     """One trajectory, also returning the `history` attribute [n_entries, order*n + 2]."""
     lib = load(backend)

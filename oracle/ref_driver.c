@@ -452,6 +452,81 @@ long ref_dopri_history(const char *model, const dde_dopri_control *ctl, size_t n
   return n_entries;
 }
 
+/* dopri_continue: every trajectory is integrated over times1, then -- the
+ * solver object kept alive, as `restartable = TRUE` does (src/r_dopri.c:432-436)
+ * -- over times2 exactly as r_dopri_continue does it (src/r_dopri.c:193-262):
+ * y_new == NULL continues from obj->y.  The outputs are those of the SECOND
+ * segment; a trajectory whose first segment failed, or that stopped at another
+ * time than times2[0], gets DDE_ERR_RESTART. */
+int ref_dopri_batch_continue(const char *model, const dde_dopri_control *ctl, size_t n,
+                             size_t n_out, size_t n_traj, const double *y0,
+                             const double *parms, size_t n_parms, size_t parms_stride,
+                             const double *times1, size_t n_times1, const double *times2,
+                             size_t n_times2, const double *y_new, const double *tcrit2,
+                             size_t n_tcrit2, double *y_out, double *out, int32_t *stats,
+                             int32_t *code, double *t_last, double *step_size) {
+  model_entry m;
+  (void) n_parms;
+  if (find_model(model, &m) != 0 || !m.deriv) {
+    return 1;
+  }
+  const size_t nt1 = ctl->return_initial ? n_times1 : n_times1 - 1;
+  const size_t nt2 = ctl->return_initial ? n_times2 : n_times2 - 1;
+  memset(y_out, 0, sizeof(double) * n * nt2 * n_traj);
+  if (out) {
+    memset(out, 0, sizeof(double) * n_out * nt2 * n_traj);
+  }
+  double *scratch = (double *) calloc(n * nt1 + n_out * nt1 + 1, sizeof(double));
+  bool *is_event = (bool *) calloc(n_tcrit2 ? n_tcrit2 : 1, sizeof(bool));
+  for (size_t j = 0; j < n_traj; ++j) {
+    dopri_data *obj = dopri_data_alloc(
+        m.deriv, n, n_out > 0 ? m.output : NULL, n_out, (void *) (parms + j * parms_stride),
+        ctl->method == DDE_DOPRI_853 ? DOPRI_853 : DOPRI_5, (size_t) ctl->n_history,
+        ctl->grow_history != 0, VERBOSE_QUIET, R_NilValue);
+    obj->rtol = ctl->rtol;
+    obj->atol = ctl->atol;
+    obj->step_size_min = fmax(fabs(ctl->step_size_min), DBL_EPSILON);
+    obj->step_size_max = fmin(fabs(ctl->step_size_max), DBL_MAX);
+    obj->step_size_initial = ctl->step_size_initial;
+    obj->step_max_n = (size_t) ctl->step_max_n;
+    obj->step_size_min_allow = ctl->step_size_min_allow != 0;
+    obj->stiff_check = (size_t) ctl->stiff_check;
+    int32_t rc = DDE_ERR_RESTART;
+    volatile int segment = 1;
+    shim_jmp_armed = 1;
+    if (setjmp(shim_jmp) == 0) {
+      dopri_integrate(obj, y0 + j * n, times1, n_times1, NULL, 0, is_event, NULL, scratch,
+                      scratch + n * nt1, ctl->return_initial != 0);
+      if (obj->code == OK_COMPLETE && times2[0] == obj->t) {
+        segment = 2;
+        dopri_integrate(obj, y_new ? y_new + j * n : obj->y, times2, n_times2, tcrit2, n_tcrit2,
+                        is_event, NULL, y_out + j * n * nt2, out ? out + j * n_out * nt2 : NULL,
+                        ctl->return_initial != 0);
+        rc = (int32_t) obj->code;
+      } else {
+        obj->n_eval = obj->n_step = obj->n_accept = obj->n_reject = 0;
+      }
+    } else if (segment == 2) {
+      rc = DDE_ERR_NONFINITE_DERIV;
+    } else {
+      obj->n_eval = obj->n_step = obj->n_accept = obj->n_reject = 0;
+    }
+    shim_jmp_armed = 0;
+    shim_release_transient();
+    stats[4 * j + DDE_STAT_N_EVAL] = (int32_t) obj->n_eval;
+    stats[4 * j + DDE_STAT_N_STEP] = (int32_t) obj->n_step;
+    stats[4 * j + DDE_STAT_N_ACCEPT] = (int32_t) obj->n_accept;
+    stats[4 * j + DDE_STAT_N_REJECT] = (int32_t) obj->n_reject;
+    code[j] = rc;
+    t_last[j] = obj->t;
+    step_size[j] = obj->step_size_initial;
+    dopri_data_free(obj);
+  }
+  free(is_event);
+  free(scratch);
+  return 0;
+}
+
 /* ---- difeq --------------------------------------------------------------- */
 
 static int32_t run_one_difeq(difeq_data *obj, size_t n, const double *y0,

@@ -332,3 +332,111 @@ def test_seir_many_parameter_free_replicates_and_long_lag(backend):
     for method in ("dopri5", "dopri853"):
         check_dopri(backend, "seir", y0, np.linspace(0, 400, 41), None, n_out=1, method=method,
                     n_history=40)
+
+
+# ---- restart: dopri_continue / dopri_data_copy -------------------------------------
+
+
+def check_continue(backend, model, y, times1, times2, parms, y_new=None, n_out=0, tcrit2=None,
+                   **kw):
+    y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    pa = None if parms is None else np.ascontiguousarray(np.atleast_2d(parms), dtype=np.float64)
+    b = dde_b200.DopriBatch(model, y.shape[1], y.shape[0],
+                            n_parms=0 if pa is None else pa.shape[1], n_out=n_out, **kw)
+    shared = pa is not None and pa.shape[0] == 1 and y.shape[0] > 1
+    b.upload(np.ascontiguousarray(y), pa, shared_parms=shared)
+    b.set_times(times1)
+    b.run()
+    b.continue_(times2, y=y_new, tcrit=tcrit2)
+    got = b.download()
+    want = pyoracle.dopri_continue(backend, model, y, times1, times2,
+                                   None if pa is None else (pa[0] if shared else pa),
+                                   y_new=y_new, n_out=n_out, tcrit2=tcrit2, **kw)
+    np.testing.assert_array_equal(got.code, want.code)
+    np.testing.assert_array_equal(got.statistics, want.statistics)
+    assert_bits_equal(got.t_last, want.t_last, "t_last")
+    assert_bits_equal(got.step_size, want.step_size, "step_size")
+    assert_bits_equal(got.y, want.y, "y")
+    if n_out:
+        assert_bits_equal(got.output, want.output, "output")
+    return b, got
+
+
+def test_continue_ode(backend):
+    lor_p = [[10.0, 28.0, 8.0 / 3.0]]
+    y0 = [[10.0, 1.0, 1.0], [1.0, 1.0, 1.0], [-3.0, 2.0, 20.0]]
+    for method in ("dopri5", "dopri853"):
+        b, got = check_continue(backend, "lorenz", y0, np.linspace(0, 2, 11), np.linspace(2, 5, 16),
+                                lor_p, n_out=2, method=method)
+        b.close()
+        # a new state at the restart (r_dopri_continue's y argument)
+        b, _ = check_continue(backend, "lorenz", y0, np.linspace(0, 2, 11), np.linspace(2, 3, 6),
+                              lor_p, y_new=np.array(y0) * 0.5, method=method, tcrit2=[2.5])
+        b.close()
+    # restart == uninterrupted run to solver tolerance (tests/testthat/test-ode.R restart
+    # tests; the split only moves one step boundary)
+    b, got = check_continue(backend, "exponential", [[1.0, 2.0]], np.linspace(0, 1, 5),
+                            np.linspace(1, 2, 5), [[0.5, 0.25]], rtol=1e-9, atol=1e-9)
+    b.close()
+    full = dde_b200.dopri_batch([[1.0, 2.0]], np.linspace(0, 2, 9), "exponential", [[0.5, 0.25]],
+                                rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got.y[0, -1], full.y[0, -1], rtol=1e-8)
+
+
+def test_continue_dde_keeps_history(backend):
+    # the ring, its oldest surviving time (t0) and the step size carry over
+    # (tests/testthat/test-dde.R:301-350); failed trajectories cannot continue
+    model, y0, parms, _, kw = workloads.mackey_glass(512, first=4096)
+    b, got = check_continue(backend, model, y0, np.linspace(0, 200, 5), np.linspace(200, 500, 7),
+                            parms, **kw)
+    assert (got.code == -10).sum() > 0 and (got.code == 1).sum() > 400
+    assert "Incorrect initial time" in got.message(int(np.argmax(got.code == -10)))
+    # a second continuation from the same handle
+    b.continue_(np.linspace(500, 600, 3))
+    third = b.download()
+    assert (third.code[got.code != 1] == -10).all()
+    b.close()
+    # the wrong start time is every trajectory's error, the wrong direction the batch's
+    b = dde_b200.DopriBatch(model, 1, 4, n_parms=3, **kw)
+    b.upload(y0[:4], parms[:4])
+    b.set_times(np.linspace(0, 50, 3))
+    b.run()
+    b.continue_([60.0, 70.0])
+    assert (b.download().code == -10).all()
+    with pytest.raises(dde_b200.DdeError, match="Incorrect sign"):
+        b.continue_([50.0, 40.0])
+    b.close()
+    for m in ("seir", "seir_int"):
+        bb, _ = check_continue(backend, m, [[1e7 - 1, 0.0, 1.0, 0.0]], np.linspace(0, 20, 21),
+                               np.linspace(20, 60, 41), None, n_out=1, method="dopri853",
+                               rtol=1e-7, atol=1e-7, n_history=1000)
+        bb.close()
+
+
+def test_continue_large_model(backend):
+    model, y0, parms, _, kw = workloads.seir_age(3)
+    b, _ = check_continue(backend, model, y0, np.linspace(0, 60, 4), np.linspace(60, 120, 4),
+                          parms, **kw)
+    b.close()
+
+
+def test_copy_is_independent(backend):
+    model, y0, parms, _, kw = workloads.mackey_glass(64, first=77)
+    a = dde_b200.DopriBatch(model, 1, 64, n_parms=3, **kw)
+    a.upload(y0, parms)
+    a.set_times(np.linspace(0, 100, 3))
+    a.run()
+    c = a.copy()
+    first = c.download()  # the copy carries the results of the run it was taken after
+    assert_bits_equal(first.y, a.download().y, "copied results")
+    c.continue_(np.linspace(100, 300, 5))
+    rc = c.download()
+    a.continue_(np.linspace(100, 300, 5))  # the original was not disturbed by the copy's run
+    ra = a.download()
+    np.testing.assert_array_equal(ra.statistics, rc.statistics)
+    assert_bits_equal(ra.y, rc.y, "y")
+    want = pyoracle.dopri_continue(backend, model, y0, np.linspace(0, 100, 3),
+                                   np.linspace(100, 300, 5), parms, **kw)
+    assert_bits_equal(ra.y, want.y, "y vs checker")
+    a.close()
+    c.close()
