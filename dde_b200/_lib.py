@@ -79,6 +79,9 @@ SYMBOLS = [
     ("dde_difeq_batch_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _SZ]),
     ("dde_difeq_batch_set_steps", C.c_int, [C.c_void_p, c_uint64_p, _SZ, C.c_int32]),
     ("dde_difeq_batch_run", C.c_int, [C.c_void_p]),
+    ("dde_difeq_batch_continue", C.c_int, [C.c_void_p, C.c_void_p, c_uint64_p, _SZ, C.c_int32]),
+    ("dde_difeq_batch_copy", C.c_void_p, [C.c_void_p]),
+    ("dde_difeq_batch_restartable", C.c_int, [C.c_void_p, C.c_int32]),
     ("dde_difeq_batch_sync", C.c_int, [C.c_void_p]),
     ("dde_difeq_batch_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),

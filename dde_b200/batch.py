@@ -142,7 +142,7 @@ class DopriBatch:
 
 
 class DifeqBatch:
-    def __init__(self, target, n, n_rep, *, n_parms=0, n_out=0, n_history=0):
+    def __init__(self, target, n, n_rep, *, n_parms=0, n_out=0, n_history=0, restartable=False):
         self._lib = _lib.load()
         self.n, self.n_rep, self.n_parms, self.n_out = int(n), int(n_rep), int(n_parms), int(n_out)
         self.n_history = int(n_history)
@@ -150,6 +150,8 @@ class DifeqBatch:
                                                   self.n_rep, self.n_history)
         if not self._h:
             raise DdeError(_lib.last_error())
+        if restartable:
+            self._lib.dde_difeq_batch_restartable(self._h, 1)
 
     def _check(self, rc):
         if rc != 0:
@@ -168,6 +170,29 @@ class DifeqBatch:
 
     def run(self):
         self._check(self._lib.dde_difeq_batch_run(self._h))
+
+    def continue_(self, steps, y=None, return_initial=True):
+        """difeq_continue (src/r_difeq.c:114-165): iterate on from the final step."""
+        st = _steps(steps)
+        if y is not None and not hasattr(y, "data_ptr"):
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            if y.size != self.n * self.n_rep:
+                raise DdeError("Incorrect size 'y' on simulation restart")
+        self._check(self._lib.dde_difeq_batch_continue(
+            self._h, _ptr(y), st.ctypes.data_as(c_uint64_p), st.shape[0],
+            int(bool(return_initial))))
+        self.steps = st
+        self.nt = st.shape[0] if return_initial else st.shape[0] - 1
+
+    def copy(self):
+        """difeq_data_copy (src/difeq.c:49-72)."""
+        h = self._lib.dde_difeq_batch_copy(self._h)
+        if not h:
+            raise DdeError(_lib.last_error())
+        other = object.__new__(DifeqBatch)
+        other.__dict__.update(self.__dict__)
+        other._h = h
+        return other
 
     def sync(self):
         self._check(self._lib.dde_difeq_batch_sync(self._h))

@@ -187,6 +187,11 @@ struct dde_difeq_batch_s {
   double *d_y_final = nullptr, *d_ring = nullptr;
   unsigned long long *d_steps = nullptr, *d_next = nullptr;
   int *d_code = nullptr;
+  unsigned *d_ring_count = nullptr;
+  bool restartable = false, kept_history = false;
+  unsigned long long steps_first = 0, steps_last = 0; /* of the steps set last */
+  unsigned long long step_origin = 0; /* first step of the handle's first run */
+  unsigned long long last_step = 0;   /* obj->step after the last run */
 };
 
 extern "C" {
@@ -1036,6 +1041,7 @@ void dde_difeq_batch_free(dde_difeq_batch_t *b) {
   free_dev(b->d_steps);
   free_dev(b->d_next);
   free_dev(b->d_code);
+  free_dev(b->d_ring_count);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -1095,6 +1101,7 @@ dde_difeq_batch_t *dde_difeq_batch_alloc(const char *model, size_t n, size_t n_o
   ok = ok && cudaMalloc(&b->d_y_final, sizeof(double) * n * n_rep) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_code, sizeof(int) * n_rep) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_next, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_ring_count, sizeof(unsigned) * n_rep) == cudaSuccess;
   if (ok && n_history > 0) {
     ok = cudaMalloc(&b->d_ring, sizeof(double) * (1 + n + n_out) * n_history * n_rep) ==
          cudaSuccess;
@@ -1162,6 +1169,8 @@ int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps, size_
                            b->stream));
   DDE_CUDA(cudaStreamSynchronize(b->stream));
   b->n_steps = n_steps;
+  b->steps_first = steps[0];
+  b->steps_last = steps[n_steps - 1];
   b->return_initial = return_initial != 0;
   b->nt = return_initial ? n_steps : n_steps - 1;
   const size_t need_y = b->n * b->nt * b->n_rep;
@@ -1185,7 +1194,11 @@ int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps, size_
   return 0;
 }
 
-int dde_difeq_batch_run(dde_difeq_batch_t *b) {
+} /* extern "C" */
+
+namespace {
+
+int difeq_run_impl(dde_difeq_batch_t *b, int restart) {
   if (b == nullptr) {
     return fail("NULL handle");
   }
@@ -1219,6 +1232,14 @@ int dde_difeq_batch_run(dde_difeq_batch_t *b) {
   a.y_final = b->d_y_final;
   a.ring = b->d_ring;
   a.next_rep = b->d_next;
+  a.restart = restart;
+  a.restartable = b->restartable ? 1 : 0;
+  a.ring_count = b->d_ring_count;
+  if (!restart) {
+    b->step_origin = b->steps_first;
+  }
+  b->kept_history = b->restartable;
+  a.step_origin = b->step_origin;
   int launches = 0;
   cudaError_t err = b->model->launch_difeq(a, b->device_sms, b->stream, &launches);
   if (err != cudaSuccess) {
@@ -1226,8 +1247,120 @@ int dde_difeq_batch_run(dde_difeq_batch_t *b) {
                 cudaGetErrorString(err));
   }
   DDE_CUDA(cudaEventRecord(b->ev1, b->stream));
+  b->last_step = b->steps_last;
   b->ran = true;
   return 0;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int dde_difeq_batch_run(dde_difeq_batch_t *b) { return difeq_run_impl(b, 0); }
+
+int dde_difeq_batch_restartable(dde_difeq_batch_t *b, int32_t on) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  b->restartable = on != 0;
+  return 0;
+}
+
+/* difeq_continue, R/difeq.R + src/r_difeq.c:114-165 */
+int dde_difeq_batch_continue(dde_difeq_batch_t *b, const double *y, const uint64_t *steps,
+                             size_t n_steps, int32_t return_initial) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle: there is nothing to continue");
+  }
+  if (steps == nullptr || n_steps < 2) {
+    return fail("At least two steps must be given"); /* src/r_difeq.c:136-138 */
+  }
+  if (steps[0] != b->last_step) {
+    return fail("Incorrect initial step on simulation restart"); /* src/r_difeq.c:139-141 */
+  }
+  if (b->n_history > 0 && !b->kept_history) {
+    return fail("the last run was not restartable: call dde_difeq_batch_restartable(b, 1) "
+                "before running (the reference's `restartable = TRUE`, R/difeq.R)");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (y != nullptr) {
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, y, sizeof(double) * b->n * b->n_rep,
+                             cudaMemcpyHostToDevice, b->stream));
+  } else { /* obj->y1, src/r_difeq.c:122-123 */
+    DDE_CUDA(cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * b->n * b->n_rep,
+                             cudaMemcpyDeviceToDevice, b->stream));
+  }
+  const int rc = dde_difeq_batch_set_steps(b, steps, n_steps, return_initial);
+  if (rc != 0) {
+    return rc;
+  }
+  return difeq_run_impl(b, 1);
+}
+
+/* difeq_data_copy, src/difeq.c:49-72 */
+dde_difeq_batch_t *dde_difeq_batch_copy(dde_difeq_batch_t *src) {
+  if (src == nullptr) {
+    fail("NULL handle");
+    return nullptr;
+  }
+  if (cudaSetDevice(src->device) != cudaSuccess || cudaStreamSynchronize(src->stream) != cudaSuccess) {
+    fail("CUDA error in dde_difeq_batch_copy");
+    (void) cudaGetLastError();
+    return nullptr;
+  }
+  dde_difeq_batch_t *b = dde_difeq_batch_alloc(src->model->name, src->n, src->n_out,
+                                               src->n_parms, src->n_rep, src->n_history);
+  if (b == nullptr) {
+    return nullptr;
+  }
+  b->parms_stride = src->parms_stride;
+  b->have_y0 = src->have_y0;
+  b->step_origin = src->step_origin;
+  b->last_step = src->last_step;
+  b->restartable = src->restartable;
+  b->kept_history = src->kept_history;
+  const size_t nr = src->n_rep, n = src->n;
+  cudaError_t err = cudaSuccess;
+#define DDE_COPY(field, bytes)                                                              \
+  if (err == cudaSuccess && src->field != nullptr && (bytes) > 0) {                         \
+    err = cudaMemcpy(b->field, src->field, (bytes), cudaMemcpyDeviceToDevice);              \
+  }
+  DDE_COPY(d_y0, sizeof(double) * n * nr)
+  DDE_COPY(d_parms, sizeof(double) * (src->n_parms ? src->n_parms : 1) * nr)
+  DDE_COPY(d_y_final, sizeof(double) * n * nr)
+  DDE_COPY(d_code, sizeof(int) * nr)
+  DDE_COPY(d_ring_count, sizeof(unsigned) * nr)
+  DDE_COPY(d_ring, sizeof(double) * (1 + n + src->n_out) * src->n_history * nr)
+#undef DDE_COPY
+  if (err == cudaSuccess && src->have_steps) {
+    std::vector<uint64_t> steps(src->n_steps);
+    err = cudaMemcpy(steps.data(), src->d_steps, sizeof(uint64_t) * src->n_steps,
+                     cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess &&
+        dde_difeq_batch_set_steps(b, steps.data(), src->n_steps, src->return_initial) != 0) {
+      dde_difeq_batch_free(b);
+      return nullptr;
+    }
+    if (err == cudaSuccess) {
+      err = cudaMemcpy(b->d_y_out, src->d_y_out, sizeof(double) * n * src->nt * nr,
+                       cudaMemcpyDeviceToDevice);
+    }
+    if (err == cudaSuccess && src->n_out > 0) {
+      err = cudaMemcpy(b->d_out, src->d_out, sizeof(double) * src->n_out * src->nt * nr,
+                       cudaMemcpyDeviceToDevice);
+    }
+  }
+  if (err != cudaSuccess) {
+    fail("CUDA error in dde_difeq_batch_copy: %s", cudaGetErrorString(err));
+    (void) cudaGetLastError();
+    dde_difeq_batch_free(b);
+    return nullptr;
+  }
+  b->ran = src->ran;
+  return b;
 }
 
 int dde_difeq_batch_sync(dde_difeq_batch_t *b) {

@@ -115,7 +115,7 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
       a.staged = 1;
     }
   }
-  auto kernel = difeq_tpt_kernel<M>;
+  auto kernel = (a.restart || a.restartable) ? difeq_tpt_kernel<M, true> : difeq_tpt_kernel<M, false>;
   cudaError_t err =
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
   if (err != cudaSuccess) {

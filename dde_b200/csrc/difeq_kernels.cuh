@@ -47,10 +47,19 @@ struct DifeqArgs {
   double *y_final; /* [n x n_rep], obj->y1 (src/difeq.c:244) */
   double *ring;    /* [n_rep][n_history][1 + n + n_out] */
   int staged;      /* history in (dynamic) shared memory instead */
+  /* restart (difeq_continue, src/r_difeq.c:114-165): ring, ring_count and code
+     of the previous run are inputs; step_origin is the step the handle's very
+     first run started at (entry k of a ring holds step_origin + k) */
+  int restart;
+  int restartable;      /* leave what a later restart needs in HBM */
+  unsigned *ring_count; /* [n_rep] entries committed */
+  unsigned long long step_origin;
   unsigned long long *next_rep;
 };
 
-template <class M>
+/* RESTART: compiled with the difeq_continue paths (start from / leave a history
+ * in HBM); the plain instantiation is ~10 % faster on C4 without them. */
+template <class M, bool RESTART>
 __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
@@ -85,6 +94,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     if (rep >= a.n_rep) {
       break;
     }
+    if (RESTART && a.restart && a.code[rep] != 1) {
+      /* a replicate whose last run failed has no state to continue from
+         ("Incorrect initial step on simulation restart", src/r_difeq.c:139-141) */
+      a.code[rep] = -10;
+      continue;
+    }
     double p[PMAX];
 #pragma unroll
     for (int i = 0; i < PMAX; ++i) {
@@ -106,14 +121,34 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     s_y0[s] = y0;
     s_step0[s] = (long long) step_first;
     s_step[s] = (long long) step;
-    s_count[s] = 0;
-    s_head[s] = 0;
     s_code[s] = 0;
     s_error[s] = 0;
     s_cfg[s] = cfg;
 
     int head = 0;
     unsigned count = 0;
+    if (RESTART && a.restart && cap > 0) {
+      /* the history the last run left; step0 is its oldest surviving entry
+         (difeq_data_reset, src/difeq.c:96-102) */
+      count = a.ring_count[rep];
+      head = (int) (count % (unsigned) cap);
+      const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
+      if (count > 0) {
+        s_step0[s] = (long long) (a.step_origin + (count - used));
+      }
+      if (a.staged) { /* back on chip */
+        for (unsigned k = 0; k < used; ++k) {
+          const double *src = ring + (size_t) k * (size_t) hl + 1;
+          double *dst = s_wc + (size_t) k * n * DDE_TPB + s;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            dst[(size_t) i * DDE_TPB] = src[i];
+          }
+        }
+      }
+    }
+    s_count[s] = count;
+    s_head[s] = head;
 #define DDE_DIFEQ_COMMIT(yy)                                  \
   do {                                                        \
     if (cap > 0) {                                            \
@@ -140,8 +175,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     }                                                         \
   } while (0)
 
-    /* the initial state is the first entry, src/difeq.c:140-156 */
-    DDE_DIFEQ_COMMIT(y);
+    /* the initial state is the first entry, src/difeq.c:140-156; on a restart
+       the ring already ends with the state the last run stopped at, and the
+       reference does not commit again (first_entry is false) */
+    if (!(RESTART && a.restart && count > 0)) {
+      DDE_DIFEQ_COMMIT(y);
+    }
 
     double *wy = a.y_out + (size_t) rep * (size_t) nt * (size_t) n;
     double *wo = has_output ? a.out + (size_t) rep * (size_t) nt * (size_t) n_out : nullptr;
@@ -220,6 +259,22 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     }
 #undef DDE_DIFEQ_COMMIT
     a.code[rep] = failed ? s_code[s] : 1; /* OK_COMPLETE */
+    if (RESTART && cap > 0 && a.restartable) {
+      /* what a later difeq_continue needs: the count, and an on-chip history
+         written back to the replicate's ring (slot order is the same) */
+      a.ring_count[rep] = count;
+      if (a.staged) {
+        const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
+        for (unsigned k = 0; k < used; ++k) {
+          double *dst = ring + (size_t) k * (size_t) hl + 1;
+          const double *src = s_wc + (size_t) k * n * DDE_TPB + s;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            dst[i] = src[(size_t) i * DDE_TPB];
+          }
+        }
+      }
+    }
   }
 }
 

@@ -243,6 +243,22 @@ int dde_difeq_batch_upload(dde_difeq_batch_t *b, const double *y0,
 int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps,
                               size_t n_steps, int32_t return_initial);
 int dde_difeq_batch_run(dde_difeq_batch_t *b);
+/* The reference's `restartable = TRUE` (R/difeq.R, src/r_difeq.c:268-271): make
+ * the following runs leave their history in HBM so that they can be continued
+ * (an on-chip history is otherwise dropped when the kernel ends).  Off by
+ * default; costs one write of the history per run. */
+int dde_difeq_batch_restartable(dde_difeq_batch_t *b, int32_t on);
+/* difeq_continue (src/r_difeq.c:114-165): iterate on from the step the last
+ * run of this handle ended at; steps[0] must be that step ("Incorrect initial
+ * step on simulation restart").  y == NULL continues from the final states
+ * (obj->y1); the history is resident.  As in the reference the restart state is
+ * not committed to the history a second time.  A replicate whose last run
+ * failed gets DDE_ERR_RESTART. */
+int dde_difeq_batch_continue(dde_difeq_batch_t *b, const double *y,
+                             const uint64_t *steps, size_t n_steps,
+                             int32_t return_initial);
+/* difeq_data_copy (src/difeq.c:49-72; Cdifeq_copy) */
+dde_difeq_batch_t *dde_difeq_batch_copy(dde_difeq_batch_t *b);
 int dde_difeq_batch_sync(dde_difeq_batch_t *b);
 int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
                              int32_t *code, double *y_final);

@@ -995,26 +995,27 @@ static void remember(iterator *it, const double *y) {
   hist_commit(&it->history);
 }
 
-/* difeq_run for one replicate with fresh state, src/difeq.c:127-258 */
-static int iterate(target_fn *target, size_t n, size_t n_out, const double *y0,
-                   const void *data, const uint64_t *steps, size_t n_steps, size_t n_history,
-                   int return_initial, double *y_out, double *out, double *y_final) {
-  iterator it;
-  memset(&it, 0, sizeof it);
-  it.n = n;
-  it.n_out = n_out;
-  it.y0 = y0;
-  it.step = it.step0 = (long long) steps[0];
-  it.have_history = n_history > 0;
-  if (it.have_history) {
-    hist_init(&it.history, n_history, 1 + n + n_out);
-  }
+/* difeq_run, src/difeq.c:127-258, on an iterator that is fresh (restart == 0)
+ * or carries the history of an earlier segment (difeq_continue). */
+static int iterate_segment(iterator *it, target_fn *target, const double *y0, const void *data,
+                           const uint64_t *steps, size_t n_steps, int return_initial,
+                           int restart, double *y_out, double *out, double *y_final) {
+  const size_t n = it->n, n_out = it->n_out;
+  it->y0 = y0;
+  it->error = 0;
+  it->step = (long long) steps[0];
+  /* difeq_data_reset, src/difeq.c:96-102: step0 is the oldest surviving entry's step */
+  it->step0 = (it->have_history && it->history.used > 0)
+                  ? (long long) hist_slot(&it->history, 0)[0]
+                  : (long long) steps[0];
   double *y = (double *) calloc(2 * n + n_out + 1, sizeof(double));
   double *y_next = y + n, *o = y + 2 * n;
   memcpy(y, y0, n * sizeof(double));
-  active_iterator = &it;
-  remember(&it, y); /* the initial state is the first entry, src/difeq.c:140-156 */
-
+  active_iterator = it;
+  if (!(restart && it->have_history && it->history.used > 0)) {
+    remember(it, y); /* the initial state is the first entry, src/difeq.c:140-156;
+                        not committed again on a restart (first_entry is false) */
+  }
   size_t i_step = 1;
   int pending_output = 0; /* the row just stored still lacks its outputs */
   if (return_initial) {
@@ -1024,41 +1025,108 @@ static int iterate(target_fn *target, size_t n, size_t n_out, const double *y0,
   }
   const long long last = (long long) steps[n_steps - 1];
   for (;;) {
-    target(n, (size_t) it.step, y, y_next, n_out, o, data);
-    if (it.error) {
+    target(n, (size_t) it->step, y, y_next, n_out, o, data);
+    if (it->error) {
       break;
     }
-    it.step++;
+    it->step++;
     memcpy(y, y_next, n * sizeof(double));
     if (n_out > 0 && pending_output) { /* src/difeq.c:204-213 */
       memcpy(out, o, n_out * sizeof(double));
       out += n_out;
       pending_output = 0;
     }
-    if (i_step < n_steps && it.step == (long long) steps[i_step]) {
+    if (i_step < n_steps && it->step == (long long) steps[i_step]) {
       memcpy(y_out, y, n * sizeof(double));
       y_out += n;
       pending_output = 1;
       i_step++;
     }
-    remember(&it, y);
-    if (it.step == last) {
+    remember(it, y);
+    if (it->step == last) {
       if (y_final) {
         memcpy(y_final, y, n * sizeof(double));
       }
       break;
     }
   }
-  if (!it.error && n_out > 0 && pending_output) { /* src/difeq.c:249-255 */
-    target(n, (size_t) it.step, y, y_next, n_out, out, data);
+  if (!it->error && n_out > 0 && pending_output) { /* src/difeq.c:249-255 */
+    target(n, (size_t) it->step, y, y_next, n_out, out, data);
   }
   active_iterator = NULL;
-  const int failed = it.error;
   free(y);
-  if (it.have_history) {
-    free(it.history.slots);
+  return it->error;
+}
+
+static void iterator_setup(iterator *it, size_t n, size_t n_out, size_t n_history) {
+  memset(it, 0, sizeof *it);
+  it->n = n;
+  it->n_out = n_out;
+  it->have_history = n_history > 0;
+  if (it->have_history) {
+    hist_init(&it->history, n_history, 1 + n + n_out);
   }
+}
+
+static void iterator_release(iterator *it) {
+  if (it->have_history) {
+    free(it->history.slots);
+  }
+}
+
+/* one replicate with fresh state */
+static int iterate(target_fn *target, size_t n, size_t n_out, const double *y0,
+                   const void *data, const uint64_t *steps, size_t n_steps, size_t n_history,
+                   int return_initial, double *y_out, double *out, double *y_final) {
+  iterator it;
+  iterator_setup(&it, n, n_out, n_history);
+  const int failed = iterate_segment(&it, target, y0, data, steps, n_steps, return_initial, 0,
+                                     y_out, out, y_final);
+  iterator_release(&it);
   return failed;
+}
+
+/* difeq_continue, src/r_difeq.c:114-165: steps1 then steps2 on the same
+ * iterator; results of the second segment (see ref_driver.c). */
+int oracle_difeq_batch_continue(const char *model, size_t n, size_t n_out, size_t n_rep,
+                                const double *y0, const double *parms, size_t n_parms,
+                                size_t parms_stride, const uint64_t *steps1, size_t n_steps1,
+                                const uint64_t *steps2, size_t n_steps2, const double *y_new,
+                                size_t n_history, int32_t return_initial, double *y_out,
+                                double *out, int32_t *code, double *y_final) {
+  const model_entry *m = find_model(model);
+  (void) n_parms;
+  if (m == NULL || m->target == NULL) {
+    return 1;
+  }
+  const size_t nt1 = return_initial ? n_steps1 : n_steps1 - 1;
+  const size_t nt2 = return_initial ? n_steps2 : n_steps2 - 1;
+  double *scratch_y = (double *) calloc(n * nt1 + n + 1, sizeof(double));
+  double *scratch_o = (double *) calloc(n_out * (nt1 > nt2 ? nt1 : nt2) + 1, sizeof(double));
+  double *y_end = scratch_y + n * nt1;
+  memset(y_out, 0, sizeof(double) * n * nt2 * n_rep);
+  if (out) {
+    memset(out, 0, sizeof(double) * n_out * nt2 * n_rep);
+  }
+  for (size_t j = 0; j < n_rep; ++j) {
+    iterator it;
+    iterator_setup(&it, n, n_out, n_history);
+    int failed = iterate_segment(&it, m->target, y0 + j * n, parms + j * parms_stride, steps1,
+                                 n_steps1, return_initial != 0, 0, scratch_y, scratch_o, y_end);
+    if (!failed && (long long) steps2[0] == it.step) {
+      failed = iterate_segment(&it, m->target, y_new ? y_new + j * n : y_end,
+                               parms + j * parms_stride, steps2, n_steps2, return_initial != 0, 1,
+                               y_out + j * n * nt2, out ? out + j * n_out * nt2 : scratch_o,
+                               y_final ? y_final + j * n : NULL);
+      code[j] = failed ? DDE_ERR_DIFEQ_HISTORY : DDE_OK_COMPLETE;
+    } else {
+      code[j] = DDE_ERR_RESTART;
+    }
+    iterator_release(&it);
+  }
+  free(scratch_y);
+  free(scratch_o);
+  return 0;
 }
 
 int oracle_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep, const double *y0,

@@ -206,6 +206,36 @@ def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, 
     return r
 
 
+def difeq_continue(backend, model, y, steps1, steps2, parms=None, *, y_new=None, n_out=0,
+                   n_history=0, return_initial=True):
+    """difeq() over steps1 then difeq_continue() over steps2 on the same object
+    (src/r_difeq.c:114-165); results of the second segment."""
+    lib = load(backend)
+    pre = "ref" if backend == "ref" else "oracle"
+    fn = getattr(lib, pre + "_difeq_batch_continue")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char_p, _SZ, _SZ, _SZ, c_double_p, c_double_p, _SZ, _SZ, c_uint64_p, _SZ,
+                   c_uint64_p, _SZ, c_double_p, _SZ, C.c_int32, c_double_p, c_double_p, c_int32_p,
+                   c_double_p]
+    y, p, n_rep, n, n_parms, stride = _prep(y, parms)
+    s1 = np.ascontiguousarray(steps1, dtype=np.uint64)
+    s2 = np.ascontiguousarray(steps2, dtype=np.uint64)
+    yn = None if y_new is None else np.ascontiguousarray(y_new, dtype=np.float64).reshape(n_rep, n)
+    nt = s2.shape[0] if return_initial else s2.shape[0] - 1
+    r = Result()
+    r.y = np.zeros((n_rep, nt, n))
+    r.output = np.zeros((n_rep, nt, n_out)) if n_out > 0 else None
+    r.code = np.zeros((n_rep,), dtype=np.int32)
+    r.y_final = np.zeros((n_rep, n))
+    rc = fn(model.encode(), n, n_out, n_rep, _dp(y), _dp(p), n_parms, stride,
+            s1.ctypes.data_as(c_uint64_p), s1.shape[0], s2.ctypes.data_as(c_uint64_p), s2.shape[0],
+            _dp(yn), n_history, int(return_initial), _dp(r.y), _dp(r.output), _ip(r.code),
+            _dp(r.y_final))
+    if rc != 0:
+        raise RuntimeError(getattr(lib, pre + "_last_message")().decode())
+    return r
+
+
 def difeq_batch(backend, model, y, steps, parms=None, *, n_out=0, n_history=0,
                 return_initial=True, shared_ring=False):
     lib = load(backend)

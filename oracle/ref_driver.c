@@ -629,3 +629,53 @@ int ref_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep,
                             parms_stride, steps, n_steps, n_history,
                             return_initial, y_out, out, code, y_final, 0);
 }
+
+/* difeq_continue (src/r_difeq.c:114-165): steps1, then -- same difeq_data
+ * object -- steps2 from y_new, or from obj->y1 when y_new is NULL.  Results of
+ * the second segment; a replicate whose first segment failed gets
+ * DDE_ERR_RESTART. */
+int ref_difeq_batch_continue(const char *model, size_t n, size_t n_out, size_t n_rep,
+                             const double *y0, const double *parms, size_t n_parms,
+                             size_t parms_stride, const uint64_t *steps1, size_t n_steps1,
+                             const uint64_t *steps2, size_t n_steps2, const double *y_new,
+                             size_t n_history, int32_t return_initial, double *y_out,
+                             double *out, int32_t *code, double *y_final) {
+  model_entry m;
+  (void) n_parms;
+  if (find_model(model, &m) != 0 || !m.target) {
+    return 1;
+  }
+  const size_t nt1 = return_initial ? n_steps1 : n_steps1 - 1;
+  const size_t nt2 = return_initial ? n_steps2 : n_steps2 - 1;
+  size_t *st1 = (size_t *) calloc(n_steps1, sizeof(size_t));
+  size_t *st2 = (size_t *) calloc(n_steps2, sizeof(size_t));
+  for (size_t i = 0; i < n_steps1; ++i) st1[i] = (size_t) steps1[i];
+  for (size_t i = 0; i < n_steps2; ++i) st2[i] = (size_t) steps2[i];
+  double *scratch_y = (double *) calloc(n * nt1 + 1, sizeof(double));
+  double *scratch_o = (double *) calloc(n_out * (nt1 > nt2 ? nt1 : nt2) + 1, sizeof(double));
+  memset(y_out, 0, sizeof(double) * n * nt2 * n_rep);
+  if (out) {
+    memset(out, 0, sizeof(double) * n_out * nt2 * n_rep);
+  }
+  for (size_t j = 0; j < n_rep; ++j) {
+    difeq_data *obj = difeq_data_alloc(m.target, n, n_out, parms + j * parms_stride, n_history,
+                                       false);
+    int32_t rc = run_one_difeq(obj, n, y0 + j * n, st1, n_steps1, scratch_y,
+                               n_out > 0 ? scratch_o : NULL, return_initial, NULL);
+    if (rc == DDE_OK_COMPLETE && st2[0] == obj->step) {
+      rc = run_one_difeq(obj, n, y_new ? y_new + j * n : obj->y1, st2, n_steps2,
+                         y_out + j * n * nt2,
+                         n_out > 0 ? (out ? out + j * n_out * nt2 : scratch_o) : NULL,
+                         return_initial, y_final ? y_final + j * n : NULL);
+    } else {
+      rc = DDE_ERR_RESTART;
+    }
+    code[j] = rc;
+    difeq_data_free(obj);
+  }
+  free(st1);
+  free(st2);
+  free(scratch_y);
+  free(scratch_o);
+  return 0;
+}

@@ -440,3 +440,73 @@ def test_copy_is_independent(backend):
     assert_bits_equal(ra.y, want.y, "y vs checker")
     a.close()
     c.close()
+
+
+def check_difeq_continue(backend, model, y, steps1, steps2, parms, y_new=None, n_out=0,
+                         n_history=0, return_initial=True):
+    y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    pa = None if parms is None else np.ascontiguousarray(np.atleast_2d(parms), dtype=np.float64)
+    b = dde_b200.DifeqBatch(model, y.shape[1], y.shape[0], n_parms=0 if pa is None else pa.shape[1],
+                            n_out=n_out, n_history=n_history, restartable=True)
+    b.upload(np.ascontiguousarray(y), pa)
+    b.set_steps(steps1, return_initial)
+    b.run()
+    b.continue_(steps2, y=y_new, return_initial=return_initial)
+    y_out, out, code, y_final = b.download()
+    want = pyoracle.difeq_continue(backend, model, y, steps1, steps2, pa, y_new=y_new, n_out=n_out,
+                                   n_history=n_history, return_initial=return_initial)
+    np.testing.assert_array_equal(code, want.code)
+    assert_bits_equal(y_out, want.y, "y")
+    ok = want.code == 1
+    assert_bits_equal(y_final[ok], want.y_final[ok], "y_final")
+    if n_out:
+        assert_bits_equal(out, want.output, "output")
+    return b, y_out, code
+
+
+def test_difeq_continue(backend):
+    # tests/testthat/test-difeq-delay.R:182-222: a restarted run continues the history
+    model, y0, parms, _, kw = workloads.sir_delay(300, n_steps=10)
+    for hist in (16, 1000, 0):
+        if hist == 0:  # the delayed model needs history; use the plain map instead
+            b, _, _ = check_difeq_continue(backend, "logistic", [[0.1, 0.2]], [0, 3, 7], [7, 9, 20],
+                                           [[1.5, 2.5]])
+            b.close()
+            continue
+        b, y2, code = check_difeq_continue(backend, model, y0, [0, 100, 150], [150, 200, 300], parms,
+                                           n_history=hist, return_initial=False)
+        assert (code == 1).all()
+        # restart == uninterrupted run, exactly: no step boundary moves in a map
+        full = dde_b200.difeq_replicate(300, y0, [0, 300], model, parms, n_history=hist,
+                                        return_step=False)
+        assert_bits_equal(np.asarray(full)[-1].T, y2[:, -1], "restart vs uninterrupted")
+        # and once more from the same handle, with a new state
+        b.continue_([300, 310], y=y2[:, -1] * 0.5, return_initial=False)
+        assert (b.download()[2] == 1).all()
+        with pytest.raises(dde_b200.DdeError, match="Incorrect initial step"):
+            b.continue_([5, 10])
+        c = b.copy()
+        c.continue_([310, 400])
+        b.continue_([310, 400])
+        assert_bits_equal(c.download()[0], b.download()[0], "copy")
+        b.close()
+        c.close()
+    # the reference's tiny-ring quirk: step0 follows the oldest surviving entry,
+    # so the first look-back after a restart is the restart state itself
+    b, y2, _ = check_difeq_continue(backend, "fib_out", [[1.0]], np.arange(6), np.arange(5, 11),
+                                    None, n_out=1, n_history=2)
+    assert y2[0, :, 0].tolist() == [13, 26, 39, 65, 104, 169]
+    b.close()
+    # a run that was not restartable dropped its on-chip history
+    nb = dde_b200.DifeqBatch("fib_out", 1, 1, n_out=1, n_history=2)
+    nb.upload(np.ones((1, 1)), None)
+    nb.set_steps(np.arange(6))
+    nb.run()
+    with pytest.raises(dde_b200.DdeError, match="not restartable"):
+        nb.continue_(np.arange(5, 11))
+    nb.close()
+    # replicates that failed cannot continue
+    model, y0, parms, _, _ = workloads.sir_delay(4, n_steps=10)
+    b, _, code = check_difeq_continue(backend, model, y0, [0, 100], [100, 120], parms, n_history=8)
+    assert (code == -10).all()
+    b.close()
