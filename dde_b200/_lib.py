@@ -60,6 +60,7 @@ SYMBOLS = [
     ("dde_dopri_batch_free", None, [C.c_void_p]),
     ("dde_dopri_batch_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _SZ]),
     ("dde_dopri_batch_set_times", C.c_int, [C.c_void_p, c_double_p, _SZ, c_double_p, _SZ]),
+    ("dde_dopri_batch_set_events", C.c_int, [C.c_void_p, c_int32_p, _SZ]),
     ("dde_dopri_batch_run", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_continue", C.c_int, [C.c_void_p, C.c_void_p, c_double_p, _SZ, c_double_p,
                                            _SZ]),

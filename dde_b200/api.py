@@ -158,13 +158,17 @@ def _prep_batch_inputs(y, parms, n_traj_hint=None):
 def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_size_min=0.0,
                 step_size_max=math.inf, step_size_initial=0.0, step_max_n=100000,
                 step_size_min_allow=False, tcrit=None, method="dopri5", stiff_check=0,
-                n_history=0, grow_history=False, return_initial=True, devices=None):
+                n_history=0, grow_history=False, return_initial=True, devices=None,
+                events=None):
     """Integrate n_traj independent trajectories of one compiled model.
 
     One call == the reference's `dopri()` run once per row of `y` (and per row
     of `parms`), concurrently on the GPU.  Arguments as R/dopri.R:293-310.
     `devices`: None = the current device; "all" or a list of device indices =
     shard the trajectories over those GPUs (dde_dopri_batch_sharded).
+    `events`: one entry per critical time -- the position of the event function
+    in the model's event table, or -1 for a plain stop (R/events.R merges
+    `event_time` into `tcrit` the same way); single device only.
     """
     lib = _lib.load()
     y, parms_arr, n_traj, n, n_parms, stride = _prep_batch_inputs(y, parms)
@@ -185,6 +189,23 @@ def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, st
             _dp(parms_arr) if n_parms else None, n_parms, stride, _dp(times), times.shape[0],
             _dp(tc), 0 if tc is None else tc.shape[0], _dp(y_out), _dp(out), _ip(stats),
             _ip(code), _dp(t_last), _dp(step_size)]
+    if events is not None:
+        if devices is not None:
+            raise DdeError("events are not supported together with 'devices'")
+        from .batch import DopriBatch
+        b = DopriBatch(func, n, n_traj, n_parms=n_parms, n_out=n_out, method=method, rtol=rtol,
+                       atol=atol, step_size_min=step_size_min, step_size_max=step_size_max,
+                       step_size_initial=step_size_initial, step_max_n=step_max_n,
+                       step_size_min_allow=step_size_min_allow, stiff_check=stiff_check,
+                       n_history=n_history, return_initial=return_initial)
+        try:
+            b.upload(y, parms_arr if n_parms else None, shared_parms=(stride == 0))
+            b.set_times(times, tc)
+            b.set_events(events)
+            b.run()
+            return b.download()
+        finally:
+            b.close()
     if devices is None:
         rc = lib.dde_dopri_batch(*args)
     else:

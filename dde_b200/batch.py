@@ -61,6 +61,13 @@ class DopriBatch:
         self.times = times
         self.nt = times.shape[0] if self.return_initial else times.shape[0] - 1
 
+    def set_events(self, events):
+        """One entry per critical time: the model's event function to apply
+        there (its position in the model's event table), or -1 for a plain stop."""
+        ev = np.ascontiguousarray(events, dtype=np.int32).ravel()
+        self._check(self._lib.dde_dopri_batch_set_events(
+            self._h, ev.ctypes.data_as(_lib.c_int32_p), ev.shape[0]))
+
     def run(self):
         self._check(self._lib.dde_dopri_batch_run(self._h))
 

@@ -169,6 +169,8 @@ struct dde_dopri_batch_s {
   int *d_stats = nullptr, *d_code = nullptr;
   double *d_ring = nullptr;
   double *d_init_k1 = nullptr, *d_init_h = nullptr, *d_y_final = nullptr;
+  int *d_event = nullptr; /* [cap_tcrit] event index per critical time, or none set */
+  bool have_events = false;
   unsigned *d_ring_count = nullptr;
   unsigned long long *d_next = nullptr;
 };
@@ -382,6 +384,7 @@ void dde_dopri_batch_free(dde_dopri_batch_t *b) {
   free_dev(b->d_init_k1);
   free_dev(b->d_init_h);
   free_dev(b->d_y_final);
+  free_dev(b->d_event);
   free_dev(b->d_ring_count);
   free_dev(b->d_next);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -562,6 +565,7 @@ int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times, size_t 
   DDE_CUDA(cudaStreamSynchronize(b->stream));
   b->n_times = n_times;
   b->n_tcrit = n_tcrit;
+  b->have_events = false; /* events belong to one set of critical times */
   b->nt = b->ctl.return_initial ? n_times : n_times - 1;
   const size_t need_y = b->n * b->nt * b->n_traj;
   const size_t need_o = b->n_out * b->nt * b->n_traj;
@@ -634,6 +638,7 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
     a.n_times = (int) b->n_times;
     a.n_tcrit = (int) b->n_tcrit;
     a.tcrit_idx0 = b->tcrit_idx0;
+    a.event = b->have_events ? b->d_event : nullptr;
     a.atol = b->ctl.atol;
     a.rtol = b->ctl.rtol;
     a.step_size_min = b->ctl.step_size_min;
@@ -676,6 +681,35 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
 extern "C" {
 
 int dde_dopri_batch_run(dde_dopri_batch_t *b) { return dopri_run_impl(b, 0); }
+
+/* is_event / events of dopri_integrate, src/dopri.h:170-171, src/r_dopri.c:77-103 */
+int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event, size_t n_tcrit) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->have_times) {
+    return fail("set the times (and critical times) before the events");
+  }
+  if (n_tcrit != b->n_tcrit) {
+    return fail("events must name one entry per critical time (%zu), got %zu", b->n_tcrit,
+                n_tcrit);
+  }
+  bool any = false;
+  for (size_t i = 0; i < n_tcrit; ++i) {
+    if (event[i] >= b->model->n_events) {
+      return fail("model '%s' has %d event functions, event %d requested", b->model->name,
+                  b->model->n_events, (int) event[i]);
+    }
+    any = any || event[i] >= 0;
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (any) {
+      DDE_CUDA(cudaMalloc(&b->d_event, sizeof(int) * n_tcrit));
+    DDE_CUDA(cudaMemcpy(b->d_event, event, sizeof(int) * n_tcrit, cudaMemcpyHostToDevice));
+  }
+  b->have_events = any;
+  return 0;
+}
 
 /* dopri_continue, R/dopri.R:469-511 + src/r_dopri.c:193-262 */
 int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double *times,

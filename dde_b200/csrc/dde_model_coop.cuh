@@ -81,6 +81,7 @@ cudaError_t launch_dopri_coop_model(int method, const DopriArgs &args, int devic
       (THREADS) * (COMPONENTS),                                                                \
       (NPARMS) >= 0 ? (NPARMS) : (THREADS) * (COMPONENTS),                                     \
       0,                                                                                       \
+      0,                                                                                       \
       &dde::launch_dopri_coop_model<dde_coop_model_##NAME, (THREADS), (COMPONENTS)>,           \
       nullptr,                                                                                 \
       nullptr};                                                                                \

@@ -28,6 +28,7 @@ struct DopriArgs {
   const double *times; /* [n_times] */
   const double *tcrit; /* [n_tcrit] */
   int n_times, n_tcrit, tcrit_idx0;
+  const int *event;    /* [n_tcrit] the model's event to apply at tcrit[i], -1: none; or NULL */
   /* controls (src/dopri.h:133-146) */
   double atol, rtol, step_size_min, step_size_max, step_size_initial;
   unsigned long long step_max_n, stiff_check;

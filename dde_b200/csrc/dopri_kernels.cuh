@@ -793,6 +793,14 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : 1)) dop
         if (stop) {
           /* critical times, src/dopri.c:476-491 */
           while (tcrit_idx < a.n_tcrit && sign * a.tcrit[tcrit_idx] <= sign * t) {
+            if (M::N_EVENTS > 0 && a.event != nullptr) {
+              /* an event changes the state (and may change the parameters) in
+                 place; k1 is NOT re-evaluated, as in the reference */
+              const int ev = a.event[tcrit_idx];
+              if (ev >= 0) {
+                M::event(ev, (size_t) n, t, y, p);
+              }
+            }
             ++tcrit_idx;
           }
           stop = false;

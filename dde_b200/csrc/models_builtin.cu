@@ -20,8 +20,11 @@ DDE_REGISTER_DOPRI(       rossler,        rossler,        3, 3)
 DDE_REGISTER_DOPRI(       mackey_glass,   mackey_glass,   1, 3)
 DDE_REGISTER_DOPRI_OUTPUT(seir,           seir,           4, -1,      seir_output,   1)
 DDE_REGISTER_DOPRI_OUTPUT(seir_int,       seir_int,       4, -1,      seir_output,   1)
-DDE_REGISTER_DOPRI(       exponential,    exponential,    0, -1)
-DDE_REGISTER_DOPRI(       linear,         linear,         0, -1)
+/* the reference's growth fixtures come with five event functions */
+DDE_EVENT_TABLE(growth_events, identity, double_variables, halve_variables, double_parameters,
+                halve_parameters)
+DDE_REGISTER_DOPRI_EVENTS(exponential,    exponential,    0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
+DDE_REGISTER_DOPRI_EVENTS(linear,         linear,         0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
 DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
 
 /*                  name       target     n  n_parms n_out */

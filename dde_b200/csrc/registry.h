@@ -25,6 +25,7 @@ struct ModelDesc {
   int n_parms;  /* >= 0 fixed; -1 = any up to DDE_DYN_MAXP */
   int n_out;    /* >= 0 fixed; -1 = any up to DDE_DYN_MAXOUT */
   int dyn_max_n, dyn_max_parms, dyn_max_out;
+  int n_events; /* event functions the model registered (src/dopri.h:53) */
   /* launchers: enqueue the kernel(s) on `stream`, return the CUDA status and
      the number of kernels launched */
   cudaError_t (*launch_dopri)(int method, const DopriArgs &args, int device_sms,

@@ -30,6 +30,37 @@ DDE_MODEL_FN void delayed_growth(size_t n, double t, const double *y,
   }
 }
 
+/* The reference's event fixtures (/root/reference/tests/testthat/growth.c:20-49):
+ * applied to the state -- or to the parameters -- at critical times. */
+DDE_MODEL_FN void identity(size_t n, double t, double *y, void *data) {
+}
+
+DDE_MODEL_FN void double_variables(size_t n, double t, double *y, void *data) {
+  for (size_t i = 0; i < n; ++i) {
+    y[i] *= 2.0;
+  }
+}
+
+DDE_MODEL_FN void halve_variables(size_t n, double t, double *y, void *data) {
+  for (size_t i = 0; i < n; ++i) {
+    y[i] /= 2.0;
+  }
+}
+
+DDE_MODEL_FN void double_parameters(size_t n, double t, double *y, void *data) {
+  double *r = (double *) data;
+  for (size_t i = 0; i < n; ++i) {
+    r[i] *= 2;
+  }
+}
+
+DDE_MODEL_FN void halve_parameters(size_t n, double t, double *y, void *data) {
+  double *r = (double *) data;
+  for (size_t i = 0; i < n; ++i) {
+    r[i] /= 2;
+  }
+}
+
 /* The same two models written for wide state vectors with the cooperative
  * macros of <dde/dde.h> (any n; the lagged state is fetched whole with
  * ylag_all). */

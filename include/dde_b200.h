@@ -162,6 +162,14 @@ int dde_dopri_batch_upload(dde_dopri_batch_t *b, const double *y0,
 int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times,
                               size_t n_times, const double *tcrit,
                               size_t n_tcrit);
+/* Events (is_event / events of dopri_integrate, src/dopri.h:170-171; R/events.R):
+ * event[i] >= 0 applies the model's event function number event[i] -- in the
+ * order of its DDE_EVENT_TABLE -- to the state when critical time tcrit[i] is
+ * reached (src/dopri.c:476-482); -1 makes tcrit[i] a plain stop.  Call after
+ * dde_dopri_batch_set_times, which clears the events.  An event function may
+ * change the trajectory's parameters; the change lasts for the run. */
+int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event,
+                               size_t n_tcrit);
 /* dopri_integrate for every trajectory, from the resident y0/parms.
  * Asynchronous on the handle's stream. */
 int dde_dopri_batch_run(dde_dopri_batch_t *b);

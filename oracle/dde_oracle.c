@@ -160,12 +160,29 @@ typedef void target_fn(size_t n, size_t step, const double *y, double *y_next, s
 #undef pow
 #undef exp
 
+typedef void event_fn(size_t n, double t, double *y, void *data); /* src/dopri.h:53 */
+
 typedef struct {
   const char *name;
   deriv_fn *deriv;
   output_fn *output;
   target_fn *target;
+  event_fn *const *events; /* in the order of the model's DDE_EVENT_TABLE */
+  int n_events;
 } model_entry;
+
+static event_fn *const growth_event_table[5] = {identity, double_variables, halve_variables,
+                                                double_parameters, halve_parameters};
+
+/* events for the dopri calls that follow (see ref_driver.c) */
+static int32_t event_index[64];
+static size_t n_event_index = 0;
+void oracle_set_events(const int32_t *index, size_t n) {
+  n_event_index = n < 64 ? n : 64;
+  for (size_t i = 0; i < n_event_index; ++i) {
+    event_index[i] = index[i];
+  }
+}
 
 static const model_entry MODELS[] = {
     {"lorenz", lorenz, lorenz_output, NULL},
@@ -173,8 +190,8 @@ static const model_entry MODELS[] = {
     {"mackey_glass", mackey_glass, NULL, NULL},
     {"seir", seir, seir_output, NULL},
     {"seir_int", seir_int, seir_output, NULL},
-    {"exponential", exponential, NULL, NULL},
-    {"linear", linear, NULL, NULL},
+    {"exponential", exponential, NULL, NULL, growth_event_table, 5},
+    {"linear", linear, NULL, NULL, growth_event_table, 5},
     {"delayed_growth", delayed_growth, NULL, NULL},
     {"exponential_wide", exponential_wide, NULL, NULL},
     {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
@@ -256,6 +273,8 @@ typedef struct {
   size_t n, n_out;
   deriv_fn *deriv;
   output_fn *output;
+  event_fn *const *events;
+  int n_events;
   const void *data;
   int order; /* 5 or 8 */
   /* controls, src/dopri.h:133-146 */
@@ -726,6 +745,12 @@ static double integrate(solver *s, const double *y_init, const double *times, si
       }
       if (stop) { /* a critical time was reached: keep the clipped h, src/dopri.c:476-494 */
         while (i_crit < n_tcrit && s->sign * tcrit[i_crit] <= s->sign * s->t) {
+          /* an event acts on the state (and maybe the parameters); k1 is left
+             as it is, src/dopri.c:478-481 */
+          if (n_event_index == n_tcrit && s->events && event_index[i_crit] >= 0 &&
+              event_index[i_crit] < s->n_events) {
+            s->events[event_index[i_crit]](n, s->t, s->y, (void *) s->data);
+          }
           i_crit++;
         }
         t_stop = (i_crit < n_tcrit && s->sign * tcrit[i_crit] < s->sign * t_end) ? tcrit[i_crit]
@@ -755,6 +780,8 @@ static void solver_setup(solver *s, const model_entry *m, const dde_dopri_contro
   s->n_out = n_out;
   s->deriv = m->deriv;
   s->output = n_out > 0 ? m->output : NULL;
+  s->events = m->events;
+  s->n_events = m->n_events;
   s->data = data;
   s->order = ctl->method == DDE_DOPRI_853 ? 8 : 5;
   s->atol = ctl->atol;

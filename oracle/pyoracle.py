@@ -110,8 +110,22 @@ def _prep(y, parms):
     return y, p, n_traj, n, n_parms, stride
 
 
+def set_events(backend, events):
+    """Events for the dopri calls that follow: one model event index (or -1) per
+    critical time; None clears."""
+    lib = load(backend)
+    fn = getattr(lib, ("ref" if backend == "ref" else "oracle") + "_set_events")
+    fn.restype = None
+    fn.argtypes = [c_int32_p, _SZ]
+    if events is None:
+        fn(None, 0)
+    else:
+        ev = np.ascontiguousarray(events, dtype=np.int32)
+        fn(ev.ctypes.data_as(c_int32_p), ev.shape[0])
+
+
 def dopri_batch(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, n_proc=0,
-                want_y=True, **ctl_kwargs):
+                want_y=True, events=None, **ctl_kwargs):
     """Run every row of y through the checker, serially (n_proc = 0) or over
     n_proc forked processes (backend "ref" only)."""
     lib = load(backend)
@@ -131,10 +145,18 @@ def dopri_batch(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, n_
     args = [model.encode(), C.byref(ctl), n, n_out, n_traj, _dp(y), _dp(p), n_parms, stride,
             _dp(times), times.shape[0], _dp(tc), 0 if tc is None else tc.shape[0], _dp(r.y),
             _dp(r.output), _ip(r.statistics), _ip(r.code), _dp(r.t_last), _dp(r.step_size)]
-    if n_proc > 0:
-        rc = getattr(lib, pre + "_dopri_batch_mp")(*args, n_proc)
-    else:
-        rc = getattr(lib, pre + "_dopri_batch")(*args)
+    if events is not None:
+        p = p.copy()  # event functions may change the parameters in place
+        args[6] = _dp(p)
+        set_events(backend, events)
+    try:
+        if n_proc > 0:
+            rc = getattr(lib, pre + "_dopri_batch_mp")(*args, n_proc)
+        else:
+            rc = getattr(lib, pre + "_dopri_batch")(*args)
+    finally:
+        if events is not None:
+            set_events(backend, None)
     if rc != 0:
         raise RuntimeError(getattr(lib, pre + "_last_message")().decode())
     r.seconds = getattr(lib, pre + "_last_seconds")()

@@ -143,7 +143,24 @@ typedef struct {
   deriv_func *deriv;
   output_func *output;
   difeq_target *target;
+  event_func *const *events; /* in the order of the model's DDE_EVENT_TABLE */
+  int n_events;
 } model_entry;
+
+static event_func *const growth_event_table[5] = {identity, double_variables, halve_variables,
+                                                  double_parameters, halve_parameters};
+
+/* Events for the dopri calls that follow (cleared by n = 0): event_index[i] >= 0
+ * applies the model's event number event_index[i] at tcrit[i], exactly the
+ * is_event / events arguments of dopri_integrate (src/r_dopri.c:77-103). */
+static int32_t event_index[64];
+static size_t n_event_index = 0;
+void ref_set_events(const int32_t *index, size_t n) {
+  n_event_index = n < 64 ? n : 64;
+  for (size_t i = 0; i < n_event_index; ++i) {
+    event_index[i] = index[i];
+  }
+}
 
 static const model_entry models[] = {
     {"lorenz", lorenz, lorenz_output, NULL},
@@ -151,8 +168,8 @@ static const model_entry models[] = {
     {"mackey_glass", mackey_glass, NULL, NULL},
     {"seir", seir, seir_output, NULL},
     {"seir_int", seir_int, seir_output, NULL},
-    {"exponential", exponential, NULL, NULL},
-    {"linear", linear, NULL, NULL},
+    {"exponential", exponential, NULL, NULL, growth_event_table, 5},
+    {"linear", linear, NULL, NULL, growth_event_table, 5},
     {"delayed_growth", delayed_growth, NULL, NULL},
     {"exponential_wide", exponential_wide, NULL, NULL},
     {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
@@ -198,6 +215,8 @@ static int find_model(const char *name, model_entry *out) {
     out->deriv = (deriv_func *) f;
     out->target = (difeq_target *) f;
     out->output = sym2[0] ? (output_func *) dlsym(h, sym2) : NULL;
+    out->events = NULL;
+    out->n_events = 0;
     return 0;
   }
   for (size_t i = 0; i < sizeof models / sizeof models[0]; ++i) {
@@ -246,10 +265,19 @@ static void run_one_dopri(const model_entry *m, const dde_dopri_control *ctl,
   obj->stiff_check = (size_t) ctl->stiff_check;
 
   bool *is_event = (bool *) calloc(n_tcrit ? n_tcrit : 1, sizeof(bool));
+  event_func **events = (event_func **) calloc(n_tcrit ? n_tcrit : 1, sizeof(event_func *));
+  if (n_event_index == n_tcrit && m->events) {
+    for (size_t i = 0; i < n_tcrit; ++i) {
+      if (event_index[i] >= 0 && event_index[i] < m->n_events) {
+        is_event[i] = true;
+        events[i] = m->events[event_index[i]];
+      }
+    }
+  }
   int32_t rc;
   shim_jmp_armed = 1;
   if (setjmp(shim_jmp) == 0) {
-    dopri_integrate(obj, y0, times, n_times, tcrit, n_tcrit, is_event, NULL,
+    dopri_integrate(obj, y0, times, n_times, tcrit, n_tcrit, is_event, events,
                     y_out, out, ctl->return_initial != 0);
     rc = (int32_t) obj->code;
   } else {
@@ -258,6 +286,7 @@ static void run_one_dopri(const model_entry *m, const dde_dopri_control *ctl,
   }
   shim_jmp_armed = 0;
   free(is_event);
+  free(events);
   shim_release_transient();
 
   if (stats) {

@@ -510,3 +510,51 @@ def test_difeq_continue(backend):
     b, _, code = check_difeq_continue(backend, model, y0, [0, 100], [100, 120], parms, n_history=8)
     assert (code == -10).all()
     b.close()
+
+
+# ---- events at critical times ---------------------------------------------------------
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dopri853"])
+def test_events(backend, method):
+    # tests/testthat/test-events.R with the reference's growth.c fixtures: events
+    # that change the state (double / halve) or the parameters, mixed with plain
+    # critical times; event order = identity, double_variables, halve_variables,
+    # double_parameters, halve_parameters
+    rng = np.random.default_rng(21)
+    for n in (1, 3):
+        y0 = rng.uniform(0.5, 2.0, size=(6, n))
+        r = rng.uniform(0.1, 1.0, size=(6, n))
+        times = np.linspace(0, 3, 13)
+        for model in ("exponential", "linear"):
+            for tcrit, ev in (([0.5, 1.0, 2.0], [1, -1, 3]), ([0.25, 1.1, 1.1, 2.9], [2, 4, 0, 1]),
+                              ([1.0], [3]), ([-1.0, 0.0, 1.5], [1, 1, 2])):
+                got = dde_b200.dopri_batch(y0, times, model, r, tcrit=tcrit, events=ev,
+                                           method=method)
+                want = pyoracle.dopri_batch(backend, model, y0, times, r, tcrit=tcrit, events=ev,
+                                            method=method)
+                np.testing.assert_array_equal(got.statistics, want.statistics)
+                np.testing.assert_array_equal(got.code, want.code)
+                assert_bits_equal(got.y, want.y, "y")
+    # analytic: doubling the state at t = 1 doubles the solution afterwards
+    # (tests/testthat/test-events.R:3-59)
+    got = dde_b200.dopri_batch([[1.0]], [0.0, 1.0, 2.0], "exponential", [[0.5]], tcrit=[1.0],
+                               events=[1], method=method, rtol=1e-9, atol=1e-9)
+    want = pyoracle.dopri_batch(backend, "exponential", [[1.0]], [0.0, 1.0, 2.0], [[0.5]],
+                                tcrit=[1.0], events=[1], method=method, rtol=1e-9, atol=1e-9)
+    assert_bits_equal(got.y, want.y, "y")
+    np.testing.assert_array_equal(got.code, want.code)
+    if method == "dopri5":
+        # (the reference does not re-evaluate k1 after an event: dop853 fails on
+        # this input there too, and so does the device)
+        np.testing.assert_allclose(got.y[0, :, 0], [1.0, np.exp(-0.5), 2 * np.exp(-1.0)],
+                                   rtol=1e-6)
+    # no such event / events without critical times
+    with pytest.raises(dde_b200.DdeError, match="event functions"):
+        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[0.5]], tcrit=[0.5], events=[7])
+    with pytest.raises(dde_b200.DdeError, match="event functions"):
+        dde_b200.dopri_batch([[10.0, 1.0, 1.0]], [0.0, 1.0], "lorenz", [10.0, 28.0, 2.0],
+                             tcrit=[0.5], events=[0])
+    with pytest.raises(dde_b200.DdeError, match="one entry per critical time"):
+        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[0.5]], tcrit=[0.5],
+                             events=[0, 1])
