@@ -223,11 +223,12 @@ class DopriResult(np.ndarray):
     step_size = None
     history = None
     output = None
+    ptr = None
 
     def __array_finalize__(self, obj):
         if obj is None:
             return
-        for name in ("statistics", "step_size", "history", "output"):
+        for name in ("statistics", "step_size", "history", "output", "ptr"):
             setattr(self, name, getattr(obj, name, None))
 
 
@@ -263,9 +264,10 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
           step_size_min_allow=False, tcrit=None, method="dopri5", stiff_check=0, n_history=0,
           grow_history=False, return_history=None, return_by_column=True, return_initial=True,
           return_time=True, return_output_with_y=True, return_statistics=False,
-          return_minimal=False):
+          return_minimal=False, restartable=False, _resume=None):
     """One trajectory; R/dopri.R:293-437.  Raises DdeError with the reference's
-    message on failure (src/r_dopri.c:264-297)."""
+    message on failure (src/r_dopri.c:264-297).  `restartable=True` keeps the
+    solver object alive in the result's `ptr` attribute for `dopri_continue`."""
     if return_history is None:
         return_history = n_history > 0
     if return_minimal:  # R/dopri.R:317-323
@@ -286,9 +288,14 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
     parms_arr = None if parms is None else np.atleast_1d(_f64(parms, "parms")).ravel()
     n_parms = 0 if parms_arr is None else parms_arr.shape[0]
     tc = None if tcrit is None else _f64(tcrit, "tcrit").ravel()
-    h = lib.dde_dopri_batch_alloc(func.encode(), C.byref(ctl), n, n_out, n_parms, 1)
-    if not h:
-        raise DdeError(_lib.last_error())
+    keep_state = False
+    if _resume is None:
+        h = lib.dde_dopri_batch_alloc(func.encode(), C.byref(ctl), n, n_out, n_parms, 1)
+        if not h:
+            raise DdeError(_lib.last_error())
+    else:
+        h, keep_state = _resume
+    keep = False
     try:
         nt = times_arr.shape[0] if return_initial else times_arr.shape[0] - 1
         y_out = np.empty((nt, n))
@@ -297,11 +304,16 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
         code = np.empty((1,), dtype=np.int32)
         t_last = np.empty((1,))
         step_size = np.empty((1,))
-        rc = lib.dde_dopri_batch_upload(h, y.ctypes.data, None if parms_arr is None else
-                                        parms_arr.ctypes.data, 0)
-        rc = rc or lib.dde_dopri_batch_set_times(h, _dp(times_arr), times_arr.shape[0], _dp(tc),
-                                                 0 if tc is None else tc.shape[0])
-        rc = rc or lib.dde_dopri_batch_run(h)
+        if _resume is None:
+            rc = lib.dde_dopri_batch_upload(h, y.ctypes.data, None if parms_arr is None else
+                                            parms_arr.ctypes.data, 0)
+            rc = rc or lib.dde_dopri_batch_set_times(h, _dp(times_arr), times_arr.shape[0],
+                                                     _dp(tc), 0 if tc is None else tc.shape[0])
+            rc = rc or lib.dde_dopri_batch_run(h)
+        else:  # dopri_continue: y is None = carry on from the final state
+            rc = lib.dde_dopri_batch_continue(h, None if keep_state else y.ctypes.data,
+                                              _dp(times_arr), times_arr.shape[0], _dp(tc),
+                                              0 if tc is None else tc.shape[0])
         rc = rc or lib.dde_dopri_batch_download(h, y_out.ctypes.data, None if out is None else
                                                 out.ctypes.data, stats.ctypes.data,
                                                 code.ctypes.data, t_last.ctypes.data,
@@ -321,8 +333,10 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
                 raise DdeError(_lib.last_error())
             history = buf[:used].copy().view(DopriHistory)
             history.n = n
+        keep = bool(restartable)
     finally:
-        lib.dde_dopri_batch_free(h)
+        if not keep:
+            lib.dde_dopri_batch_free(h)
     ret, output_attr = _bind(times_arr, y_out, out, return_time, return_output_with_y,
                              return_by_column, return_initial)
     ret = np.ascontiguousarray(ret).view(DopriResult)
@@ -331,6 +345,76 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
     if return_statistics:
         ret.statistics = dict(zip(STAT_NAMES, (int(v) for v in stats)))
         ret.step_size = float(step_size[0])
+    if keep:  # the "ptr" / "restart_data" attributes, R/dopri.R:424-436
+        ret.ptr = _DopriPtr(h, dict(func=func, n=n, n_out=n_out, rtol=rtol, atol=atol,
+                                    step_size_min=step_size_min, step_size_max=step_size_max,
+                                    step_max_n=step_max_n, step_size_min_allow=step_size_min_allow,
+                                    method=method, stiff_check=stiff_check, n_history=n_history,
+                                    t_last=float(t_last[0])))
+    return ret
+
+
+class _DopriPtr:
+    """The live solver object behind a restartable result (R: an external
+    pointer with a finaliser, src/r_dopri.c:375-392)."""
+
+    def __init__(self, handle, meta):
+        self.handle = handle
+        self.meta = meta
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().dde_dopri_batch_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def dopri_continue(obj, times, y=None, *, copy=False, tcrit=None, return_history=None,
+                   return_by_column=True, return_initial=True, return_time=True,
+                   return_output_with_y=True, return_statistics=False, restartable=False):
+    """Continue a restartable `dopri()` result; R/dopri.R:469-511."""
+    ptr = getattr(obj, "ptr", None)
+    if not isinstance(ptr, _DopriPtr) or not ptr.handle:
+        raise DdeError("Expected an object created with restartable = TRUE")
+    lib = _lib.load()
+    m = ptr.meta
+    handle = ptr.handle
+    if copy:  # dopri_copy, then continue the copy: the original stays usable
+        handle = lib.dde_dopri_batch_copy(ptr.handle)
+        if not handle:
+            raise DdeError(_lib.last_error())
+    elif restartable:
+        ptr.handle = None  # ownership moves to the new result
+    times_arr = _f64(times, "times").ravel()
+    if times_arr.shape[0] >= 1 and times_arr[0] != m["t_last"]:
+        if copy:
+            lib.dde_dopri_batch_free(handle)
+        elif restartable:
+            ptr.handle = handle
+        raise DdeError("Incorrect initial time on integration restart")  # src/r_dopri.c:216
+    if y is not None and np.size(y) != m["n"]:
+        raise DdeError("Incorrect size 'y' on integration restart")  # src/r_dopri.c:203
+    keep_alive = restartable or not copy
+    ret = dopri(np.zeros(m["n"]) if y is None else y, times_arr, m["func"], None, n_out=m["n_out"],
+                rtol=m["rtol"], atol=m["atol"], step_size_min=m["step_size_min"],
+                step_size_max=m["step_size_max"], step_max_n=m["step_max_n"],
+                step_size_min_allow=m["step_size_min_allow"], tcrit=tcrit, method=m["method"],
+                stiff_check=m["stiff_check"], n_history=m["n_history"],
+                return_history=return_history, return_by_column=return_by_column,
+                return_initial=return_initial, return_time=return_time,
+                return_output_with_y=return_output_with_y, return_statistics=return_statistics,
+                restartable=keep_alive, _resume=(handle, y is None))
+    if not restartable:
+        if copy:
+            ret.ptr = None  # the temporary copy is freed with its _DopriPtr
+        else:
+            # the original object keeps its (advanced) solver, as in R without copy
+            ptr.handle = ret.ptr.handle
+            ptr.meta = ret.ptr.meta
+            ret.ptr.handle = None
+            ret.ptr = None
     return ret
 
 

@@ -558,3 +558,26 @@ def test_events(backend, method):
     with pytest.raises(dde_b200.DdeError, match="one entry per critical time"):
         dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[0.5]], tcrit=[0.5],
                              events=[0, 1])
+
+
+def test_dopri_continue_r_style(backend):
+    # dopri(..., restartable = TRUE) then dopri_continue(): R/dopri.R:469-511
+    p = [10.0, 28.0, 8.0 / 3.0]
+    first = dde_b200.dopri([10.0, 1.0, 1.0], np.linspace(0, 2, 11), "lorenz", p, restartable=True)
+    assert first.ptr is not None
+    second = dde_b200.dopri_continue(first, np.linspace(2, 4, 11), copy=True,
+                                     return_statistics=True)
+    again = dde_b200.dopri_continue(first, np.linspace(2, 4, 11), copy=True)
+    assert_bits_equal(np.asarray(second), np.asarray(again), "copy leaves the original alone")
+    want = pyoracle.dopri_continue(backend, "lorenz", [10.0, 1.0, 1.0], np.linspace(0, 2, 11),
+                                   np.linspace(2, 4, 11), p)
+    assert_bits_equal(np.asarray(second)[:, 1:], want.y[0], "y")
+    assert second.statistics["n_step"] == want.statistics[0, 1]
+    with pytest.raises(dde_b200.DdeError, match="Incorrect initial time"):
+        dde_b200.dopri_continue(first, np.linspace(3, 4, 3))
+    with pytest.raises(dde_b200.DdeError, match="restartable"):
+        dde_b200.dopri_continue(second, np.linspace(4, 5, 3))
+    third = dde_b200.dopri_continue(first, np.linspace(2, 4, 11))  # advances `first` itself
+    assert_bits_equal(np.asarray(third), np.asarray(second), "in place")
+    fourth = dde_b200.dopri_continue(first, np.linspace(4, 5, 6), restartable=True)
+    assert fourth.ptr is not None and np.asarray(fourth)[0, 0] == 4.0
