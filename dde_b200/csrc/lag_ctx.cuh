@@ -148,10 +148,14 @@ extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when stage
 /* debug build only: [0] misses above, [1] misses below, [2] misses on an empty
    window, [3] entries appended by lag_window_ensure, [4] failures, [5] ring
    probes of the search, [6] queries answered from the ring directly */
-static __device__ unsigned long long dde_lag_stats[8];
+static __device__ unsigned long long dde_lag_stats[16];
 #define DDE_LAG_COUNT(i) atomicAdd(&dde_lag_stats[i], 1ULL)
 #define DDE_LAG_TRACE(...) ((void) 0)
+/* the same build checks every ring / window index it forms (compute-sanitizer
+   is not available on the GPU pool): violations are counted in slot [15] */
+#define DDE_CHECK(cond) ((cond) ? (void) 0 : (void) atomicAdd(&dde_lag_stats[15], 1ULL))
 #else
+#define DDE_CHECK(cond) ((void) 0)
 #define DDE_LAG_TRACE(...) ((void) 0)
 #define DDE_LAG_COUNT(i) ((void) 0)
 #endif
@@ -175,6 +179,8 @@ __device__ __forceinline__ int ring_slot_back(int head, int back, int cap) {
 /* ring slot of logical entry idx (0 = first entry ever committed) */
 __device__ __forceinline__ const double *ring_entry(int s, unsigned idx) {
   const int slot = ring_slot_back(s_head[s], (int) (s_count[s] - idx), s_lag_u.cap);
+  DDE_CHECK(idx < s_count[s] && s_count[s] - idx <= (unsigned) s_lag_u.cap && slot >= 0 &&
+            slot < s_lag_u.cap);
   return s_ring[s] + (size_t) slot * (size_t) s_lag_u.hl;
 }
 
@@ -207,6 +213,7 @@ __device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
   const unsigned count = s_count[s];
   const double *e = ring_entry(s, idx);
   const int w = (int) (idx % DDE_WIN);
+  DDE_CHECK(s_wn[s] <= DDE_WIN);
   double top = pos_inf();
   if (idx + 1 < count) {
     top = sign * ring_entry(s, idx + 1)[nc];
@@ -496,6 +503,8 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
   if (below > 0 && st < s_wtop[s]) {
     hit.idx = s_wbase[s] + below - 1;
     hit.slot = (int) (hit.idx % DDE_WIN);
+    DDE_CHECK(below <= s_wn[s] && hit.idx < s_count[s] &&
+              s_count[s] - hit.idx <= (unsigned) s_lag_u.cap);
     hit.t_old = sign * s_wt[hit.slot][s];
     hit.h = s_wh[hit.slot][s];
     return hit;

@@ -37,7 +37,7 @@ DDE_REGISTER_DIFEQ(sir_delay, sir_delay, 3, 2,      0)
 #ifdef DDE_LAG_STATS
 /* debug build only: read and clear the lag-window counters of this module */
 extern "C" void dde_debug_lag_stats(unsigned long long *out) {
-  unsigned long long zero[8] = {0};
+  unsigned long long zero[16] = {0};
   cudaMemcpyFromSymbol(out, dde::dde_lag_stats, sizeof zero);
   cudaMemcpyToSymbol(dde::dde_lag_stats, zero, sizeof zero);
 }
