@@ -33,7 +33,7 @@ namespace dde {
 template <class M, int METHOD, int TPT, int CMAX>
 cudaError_t launch_dopri_coop_method(const DopriArgs &args, int device_sms, cudaStream_t stream) {
   auto kernel = dopri_coop_kernel<M, METHOD, TPT, CMAX>;
-  const size_t dyn = sizeof(double) * 4 * (size_t) args.n + DDE_COOP_SCRATCH_BYTES;
+  const size_t dyn = sizeof(double) * DDE_COOP_NVEC * (size_t) args.n + DDE_COOP_SCRATCH_BYTES;
   cudaError_t err =
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
   if (err != cudaSuccess) {

@@ -5,15 +5,17 @@
  * Same reference semantics as dopri_kernels.cuh (it restates the same code:
  * /root/reference/src/dopri.c:138-219,291-572, src/dopri_5.c, src/dopri_853.c),
  * different mapping:
- *   - thread `tid` owns components tid, tid + TPT, tid + 2 TPT, ... (at most
- *     CMAX of them) of y, k1..k10 and of the dense-output coefficients, in
- *     registers; every per-component loop of the reference becomes a loop over
- *     the thread's components, so ring commits, output rows and lag reads are
- *     coalesced along the component index;
- *   - the model's deriv() is called by the whole block at once on a stage
- *     vector staged in shared memory (the cooperative model ABI of
- *     <dde/dde.h>: DDE_FOR / DDE_SCRATCH / DDE_SYNC), one inlined instance
- *     inside a block-uniform stage loop;
+ *   - the solver object (y, k1..k10, the stage input) is a set of shared-memory
+ *     vectors; thread `tid` works on components tid, tid + TPT, ... of every
+ *     per-component loop of the reference, so ring commits, output rows and lag
+ *     reads are coalesced along the component index, registers stay few and
+ *     several blocks are resident per SM;
+ *   - the stage loops are driven by the tableau as data (lists of
+ *     (slot, weight) terms in constant memory, summed left to right exactly as
+ *     the reference's expressions), so the code is a few small loops;
+ *   - the model's deriv() is called by the whole block at once and reads the
+ *     stage vector / writes the derivative slot in place (the cooperative model
+ *     ABI of <dde/dde.h>: DDE_FOR / DDE_SCRATCH / DDE_SYNC);
  *   - control flow is uniform across the block (one t, one h, one
  *     accept/reject decision per block), so there is no divergence at all;
  *     blocks are persistent and fetch trajectories from an atomic counter;
@@ -65,7 +67,7 @@ struct CoopCtx {
 };
 
 __shared__ CoopCtx s_cc;
-extern __shared__ double s_coop_dyn[]; /* yin[n] dydt[n] red[2n] scratch[...] */
+extern __shared__ double s_coop_dyn[]; /* 16 solver vectors of n doubles, then model scratch */
 
 __device__ __forceinline__ double coop_na_real() {
   return __longlong_as_double(0x7FF00000000007A2LL);
@@ -184,8 +186,8 @@ __device__ __forceinline__ void coop_ylag_indexed(double t, const Index *idx, si
 /* ---- the model-facing functions, collective versions ------------------------ */
 
 static __device__ __forceinline__ char *dde_coop_scratch(void) {
-  /* after yin, dydt, red[2n] */
-  return (char *) (dde::s_coop_dyn + 4 * (size_t) dde::s_cc.n);
+  /* after the DDE_COOP_NVEC solver vectors */
+  return (char *) (dde::s_coop_dyn + 16 * (size_t) dde::s_cc.n);
 }
 
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
@@ -228,24 +230,101 @@ namespace dde {
 
 __device__ __forceinline__ double csq(double x) { return x * x; }
 
-/* Sum term[i], i = 0 .. n-1, in that order (the reference's loops), from the
- * per-thread terms of components tid + j TPT.  One or two sums at a time. */
-template <int TPT, int CMAX, int NSUM>
-__device__ __forceinline__ void coop_seqsum(int n, const double (*term)[CMAX], double *result) {
-  double *red = s_coop_dyn + 2 * (size_t) n;
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < NSUM; ++k) {
-#pragma unroll
-    for (int j = 0; j < CMAX; ++j) {
-      const int i = tid + j * TPT;
-      if (i < n) {
-        red[(size_t) k * n + i] = term[k][j];
-      }
-    }
-  }
+/* ---- tableaux as data: the stage loops below walk lists of (slot, weight)
+ * terms, each sum formed left to right over the same terms in the same order
+ * as the reference's hand-written expressions (src/dopri_5.c:54-94,
+ * src/dopri_853.c:178-246,315-363).  Slot j is the reference's k[j-1]. */
+struct CoopTerm {
+  int k;
+  double a;
+};
+struct CoopStage {
+  double c; /* node; 1.0 means t + h exactly as the reference computes it */
+  int dst;  /* slot that receives f(t + c h, stage input) */
+  int n_terms;
+  CoopTerm t[9];
+};
+
+static __constant__ CoopStage c_dp5_stages[6] = {
+    {DP5_C2_LIT, 2, 1, {{1, DP5_A21_LIT}}},
+    {DP5_C3_LIT, 3, 2, {{1, DP5_A31_LIT}, {2, DP5_A32_LIT}}},
+    {DP5_C4_LIT, 4, 3, {{1, DP5_A41_LIT}, {2, DP5_A42_LIT}, {3, DP5_A43_LIT}}},
+    {DP5_C5_LIT, 5, 4, {{1, DP5_A51_LIT}, {2, DP5_A52_LIT}, {3, DP5_A53_LIT}, {4, DP5_A54_LIT}}},
+    {1.0, 6, 5,
+     {{1, DP5_A61_LIT}, {2, DP5_A62_LIT}, {3, DP5_A63_LIT}, {4, DP5_A64_LIT}, {5, DP5_A65_LIT}}},
+    {1.0, 2, 5,
+     {{1, DP5_A71_LIT}, {3, DP5_A73_LIT}, {4, DP5_A74_LIT}, {5, DP5_A75_LIT}, {6, DP5_A76_LIT}}},
+};
+static __constant__ CoopTerm c_dp5_err[6] = {{1, DP5_E1_LIT}, {3, DP5_E3_LIT}, {4, DP5_E4_LIT},
+                                             {5, DP5_E5_LIT}, {6, DP5_E6_LIT}, {2, DP5_E7_LIT}};
+static __constant__ CoopTerm c_dp5_dense[6] = {{1, DP5_D1_LIT}, {3, DP5_D3_LIT}, {4, DP5_D4_LIT},
+                                               {5, DP5_D5_LIT}, {6, DP5_D6_LIT}, {2, DP5_D7_LIT}};
+static __constant__ CoopStage c_dp8_stages[11] = {
+    {DP8_C2_LIT, 2, 1, {{1, DP8_A21_LIT}}},
+    {DP8_C3_LIT, 3, 2, {{1, DP8_A31_LIT}, {2, DP8_A32_LIT}}},
+    {DP8_C4_LIT, 4, 2, {{1, DP8_A41_LIT}, {3, DP8_A43_LIT}}},
+    {DP8_C5_LIT, 5, 3, {{1, DP8_A51_LIT}, {3, DP8_A53_LIT}, {4, DP8_A54_LIT}}},
+    {DP8_C6_LIT, 6, 3, {{1, DP8_A61_LIT}, {4, DP8_A64_LIT}, {5, DP8_A65_LIT}}},
+    {DP8_C7_LIT, 7, 4, {{1, DP8_A71_LIT}, {4, DP8_A74_LIT}, {5, DP8_A75_LIT}, {6, DP8_A76_LIT}}},
+    {DP8_C8_LIT, 8, 5,
+     {{1, DP8_A81_LIT}, {4, DP8_A84_LIT}, {5, DP8_A85_LIT}, {6, DP8_A86_LIT}, {7, DP8_A87_LIT}}},
+    {DP8_C9_LIT, 9, 6,
+     {{1, DP8_A91_LIT}, {4, DP8_A94_LIT}, {5, DP8_A95_LIT}, {6, DP8_A96_LIT}, {7, DP8_A97_LIT},
+      {8, DP8_A98_LIT}}},
+    {DP8_C10_LIT, 10, 7,
+     {{1, DP8_A101_LIT}, {4, DP8_A104_LIT}, {5, DP8_A105_LIT}, {6, DP8_A106_LIT},
+      {7, DP8_A107_LIT}, {8, DP8_A108_LIT}, {9, DP8_A109_LIT}}},
+    {DP8_C11_LIT, 2, 8,
+     {{1, DP8_A111_LIT}, {4, DP8_A114_LIT}, {5, DP8_A115_LIT}, {6, DP8_A116_LIT},
+      {7, DP8_A117_LIT}, {8, DP8_A118_LIT}, {9, DP8_A119_LIT}, {10, DP8_A1110_LIT}}},
+    {1.0, 3, 9,
+     {{1, DP8_A121_LIT}, {4, DP8_A124_LIT}, {5, DP8_A125_LIT}, {6, DP8_A126_LIT},
+      {7, DP8_A127_LIT}, {8, DP8_A128_LIT}, {9, DP8_A129_LIT}, {10, DP8_A1210_LIT},
+      {2, DP8_A1211_LIT}}},
+};
+static __constant__ CoopTerm c_dp8_b[8] = {{1, DP8_B1_LIT}, {6, DP8_B6_LIT},   {7, DP8_B7_LIT},
+                                           {8, DP8_B8_LIT}, {9, DP8_B9_LIT},   {10, DP8_B10_LIT},
+                                           {2, DP8_B11_LIT}, {3, DP8_B12_LIT}};
+static __constant__ CoopTerm c_dp8_er[8] = {{1, DP8_ER1_LIT}, {6, DP8_ER6_LIT},   {7, DP8_ER7_LIT},
+                                            {8, DP8_ER8_LIT}, {9, DP8_ER9_LIT},   {10, DP8_ER10_LIT},
+                                            {2, DP8_ER11_LIT}, {3, DP8_ER12_LIT}};
+static __constant__ CoopStage c_dp8_extra[3] = {
+    {DP8_C14_LIT, 10, 8,
+     {{1, DP8_A141_LIT}, {7, DP8_A147_LIT}, {8, DP8_A148_LIT}, {9, DP8_A149_LIT},
+      {10, DP8_A1410_LIT}, {2, DP8_A1411_LIT}, {3, DP8_A1412_LIT}, {4, DP8_A1413_LIT}}},
+    {DP8_C15_LIT, 2, 8,
+     {{1, DP8_A151_LIT}, {6, DP8_A156_LIT}, {7, DP8_A157_LIT}, {8, DP8_A158_LIT},
+      {2, DP8_A1511_LIT}, {3, DP8_A1512_LIT}, {4, DP8_A1513_LIT}, {10, DP8_A1514_LIT}}},
+    {DP8_C16_LIT, 3, 8,
+     {{1, DP8_A161_LIT}, {6, DP8_A166_LIT}, {7, DP8_A167_LIT}, {8, DP8_A168_LIT},
+      {9, DP8_A169_LIT}, {4, DP8_A1613_LIT}, {10, DP8_A1614_LIT}, {2, DP8_A1615_LIT}}},
+};
+static __constant__ CoopTerm c_dp8_d1[4][8] = {
+    {{1, DP8_D41_LIT}, {6, DP8_D46_LIT}, {7, DP8_D47_LIT}, {8, DP8_D48_LIT}, {9, DP8_D49_LIT},
+     {10, DP8_D410_LIT}, {2, DP8_D411_LIT}, {3, DP8_D412_LIT}},
+    {{1, DP8_D51_LIT}, {6, DP8_D56_LIT}, {7, DP8_D57_LIT}, {8, DP8_D58_LIT}, {9, DP8_D59_LIT},
+     {10, DP8_D510_LIT}, {2, DP8_D511_LIT}, {3, DP8_D512_LIT}},
+    {{1, DP8_D61_LIT}, {6, DP8_D66_LIT}, {7, DP8_D67_LIT}, {8, DP8_D68_LIT}, {9, DP8_D69_LIT},
+     {10, DP8_D610_LIT}, {2, DP8_D611_LIT}, {3, DP8_D612_LIT}},
+    {{1, DP8_D71_LIT}, {6, DP8_D76_LIT}, {7, DP8_D77_LIT}, {8, DP8_D78_LIT}, {9, DP8_D79_LIT},
+     {10, DP8_D710_LIT}, {2, DP8_D711_LIT}, {3, DP8_D712_LIT}},
+};
+static __constant__ CoopTerm c_dp8_d2[4][4] = {
+    {{4, DP8_D413_LIT}, {10, DP8_D414_LIT}, {2, DP8_D415_LIT}, {3, DP8_D416_LIT}},
+    {{4, DP8_D513_LIT}, {10, DP8_D514_LIT}, {2, DP8_D515_LIT}, {3, DP8_D516_LIT}},
+    {{4, DP8_D613_LIT}, {10, DP8_D614_LIT}, {2, DP8_D615_LIT}, {3, DP8_D616_LIT}},
+    {{4, DP8_D713_LIT}, {10, DP8_D714_LIT}, {2, DP8_D715_LIT}, {3, DP8_D716_LIT}},
+};
+
+/* shared-memory vectors of one trajectory, n doubles each */
+#define DDE_COOP_NVEC 16 /* y, k1..k10, stage input, 4 x scratch */
+
+/* Sum red[k][i], i = 0 .. n-1, in that order (the reference's loops), from the
+ * terms all threads have written.  NSUM <= 2 sums at a time. */
+template <int NSUM>
+__device__ __forceinline__ void coop_seqsum(int n, const double *red, double *result) {
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     double acc[NSUM];
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) {
@@ -271,15 +350,18 @@ __device__ __forceinline__ void coop_seqsum(int n, const double (*term)[CMAX], d
 }
 
 template <class M, int METHOD, int TPT, int CMAX>
-__global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
+__global__ void __launch_bounds__(TPT, (TPT >= 256 ? 2 : (TPT >= 128 ? 4 : 8))) dopri_coop_kernel(const DopriArgs a) {
   constexpr int ORDER = METHOD == 0 ? 5 : 8;
-  constexpr int NST_STEP = METHOD == 0 ? 6 : 11;
-  constexpr int NST = METHOD == 0 ? 6 : 16;
   const int n = a.n;
   const int hl = ORDER * n + 2;
   const int tid = threadIdx.x;
-  double *yin_s = s_coop_dyn;
-  double *dydt_s = s_coop_dyn + n;
+  /* the solver object of src/dopri.h:55-161 for one trajectory, in shared memory */
+  double *Y = s_coop_dyn;               /* obj->y */
+  double *K = s_coop_dyn + n;           /* obj->k[0..9]: slot j at K + (j - 1) n */
+  double *YIN = s_coop_dyn + 11 * (size_t) n; /* obj->y1: the stage input */
+  double *RED = s_coop_dyn + 12 * (size_t) n; /* 4 n: norm terms / dense coefficients in the making */
+#define KV(j) (K + (size_t) ((j) -1) * n)
+#define DDE_EACH(i) for (int i = tid; i < n; i += TPT)
 
   constexpr double step_factor_min = METHOD == 0 ? 0.2 : 0.333;
   constexpr double step_factor_max = METHOD == 0 ? 10.0 : 6.0;
@@ -290,10 +372,6 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
   const int n_times = a.n_times;
   const int nt = a.return_initial ? n_times : n_times - 1;
   const double t_end = a.times[n_times - 1];
-
-#define DDE_CLOOP(j, i)                                        \
-  _Pragma("unroll") for (int j = 0; j < CMAX; ++j)             \
-    if (const int i = tid + j * TPT; i < n)
 
   for (;;) {
     /* ---- next trajectory (persistent blocks) ---- */
@@ -346,10 +424,9 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       s_cc.code = 0;
       s_cc.c_valid = 0;
     }
+    DDE_EACH(i) { Y[i] = y0[i]; }
     __syncthreads();
 
-    double y[CMAX], k1[CMAX];
-    DDE_CLOOP(j, i) { y[j] = y0[i]; }
     double t = a.times[0];
     int times_idx = 1, tcrit_idx = a.tcrit_idx0;
     int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
@@ -362,34 +439,46 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
     }
     double *yo = a.y_out + (size_t) traj * (size_t) nt * (size_t) n;
     if (a.return_initial) { /* src/dopri.c:320-327 */
-      DDE_CLOOP(j, i) { yo[i] = y[j]; }
+      DDE_EACH(i) { yo[i] = Y[i]; }
       yo += n;
     }
 
-    /* one RHS evaluation by the whole block, src/dopri.c:831-835 */
-#define DDE_COOP_EVAL(tt, src, dst)                                  \
-  do {                                                               \
-    DDE_CLOOP(j_, i_) { yin_s[i_] = (src)[j_]; }                     \
-    __syncthreads();                                                 \
-    M::deriv((size_t) n, (tt), yin_s, dydt_s, p);                    \
-    __syncthreads();                                                 \
-    DDE_CLOOP(j_, i_) { (dst)[j_] = dydt_s[i_]; }                    \
-    ++n_eval;                                                        \
+    /* one RHS evaluation by the whole block, src/dopri.c:831-835: the stage
+       vector and the derivative slot are shared-memory vectors, so the model
+       reads and writes them in place */
+#define DDE_COOP_EVAL(tt, src, dst)                \
+  do {                                             \
+    __syncthreads();                               \
+    M::deriv((size_t) n, (tt), (src), (dst), p);   \
+    __syncthreads();                               \
+    ++n_eval;                                      \
+  } while (0)
+    /* stage input y + h * (sum of the stage's terms) into `into`, then its evaluation */
+#define DDE_COOP_STAGE(st, first, into)                                              \
+  do {                                                                               \
+    const CoopStage &st_ = (st);                                                     \
+    DDE_EACH(i) {                                                                    \
+      if (first) { /* written h * A21 * k1, i.e. (h A21) k1 */                       \
+        (into)[i] = Y[i] + h * st_.t[0].a * KV(1)[i];                                \
+      } else {                                                                       \
+        double acc = st_.t[0].a * KV(st_.t[0].k)[i];                                 \
+        for (int q = 1; q < st_.n_terms; ++q) {                                      \
+          acc = acc + st_.t[q].a * KV(st_.t[q].k)[i];                                \
+        }                                                                            \
+        (into)[i] = Y[i] + h * acc;                                                  \
+      }                                                                              \
+    }                                                                                \
+    DDE_COOP_EVAL(st_.c == 1.0 ? t + h : t + st_.c * h, (into), KV(st_.dst));        \
   } while (0)
 
     bool done = false;
     double h = 0.0;
     /* k1 = f(t0, y0), finiteness check, dopri_h_init: src/dopri.c:329-339,527-572 */
-    DDE_COOP_EVAL(t, y, k1);
+    DDE_COOP_EVAL(t, Y, KV(1));
     {
-      double bad[1][CMAX];
-#pragma unroll
-      for (int j = 0; j < CMAX; ++j) {
-        bad[0][j] = 0.0;
-      }
-      DDE_CLOOP(j, i) { bad[0][j] = isfinite(k1[j]) ? 0.0 : 1.0; }
+      DDE_EACH(i) { RED[i] = isfinite(KV(1)[i]) ? 0.0 : 1.0; }
       double nbad;
-      coop_seqsum<TPT, CMAX, 1>(n, bad, &nbad);
+      coop_seqsum<1>(n, RED, &nbad);
       if (nbad > 0.0) {
         if (tid == 0) {
           s_cc.code = -8; /* DDE_ERR_NONFINITE_DERIV */
@@ -401,27 +490,25 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       if (ssi > 0.0) {
         h = ssi;
       } else {
-        double term[2][CMAX];
-        DDE_CLOOP(j, i) {
-          const double sk = atol + rtol * fabs(y[j]);
-          term[0][j] = csq(k1[j] / sk);
-          term[1][j] = csq(y[j] / sk);
+        DDE_EACH(i) {
+          const double sk = atol + rtol * fabs(Y[i]);
+          RED[i] = csq(KV(1)[i] / sk);
+          RED[n + i] = csq(Y[i] / sk);
         }
         double norms[2];
-        coop_seqsum<TPT, CMAX, 2>(n, term, norms);
+        coop_seqsum<2>(n, RED, norms);
         const double norm_f = norms[0], norm_y = norms[1];
         h = (norm_f <= 1e-10 || norm_y <= 1e-10) ? 1e-6 : sqrt(norm_y / norm_f) * 0.01;
         h = copysign(fmin(h, a.step_size_max), sign);
-        double ye[CMAX], f1[CMAX];
-        DDE_CLOOP(j, i) { ye[j] = y[j] + h * k1[j]; }
-        DDE_COOP_EVAL(t + h, ye, f1);
-        double term2[1][CMAX];
-        DDE_CLOOP(j, i) {
-          const double sk = atol + rtol * fabs(y[j]);
-          term2[0][j] = csq((f1[j] - k1[j]) / sk);
+        /* the reference uses k[1] for f1 and k[2] for the Euler point */
+        DDE_EACH(i) { KV(3)[i] = Y[i] + h * KV(1)[i]; }
+        DDE_COOP_EVAL(t + h, KV(3), KV(2));
+        DDE_EACH(i) {
+          const double sk = atol + rtol * fabs(Y[i]);
+          RED[i] = csq((KV(2)[i] - KV(1)[i]) / sk);
         }
         double der2;
-        coop_seqsum<TPT, CMAX, 1>(n, term2, &der2);
+        coop_seqsum<1>(n, RED, &der2);
         der2 = sqrt(der2) / h;
         const double der12 = fmax(fabs(der2), sqrt(norm_f));
         const double h1 = (der12 <= 1e-15) ? fmax(1e-6, fabs(h) * 1e-3)
@@ -465,422 +552,227 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       }
       ++n_step;
 
-      double k2[CMAX], k3[CMAX], k4[CMAX], k5[CMAX], k6[CMAX], k7[CMAX], k8[CMAX], k9[CMAX],
-          k10[CMAX], ysave[CMAX], hd[ORDER * CMAX], yin[CMAX], kt[CMAX];
-      bool accepted = false, step_done = false, lag_failed = false, gave_up = false;
-      double h_new = 0.0;
-
+      /* ---- dopri_step + dopri_error ---- */
+      double err;
+      if (METHOD == 0) {
+        /* dopri5_step, src/dopri_5.c:42-95: stage 5 is formed in `ysti` (slot 7) */
 #pragma unroll 1
-      for (int st = 0; st < NST; ++st) {
-        if (st >= NST_STEP && !accepted) {
+        for (int j = 0; j < 6; ++j) {
+          DDE_COOP_STAGE(c_dp5_stages[j], j == 0, j == 4 ? KV(7) : YIN);
+        }
+        DDE_EACH(i) {
+          /* the fifth dense coefficient, formed on every attempt before k4 is
+             overwritten (src/dopri_5.c:84-94) */
+          double d = c_dp5_dense[0].a * KV(c_dp5_dense[0].k)[i];
+          double e = c_dp5_err[0].a * KV(c_dp5_err[0].k)[i];
+#pragma unroll
+          for (int q = 1; q < 6; ++q) {
+            d = d + c_dp5_dense[q].a * KV(c_dp5_dense[q].k)[i];
+            e = e + c_dp5_err[q].a * KV(c_dp5_err[q].k)[i];
+          }
+          RED[3 * (size_t) n + i] = h * d;
+          KV(4)[i] = h * e;
+          const double sk = atol + rtol * fmax(fabs(Y[i]), fabs(YIN[i]));
+          RED[i] = csq(KV(4)[i] / sk);
+        }
+        if (s_cc.error) { /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
           break;
         }
-        double tt;
-        /* -- the input of evaluation st (block-uniform switch) -- */
-        if (METHOD == 0) {
-          switch (st) { /* dopri5_step, src/dopri_5.c:54-80 */
-            case 0:
-              DDE_CLOOP(j, i) { yin[j] = y[j] + h * DP5_A21 * k1[j]; }
-              tt = t + DP5_C2 * h;
-              break;
-            case 1:
-              DDE_CLOOP(j, i) { yin[j] = y[j] + h * (DP5_A31 * k1[j] + DP5_A32 * k2[j]); }
-              tt = t + DP5_C3 * h;
-              break;
-            case 2:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP5_A41 * k1[j] + DP5_A42 * k2[j] + DP5_A43 * k3[j]);
-              }
-              tt = t + DP5_C4 * h;
-              break;
-            case 3:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP5_A51 * k1[j] + DP5_A52 * k2[j] + DP5_A53 * k3[j] +
-                                     DP5_A54 * k4[j]);
-              }
-              tt = t + DP5_C5 * h;
-              break;
-            case 4:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP5_A61 * k1[j] + DP5_A62 * k2[j] + DP5_A63 * k3[j] +
-                                     DP5_A64 * k4[j] + DP5_A65 * k5[j]);
-                ysave[j] = yin[j];
-              }
-              tt = t + h;
-              break;
-            default:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP5_A71 * k1[j] + DP5_A73 * k3[j] + DP5_A74 * k4[j] +
-                                     DP5_A75 * k5[j] + DP5_A76 * k6[j]);
-              }
-              tt = t + h;
-              break;
-          }
-        } else {
-          switch (st) { /* dopri853_step, src/dopri_853.c:178-240; :304,330-347 */
-            case 0:
-              DDE_CLOOP(j, i) { yin[j] = y[j] + h * DP8_A21 * k1[j]; }
-              tt = t + DP8_C2 * h;
-              break;
-            case 1:
-              DDE_CLOOP(j, i) { yin[j] = y[j] + h * (DP8_A31 * k1[j] + DP8_A32 * k2[j]); }
-              tt = t + DP8_C3 * h;
-              break;
-            case 2:
-              DDE_CLOOP(j, i) { yin[j] = y[j] + h * (DP8_A41 * k1[j] + DP8_A43 * k3[j]); }
-              tt = t + DP8_C4 * h;
-              break;
-            case 3:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A51 * k1[j] + DP8_A53 * k3[j] + DP8_A54 * k4[j]);
-              }
-              tt = t + DP8_C5 * h;
-              break;
-            case 4:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A61 * k1[j] + DP8_A64 * k4[j] + DP8_A65 * k5[j]);
-              }
-              tt = t + DP8_C6 * h;
-              break;
-            case 5:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A71 * k1[j] + DP8_A74 * k4[j] + DP8_A75 * k5[j] +
-                                     DP8_A76 * k6[j]);
-              }
-              tt = t + DP8_C7 * h;
-              break;
-            case 6:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A81 * k1[j] + DP8_A84 * k4[j] + DP8_A85 * k5[j] +
-                                     DP8_A86 * k6[j] + DP8_A87 * k7[j]);
-              }
-              tt = t + DP8_C8 * h;
-              break;
-            case 7:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A91 * k1[j] + DP8_A94 * k4[j] + DP8_A95 * k5[j] +
-                                     DP8_A96 * k6[j] + DP8_A97 * k7[j] + DP8_A98 * k8[j]);
-              }
-              tt = t + DP8_C9 * h;
-              break;
-            case 8:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A101 * k1[j] + DP8_A104 * k4[j] + DP8_A105 * k5[j] +
-                                     DP8_A106 * k6[j] + DP8_A107 * k7[j] + DP8_A108 * k8[j] +
-                                     DP8_A109 * k9[j]);
-              }
-              tt = t + DP8_C10 * h;
-              break;
-            case 9:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A111 * k1[j] + DP8_A114 * k4[j] + DP8_A115 * k5[j] +
-                                     DP8_A116 * k6[j] + DP8_A117 * k7[j] + DP8_A118 * k8[j] +
-                                     DP8_A119 * k9[j] + DP8_A1110 * k10[j]);
-              }
-              tt = t + DP8_C11 * h;
-              break;
-            case 10:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A121 * k1[j] + DP8_A124 * k4[j] + DP8_A125 * k5[j] +
-                                     DP8_A126 * k6[j] + DP8_A127 * k7[j] + DP8_A128 * k8[j] +
-                                     DP8_A129 * k9[j] + DP8_A1210 * k10[j] + DP8_A1211 * k2[j]);
-                ysave[j] = yin[j];
-              }
-              tt = t + h;
-              break;
-            case 11: /* the redundant evaluation at the OLD time, src/dopri.c:400-403 */
-              DDE_CLOOP(j, i) { yin[j] = k5[j]; }
-              tt = t;
-              break;
-            case 12: /* src/dopri_853.c:304 */
-              DDE_CLOOP(j, i) { yin[j] = k5[j]; }
-              tt = t + h;
-              break;
-            case 13:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A141 * k1[j] + DP8_A147 * k7[j] + DP8_A148 * k8[j] +
-                                     DP8_A149 * k9[j] + DP8_A1410 * k10[j] + DP8_A1411 * k2[j] +
-                                     DP8_A1412 * k3[j] + DP8_A1413 * k4[j]);
-              }
-              tt = t + DP8_C14 * h;
-              break;
-            case 14:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A151 * k1[j] + DP8_A156 * k6[j] + DP8_A157 * k7[j] +
-                                     DP8_A158 * k8[j] + DP8_A1511 * k2[j] + DP8_A1512 * k3[j] +
-                                     DP8_A1513 * k4[j] + DP8_A1514 * k10[j]);
-              }
-              tt = t + DP8_C15 * h;
-              break;
-            default:
-              DDE_CLOOP(j, i) {
-                yin[j] = y[j] + h * (DP8_A161 * k1[j] + DP8_A166 * k6[j] + DP8_A167 * k7[j] +
-                                     DP8_A168 * k8[j] + DP8_A169 * k9[j] + DP8_A1613 * k4[j] +
-                                     DP8_A1614 * k10[j] + DP8_A1615 * k2[j]);
-              }
-              tt = t + DP8_C16 * h;
-              break;
-          }
-        }
-
-        /* -- the one hot copy of the model -- */
-        DDE_COOP_EVAL(tt, yin, kt);
-
-        /* -- file the result -- */
-        bool attempt_done = false;
-        if (METHOD == 0) {
-          switch (st) {
-            case 0: DDE_CLOOP(j, i) { k2[j] = kt[j]; } break;
-            case 1: DDE_CLOOP(j, i) { k3[j] = kt[j]; } break;
-            case 2: DDE_CLOOP(j, i) { k4[j] = kt[j]; } break;
-            case 3: DDE_CLOOP(j, i) { k5[j] = kt[j]; } break;
-            case 4: DDE_CLOOP(j, i) { k6[j] = kt[j]; } break;
-            default:
-              DDE_CLOOP(j, i) { k2[j] = kt[j]; }
-              attempt_done = true;
-              break;
-          }
-        } else {
-          switch (st) {
-            case 0: DDE_CLOOP(j, i) { k2[j] = kt[j]; } break;
-            case 1: DDE_CLOOP(j, i) { k3[j] = kt[j]; } break;
-            case 2: DDE_CLOOP(j, i) { k4[j] = kt[j]; } break;
-            case 3: DDE_CLOOP(j, i) { k5[j] = kt[j]; } break;
-            case 4: DDE_CLOOP(j, i) { k6[j] = kt[j]; } break;
-            case 5: DDE_CLOOP(j, i) { k7[j] = kt[j]; } break;
-            case 6: DDE_CLOOP(j, i) { k8[j] = kt[j]; } break;
-            case 7: DDE_CLOOP(j, i) { k9[j] = kt[j]; } break;
-            case 8: DDE_CLOOP(j, i) { k10[j] = kt[j]; } break;
-            case 9: DDE_CLOOP(j, i) { k2[j] = kt[j]; } break;
-            case 10: /* src/dopri_853.c:242-246 */
-              DDE_CLOOP(j, i) {
-                k3[j] = kt[j];
-                k4[j] = DP8_B1 * k1[j] + DP8_B6 * k6[j] + DP8_B7 * k7[j] + DP8_B8 * k8[j] +
-                        DP8_B9 * k9[j] + DP8_B10 * k10[j] + DP8_B11 * k2[j] + DP8_B12 * k3[j];
-                k5[j] = y[j] + h * k4[j];
-              }
-              attempt_done = true;
-              break;
-            case 11: DDE_CLOOP(j, i) { k4[j] = kt[j]; } break;
-            case 12: /* src/dopri_853.c:306-327 */
-              DDE_CLOOP(j, i) {
-                k4[j] = kt[j];
-                const double ydiff = k5[j] - y[j];
-                const double bspl = h * k1[j] - ydiff;
-                hd[0 * CMAX + j] = y[j];
-                hd[1 * CMAX + j] = ydiff;
-                hd[2 * CMAX + j] = bspl;
-                hd[3 * CMAX + j] = ydiff - h * k4[j] - bspl;
-                hd[4 * CMAX + j] = DP8_D41 * k1[j] + DP8_D46 * k6[j] + DP8_D47 * k7[j] +
-                                   DP8_D48 * k8[j] + DP8_D49 * k9[j] + DP8_D410 * k10[j] +
-                                   DP8_D411 * k2[j] + DP8_D412 * k3[j];
-                hd[5 * CMAX + j] = DP8_D51 * k1[j] + DP8_D56 * k6[j] + DP8_D57 * k7[j] +
-                                   DP8_D58 * k8[j] + DP8_D59 * k9[j] + DP8_D510 * k10[j] +
-                                   DP8_D511 * k2[j] + DP8_D512 * k3[j];
-                hd[6 * CMAX + j] = DP8_D61 * k1[j] + DP8_D66 * k6[j] + DP8_D67 * k7[j] +
-                                   DP8_D68 * k8[j] + DP8_D69 * k9[j] + DP8_D610 * k10[j] +
-                                   DP8_D611 * k2[j] + DP8_D612 * k3[j];
-                hd[7 * CMAX + j] = DP8_D71 * k1[j] + DP8_D76 * k6[j] + DP8_D77 * k7[j] +
-                                   DP8_D78 * k8[j] + DP8_D79 * k9[j] + DP8_D710 * k10[j] +
-                                   DP8_D711 * k2[j] + DP8_D712 * k3[j];
-              }
-              break;
-            case 13: DDE_CLOOP(j, i) { k10[j] = kt[j]; } break;
-            case 14: DDE_CLOOP(j, i) { k2[j] = kt[j]; } break;
-            default: /* 15, src/dopri_853.c:350-366 */
-              DDE_CLOOP(j, i) {
-                k3[j] = kt[j];
-                hd[4 * CMAX + j] = h * (hd[4 * CMAX + j] + DP8_D413 * k4[j] + DP8_D414 * k10[j] +
-                                        DP8_D415 * k2[j] + DP8_D416 * k3[j]);
-                hd[5 * CMAX + j] = h * (hd[5 * CMAX + j] + DP8_D513 * k4[j] + DP8_D514 * k10[j] +
-                                        DP8_D515 * k2[j] + DP8_D516 * k3[j]);
-                hd[6 * CMAX + j] = h * (hd[6 * CMAX + j] + DP8_D613 * k4[j] + DP8_D614 * k10[j] +
-                                        DP8_D615 * k2[j] + DP8_D616 * k3[j]);
-                hd[7 * CMAX + j] = h * (hd[7 * CMAX + j] + DP8_D713 * k4[j] + DP8_D714 * k10[j] +
-                                        DP8_D715 * k2[j] + DP8_D716 * k3[j]);
-              }
-              step_done = true;
-              break;
-          }
-        }
-
-        if (attempt_done) {
-          if (s_cc.error) { /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
-            lag_failed = true;
-            break;
-          }
-          double err;
-          if (METHOD == 0) { /* dopri5_error, src/dopri_5.c:97-104 (see dopri_kernels.cuh) */
-            double term[1][CMAX];
-            DDE_CLOOP(j, i) {
-              const double ke = h * (DP5_E1 * k1[j] + DP5_E3 * k3[j] + DP5_E4 * k4[j] +
-                                     DP5_E5 * k5[j] + DP5_E6 * k6[j] + DP5_E7 * k2[j]);
-              const double sk = atol + rtol * fmax(fabs(y[j]), fabs(yin[j]));
-              term[0][j] = csq(ke / sk);
-            }
-            coop_seqsum<TPT, CMAX, 1>(n, term, &err);
-            err = sqrt(err / (double) n);
-          } else { /* dopri853_error, src/dopri_853.c:249-283 */
-            double term[2][CMAX];
-            DDE_CLOOP(j, i) {
-              const double sk = atol + rtol * fmax(fabs(y[j]), fabs(k5[j]));
-              double erri = k4[j] - DP8_BHH1 * k1[j] - DP8_BHH2 * k9[j] - DP8_BHH3 * k3[j];
-              term[1][j] = csq(erri / sk);
-              erri = DP8_ER1 * k1[j] + DP8_ER6 * k6[j] + DP8_ER7 * k7[j] + DP8_ER8 * k8[j] +
-                     DP8_ER9 * k9[j] + DP8_ER10 * k10[j] + DP8_ER11 * k2[j] + DP8_ER12 * k3[j];
-              term[0][j] = csq(erri / sk);
-            }
-            double sums[2];
-            coop_seqsum<TPT, CMAX, 2>(n, term, sums);
-            double deno = sums[0] + 0.01 * sums[1];
-            deno = deno < 0 ? 1.0 : deno;
-            err = sign * sums[0] * sqrt(1.0 / ((double) n * deno));
-          }
-          /* dopri_h_new, src/dopri.c:516-525 */
-          const double fac11 = dde_pow(err, step_constant);
-          const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
-          double fac = fac11 / facb;
-          fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
-          h_new = h / fac;
-          accepted = (err <= 1) || force_this_step;
-          if (accepted) {
-            fac_old = fmax(err, 1e-4);
-            ++n_accept;
-            if (METHOD == 0) {
-              step_done = true;
-            }
-          } else { /* src/dopri.c:495-509 */
-            h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);
-            reject = true;
-            if (n_accept >= 1) {
-              ++n_reject;
-            }
-            last = false;
-            stop = false;
-            h = h_new;
-          }
-        }
-
-        /* dopri_test_stiff, src/dopri.c:668-693 */
-        if ((METHOD == 0 ? step_done : st == 11) && a.stiff_check != 0 &&
-            (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
-          double term[2][CMAX];
-          DDE_CLOOP(j, i) {
-            if (METHOD == 0) {
-              term[0][j] = csq(k2[j] - k6[j]);
-              term[1][j] = csq(yin[j] - ysave[j]);
-            } else {
-              term[0][j] = csq(k4[j] - k3[j]);
-              term[1][j] = csq(k5[j] - ysave[j]);
-            }
-          }
-          double sums[2];
-          coop_seqsum<TPT, CMAX, 2>(n, term, sums);
-          const bool stiff = sums[1] > 0 &&
-                             fabs(h) * sqrt(sums[0] / sums[1]) > (METHOD == 0 ? 3.25 : 6.1);
-          if (stiff) {
-            stiff_n_nonstiff = 0;
-            if (stiff_n_stiff++ >= 15) {
-              gave_up = true;
-            }
-          } else if (stiff_n_stiff > 0) {
-            if (stiff_n_nonstiff++ >= 6) {
-              stiff_n_stiff = 0;
-            }
-          }
-          if (gave_up) {
-            break;
-          }
-        }
-      } /* stages */
-
-      if (lag_failed) {
-        break;
-      }
-      if (gave_up) {
-        if (tid == 0) {
-          s_cc.error = 1;
-          s_cc.code = -7; /* ERR_STIFF */
-        }
-        break;
-      }
-      if (!step_done) {
-        continue; /* rejected: next attempt */
-      }
-
-      /* ---- the rest of an accepted step, src/dopri.c:410-494 ---- */
-      if (METHOD == 0) { /* dopri5_save_history, src/dopri_5.c:106-118,84-89; yin is y1 */
-        DDE_CLOOP(j, i) {
-          const double ydiff = yin[j] - y[j];
-          const double bspl = h * k1[j] - ydiff;
-          hd[0 * CMAX + j] = y[j];
-          hd[1 * CMAX + j] = ydiff;
-          hd[2 * CMAX + j] = bspl;
-          hd[3 * CMAX + j] = -h * k2[j] + ydiff - bspl;
-          hd[4 * CMAX + j] = h * (DP5_D1 * k1[j] + DP5_D3 * k3[j] + DP5_D4 * k4[j] +
-                                  DP5_D5 * k5[j] + DP5_D6 * k6[j] + DP5_D7 * k2[j]);
-        }
-        DDE_CLOOP(j, i) {
-          k1[j] = k2[j];
-          y[j] = yin[j];
-        }
+        coop_seqsum<1>(n, RED, &err);
+        err = sqrt(err / (double) n);
       } else {
-        DDE_CLOOP(j, i) {
-          k1[j] = k4[j];
-          y[j] = k5[j];
+        /* dopri853_step, src/dopri_853.c:159-247 */
+#pragma unroll 1
+        for (int j = 0; j < 11; ++j) {
+          DDE_COOP_STAGE(c_dp8_stages[j], j == 0, YIN);
+        }
+        DDE_EACH(i) {
+          double b = c_dp8_b[0].a * KV(c_dp8_b[0].k)[i];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) {
+            b = b + c_dp8_b[q].a * KV(c_dp8_b[q].k)[i];
+          }
+          KV(4)[i] = b;
+          KV(5)[i] = Y[i] + h * b;
+          /* dopri853_error, src/dopri_853.c:249-283 */
+          const double sk = atol + rtol * fmax(fabs(Y[i]), fabs(KV(5)[i]));
+          double erri = KV(4)[i] - DP8_BHH1 * KV(1)[i] - DP8_BHH2 * KV(9)[i] - DP8_BHH3 * KV(3)[i];
+          RED[n + i] = csq(erri / sk);
+          erri = c_dp8_er[0].a * KV(c_dp8_er[0].k)[i];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) {
+            erri = erri + c_dp8_er[q].a * KV(c_dp8_er[q].k)[i];
+          }
+          RED[i] = csq(erri / sk);
+        }
+        if (s_cc.error) {
+          break;
+        }
+        double sums[2];
+        coop_seqsum<2>(n, RED, sums);
+        double deno = sums[0] + 0.01 * sums[1];
+        deno = deno < 0 ? 1.0 : deno;
+        err = sign * sums[0] * sqrt(1.0 / ((double) n * deno));
+      }
+
+      /* dopri_h_new, src/dopri.c:516-525 */
+      const double fac11 = dde_pow(err, step_constant);
+      const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
+      double fac = fac11 / facb;
+      fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
+      double h_new = h / fac;
+      if (!((err <= 1) || force_this_step)) {
+        /* rejected, src/dopri.c:495-509 */
+        h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);
+        reject = true;
+        if (n_accept >= 1) {
+          ++n_reject;
+        }
+        last = false;
+        stop = false;
+        h = h_new;
+        continue;
+      }
+
+      /* ---- accepted, src/dopri.c:396-494 ---- */
+      fac_old = fmax(err, 1e-4);
+      ++n_accept;
+      if (METHOD == 1) { /* the redundant evaluation at the OLD time, src/dopri.c:400-403 */
+        DDE_COOP_EVAL(t, KV(5), KV(4));
+      }
+      /* dopri_test_stiff, src/dopri.c:668-693 */
+      if (a.stiff_check != 0 &&
+          (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
+        DDE_EACH(i) {
+          if (METHOD == 0) { /* src/dopri_5.c:129-140 */
+            RED[i] = csq(KV(2)[i] - KV(6)[i]);
+            RED[n + i] = csq(YIN[i] - KV(7)[i]);
+          } else { /* src/dopri_853.c:382-394 */
+            RED[i] = csq(KV(4)[i] - KV(3)[i]);
+            RED[n + i] = csq(KV(5)[i] - YIN[i]);
+          }
+        }
+        double sums[2];
+        coop_seqsum<2>(n, RED, sums);
+        const bool stiff =
+            sums[1] > 0 && fabs(h) * sqrt(sums[0] / sums[1]) > (METHOD == 0 ? 3.25 : 6.1);
+        bool gave_up = false;
+        if (stiff) {
+          stiff_n_nonstiff = 0;
+          if (stiff_n_stiff++ >= 15) {
+            gave_up = true;
+          }
+        } else if (stiff_n_stiff > 0) {
+          if (stiff_n_nonstiff++ >= 6) {
+            stiff_n_stiff = 0;
+          }
+        }
+        if (gave_up) {
+          if (tid == 0) {
+            s_cc.error = 1;
+            s_cc.code = -7; /* ERR_STIFF */
+          }
+          break;
         }
       }
+      if (METHOD == 1) {
+        /* dopri853_save_history, src/dopri_853.c:285-367: one more evaluation,
+           the first half of coefficients 4..7 (before slots 10, 2, 3 are
+           reused), three more stages */
+        DDE_COOP_EVAL(t + h, KV(5), KV(4));
+        DDE_EACH(i) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            double d = c_dp8_d1[r][0].a * KV(c_dp8_d1[r][0].k)[i];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+              d = d + c_dp8_d1[r][q].a * KV(c_dp8_d1[r][q].k)[i];
+            }
+            RED[(size_t) r * n + i] = d;
+          }
+        }
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+          DDE_COOP_STAGE(c_dp8_extra[j], false, YIN);
+        }
+      }
+
+      /* dense coefficients of the step, per component: into the ring's head
+         slot (ring_buffer_head_advance, src/dopri.c:460) and, evaluated at the
+         requested times the step has passed, into the output rows
+         (src/dopri.c:437-456) */
       const double t_old = t;
       t += h;
-
-      /* output rows, src/dopri.c:437-456 */
-      while (times_idx < n_times) {
-        const double tq = a.times[times_idx];
-        if (!(last || sign * tq <= sign * t)) {
-          break;
-        }
-        const double theta = (tq - t_old) / h;
-        const double theta1 = 1 - theta;
-        DDE_CLOOP(j, i) {
-          double c[ORDER];
-#pragma unroll
-          for (int q = 0; q < ORDER; ++q) {
-            c[q] = hd[q * CMAX + j];
-          }
-          yo[i] = coop_interp(c, ORDER, 1, theta, theta1);
-        }
-        yo += n;
-        ++times_idx;
+      int rows = 0; /* how many requested times this step emits */
+      while (times_idx + rows < n_times &&
+             (last || sign * a.times[times_idx + rows] <= sign * t)) {
+        ++rows;
       }
-
-      /* ring_buffer_head_advance, src/dopri.c:460 */
-      if (a.n_history > 0) {
-        double *dst = ring + (size_t) s_cc.head * (size_t) hl;
-        DDE_CLOOP(j, i) {
+      double *dst = a.n_history > 0 ? ring + (size_t) s_cc.head * (size_t) hl : nullptr;
+      DDE_EACH(i) {
+        double c[ORDER];
+        if (METHOD == 0) { /* dopri5_save_history, src/dopri_5.c:106-118; YIN is y1 */
+          const double ydiff = YIN[i] - Y[i];
+          const double bspl = h * KV(1)[i] - ydiff;
+          c[0] = Y[i];
+          c[1] = ydiff;
+          c[2] = bspl;
+          c[3] = -h * KV(2)[i] + ydiff - bspl;
+          c[4] = RED[3 * (size_t) n + i];
+        } else { /* src/dopri_853.c:306-314,350-363 */
+          const double ydiff = KV(5)[i] - Y[i];
+          const double bspl = h * KV(1)[i] - ydiff;
+          c[0] = Y[i];
+          c[1] = ydiff;
+          c[2] = bspl;
+          c[3] = ydiff - h * KV(4)[i] - bspl;
 #pragma unroll
-          for (int q = 0; q < ORDER; ++q) {
-            dst[(size_t) q * n + i] = hd[q * CMAX + j];
-          }
-        }
-        __syncthreads(); /* everybody has read the context */
-        if (tid == 0) {
-          dst[ORDER * n] = t_old;
-          dst[ORDER * n + 1] = h;
-          const unsigned newest = s_cc.count;
-          s_cc.head = s_cc.head + 1 == a.n_history ? 0 : s_cc.head + 1;
-          s_cc.count = newest + 1;
-          if (s_cc.c_valid) {
-            const unsigned tail = s_cc.count > (unsigned) a.n_history
-                                      ? s_cc.count - (unsigned) a.n_history : 0u;
-            if (s_cc.c_idx < tail) {
-              s_cc.c_valid = 0; /* recycled by the overwrite policy */
-            } else if (s_cc.c_idx + 1 == newest) {
-              s_cc.c_tn = sign * t_old; /* its successor exists now */
+          for (int r = 0; r < 4; ++r) {
+            double d = RED[(size_t) r * n + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              d = d + c_dp8_d2[r][q].a * KV(c_dp8_d2[r][q].k)[i];
             }
+            c[4 + r] = h * d;
           }
         }
-        __syncthreads();
+        if (dst != nullptr) {
+#pragma unroll
+          for (int q = 0; q < ORDER; ++q) {
+            dst[(size_t) q * n + i] = c[q];
+          }
+        }
+        for (int r = 0; r < rows; ++r) {
+          const double theta = (a.times[times_idx + r] - t_old) / h;
+          const double theta1 = 1 - theta;
+          yo[(size_t) r * n + i] = coop_interp(c, ORDER, 1, theta, theta1);
+        }
       }
+      yo += (size_t) rows * n;
+      times_idx += rows;
+      __syncthreads(); /* every thread is done with y, k1 and the context */
+      /* y <- y1 / k5, k1 <- k2 / k4: src/dopri.c:414-424 */
+      DDE_EACH(i) {
+        Y[i] = METHOD == 0 ? YIN[i] : KV(5)[i];
+        KV(1)[i] = METHOD == 0 ? KV(2)[i] : KV(4)[i];
+      }
+      if (a.n_history > 0 && tid == 0) {
+        dst[ORDER * n] = t_old;
+        dst[ORDER * n + 1] = h;
+        const unsigned newest = s_cc.count;
+        s_cc.head = s_cc.head + 1 == a.n_history ? 0 : s_cc.head + 1;
+        s_cc.count = newest + 1;
+        if (s_cc.c_valid) {
+          const unsigned tail = s_cc.count > (unsigned) a.n_history
+                                    ? s_cc.count - (unsigned) a.n_history : 0u;
+          if (s_cc.c_idx < tail) {
+            s_cc.c_valid = 0; /* recycled by the overwrite policy */
+          } else if (s_cc.c_idx + 1 == newest) {
+            s_cc.c_tn = sign * t_old; /* its successor exists now */
+          }
+        }
+      }
+      __syncthreads();
 
       if (last) {
         step_size_exit = h_save; /* src/dopri.c:463 */
@@ -921,11 +813,13 @@ __global__ void __launch_bounds__(TPT) dopri_coop_kernel(const DopriArgs a) {
       a.ring_count[traj] = s_cc.count;
     }
     if (a.y_final != nullptr) {
-      DDE_CLOOP(j, i) { a.y_final[traj * n + i] = y[j]; }
+      DDE_EACH(i) { a.y_final[traj * n + i] = Y[i]; }
     }
 #undef DDE_COOP_EVAL
+#undef DDE_COOP_STAGE
   }
-#undef DDE_CLOOP
+#undef KV
+#undef DDE_EACH
 }
 
 } /* namespace dde */
