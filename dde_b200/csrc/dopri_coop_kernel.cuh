@@ -42,6 +42,9 @@
 #ifndef DDE_COOP_SCRATCH_BYTES
 #define DDE_COOP_SCRATCH_BYTES 8192 /* what a model may claim with DDE_SCRATCH */
 #endif
+#ifndef DDE_COOP_MAX_TABLE
+#define DDE_COOP_MAX_TABLE 1024 /* longest ring whose step times are kept in shared memory */
+#endif
 
 namespace dde {
 
@@ -54,6 +57,9 @@ struct CoopCtx {
   unsigned count;          /* entries committed */
   int head;                /* slot of the next commit */
   int error, code;         /* obj->error, obj->code */
+  /* start time (sign-adjusted) and step of every ring slot, in shared memory
+     when the ring is short enough: a look-up is then a block-wide scan */
+  double *tab_t, *tab_h;
   /* cached bracket: entry c_idx covers [c_ts, c_tn) in sign-adjusted time */
   unsigned c_idx;
   int c_valid;
@@ -87,6 +93,39 @@ __device__ __forceinline__ const double *coop_entry(unsigned idx) {
  * src/dopri.c:742-769.  Thread 0 searches, everybody gets the answer.  On
  * failure ERR_YLAG_FAIL is recorded and false returned. */
 __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_old, double *h) {
+  if (s_cc.tab_t != nullptr) {
+    /* every thread tests the entries it owns: the wanted one starts at or
+       before t while its successor (if any) starts after t */
+    const double st = s_cc.sign * t;
+    const unsigned count = s_cc.count;
+    const unsigned cap = (unsigned) s_cc.cap;
+    const unsigned used = count < cap ? count : cap;
+    const unsigned tail = count - used;
+    if (threadIdx.x == 0) {
+      s_cc.b_ok = 0;
+    }
+    __syncthreads();
+    for (unsigned k = threadIdx.x; k < used; k += blockDim.x) {
+      const unsigned j = tail + k; /* logical index; slot j % cap */
+      const double tj = s_cc.tab_t[j % cap];
+      if (tj <= st && (j + 1 == count || !(s_cc.tab_t[(j + 1) % cap] <= st))) {
+        s_cc.b_ok = 1;
+        s_cc.b_idx = j;
+        s_cc.b_told = s_cc.sign * tj;
+        s_cc.b_h = s_cc.tab_h[j % cap];
+      }
+    }
+    __syncthreads();
+    const bool found = s_cc.b_ok != 0;
+    if (!found && threadIdx.x == 0) {
+      s_cc.error = 1;
+      s_cc.code = -6; /* ERR_YLAG_FAIL */
+    }
+    *idx = s_cc.b_idx;
+    *t_old = s_cc.b_told;
+    *h = s_cc.b_h;
+    return found;
+  }
   if (threadIdx.x == 0) {
     const double sign = s_cc.sign;
     const double st = sign * t;
@@ -423,9 +462,26 @@ __global__ void __launch_bounds__(TPT, (TPT >= 256 ? 2 : (TPT >= 128 ? 4 : 8))) 
       s_cc.error = 0;
       s_cc.code = 0;
       s_cc.c_valid = 0;
+      /* the table of step times follows the model's scratch area */
+      double *tab = (double *) ((char *) (s_coop_dyn + DDE_COOP_NVEC * (size_t) n) +
+                                DDE_COOP_SCRATCH_BYTES);
+      const bool have_tab = a.n_history > 0 && a.n_history <= DDE_COOP_MAX_TABLE;
+      s_cc.tab_t = have_tab ? tab : nullptr;
+      s_cc.tab_h = have_tab ? tab + a.n_history : nullptr;
     }
     DDE_EACH(i) { Y[i] = y0[i]; }
     __syncthreads();
+    if (s_cc.tab_t != nullptr && s_cc.count > 0) { /* restart: the times of the surviving entries */
+      const unsigned cap = (unsigned) a.n_history;
+      const unsigned used = s_cc.count < cap ? s_cc.count : cap;
+      for (unsigned k = tid; k < used; k += TPT) {
+        const unsigned slot = (s_cc.count - used + k) % cap;
+        const double *e = ring + (size_t) slot * (size_t) hl;
+        s_cc.tab_t[slot] = sign * e[hl - 2];
+        s_cc.tab_h[slot] = e[hl - 1];
+      }
+      __syncthreads();
+    }
 
     double t = a.times[0];
     int times_idx = 1, tcrit_idx = a.tcrit_idx0;
@@ -759,6 +815,10 @@ __global__ void __launch_bounds__(TPT, (TPT >= 256 ? 2 : (TPT >= 128 ? 4 : 8))) 
       if (a.n_history > 0 && tid == 0) {
         dst[ORDER * n] = t_old;
         dst[ORDER * n + 1] = h;
+        if (s_cc.tab_t != nullptr) {
+          s_cc.tab_t[s_cc.head] = sign * t_old;
+          s_cc.tab_h[s_cc.head] = h;
+        }
         const unsigned newest = s_cc.count;
         s_cc.head = s_cc.head + 1 == a.n_history ? 0 : s_cc.head + 1;
         s_cc.count = newest + 1;
