@@ -42,6 +42,9 @@
 #ifndef DDE_COOP_SCRATCH_BYTES
 #define DDE_COOP_SCRATCH_BYTES 8192 /* what a model may claim with DDE_SCRATCH */
 #endif
+#ifndef DDE_COOP_MINB256
+#define DDE_COOP_MINB256 3 /* resident 256-thread blocks the register allocation must allow */
+#endif
 #ifndef DDE_COOP_MAX_TABLE
 #define DDE_COOP_MAX_TABLE 1024 /* longest ring whose step times are kept in shared memory */
 #endif
@@ -389,7 +392,7 @@ __device__ __forceinline__ void coop_seqsum(int n, const double *red, double *re
 }
 
 template <class M, int METHOD, int TPT, int CMAX>
-__global__ void __launch_bounds__(TPT, (TPT >= 256 ? 2 : (TPT >= 128 ? 4 : 8))) dopri_coop_kernel(const DopriArgs a) {
+__global__ void __launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 128 ? 4 : 8))) dopri_coop_kernel(const DopriArgs a) {
   constexpr int ORDER = METHOD == 0 ? 5 : 8;
   const int n = a.n;
   const int hl = ORDER * n + 2;
