@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""C3 Lorenz half only, for profiling: usage tools/run_c3.py [n_traj] [n_times]"""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import dde_b200
+from dde_b200 import workloads
+n_traj = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+n_times = int(sys.argv[2]) if len(sys.argv) > 2 else 1001
+model, y0, parms, times, kw = workloads.lorenz_sweep(n_traj, n_times=n_times)
+b = dde_b200.DopriBatch(model, 3, n_traj, n_parms=3, **kw)
+b.set_times(times)
+b.upload(y0, parms)
+for _ in range(2):
+    b.run()
+    b.sync()
+r = b.download(want_y=False)
+print("ms", b.last_ms(), "traj/s %.4g" % (n_traj / (b.last_ms() * 1e-3)), "accepted steps/s %.4g" %
+      (r.statistics[:, 2].sum() / (b.last_ms() * 1e-3)), "steps per traj %.1f" % r.statistics[:, 1].mean())
+b.close()
