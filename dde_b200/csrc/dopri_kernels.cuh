@@ -257,198 +257,24 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
         k10[NMAX], k14[NMAX], k15[NMAX], ysave[NMAX], hd[ORDER * NMAX];
     bool accepted = false;
     double h_new = 0.0;
+    /* the stage input and its time, prepared one evaluation ahead */
+    double yin[NMAX], kt[NMAX], tt = t;
+    if (run) { /* input of evaluation 0: src/dopri_5.c:54-57, src/dopri_853.c:178-181 */
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        yin[i] = y[i] + h * (METHOD == 0 ? DP5_A21 : DP8_A21) * k1[i];
+      }
+      tt = t + (METHOD == 0 ? DP5_C2 : DP8_C2) * h;
+    }
 
 #pragma unroll 1
     for (int st = 0; st < NST; ++st) {
       if (!(run && (st < NST_STEP || accepted))) {
         continue;
       }
-      /* -- 1. the input of evaluation `st` (warp-uniform switch) -- */
-      double yin[NMAX], kt[NMAX], tt;
-      if (METHOD == 0) {
-        switch (st) { /* dopri5_step, src/dopri_5.c:54-80 */
-          case 0:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * DP5_A21 * k1[i];
-            }
-            tt = t + DP5_C2 * h;
-            break;
-          case 1:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
-            }
-            tt = t + DP5_C3 * h;
-            break;
-          case 2:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
-            }
-            tt = t + DP5_C4 * h;
-            break;
-          case 3:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
-                                   DP5_A54 * k4[i]);
-            }
-            tt = t + DP5_C5 * h;
-            break;
-          case 4:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP5_A61 * k1[i] + DP5_A62 * k2[i] + DP5_A63 * k3[i] +
-                                   DP5_A64 * k4[i] + DP5_A65 * k5[i]);
-              ysave[i] = yin[i];
-            }
-            tt = t + h;
-            break;
-          default: /* 5 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP5_A71 * k1[i] + DP5_A73 * k3[i] + DP5_A74 * k4[i] +
-                                   DP5_A75 * k5[i] + DP5_A76 * k6[i]);
-            }
-            tt = t + h;
-            break;
-        }
-      } else {
-        switch (st) { /* dopri853_step, src/dopri_853.c:178-240 */
-          case 0:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * DP8_A21 * k1[i];
-            }
-            tt = t + DP8_C2 * h;
-            break;
-          case 1:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
-            }
-            tt = t + DP8_C3 * h;
-            break;
-          case 2:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
-            }
-            tt = t + DP8_C4 * h;
-            break;
-          case 3:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
-            }
-            tt = t + DP8_C5 * h;
-            break;
-          case 4:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
-            }
-            tt = t + DP8_C6 * h;
-            break;
-          case 5:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
-                                   DP8_A76 * k6[i]);
-            }
-            tt = t + DP8_C7 * h;
-            break;
-          case 6:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
-                                   DP8_A86 * k6[i] + DP8_A87 * k7[i]);
-            }
-            tt = t + DP8_C8 * h;
-            break;
-          case 7:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
-                                   DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
-            }
-            tt = t + DP8_C9 * h;
-            break;
-          case 8:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A101 * k1[i] + DP8_A104 * k4[i] + DP8_A105 * k5[i] +
-                                   DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
-                                   DP8_A109 * k9[i]);
-            }
-            tt = t + DP8_C10 * h;
-            break;
-          case 9:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A111 * k1[i] + DP8_A114 * k4[i] + DP8_A115 * k5[i] +
-                                   DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
-                                   DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
-            }
-            tt = t + DP8_C11 * h;
-            break;
-          case 10:
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A121 * k1[i] + DP8_A124 * k4[i] + DP8_A125 * k5[i] +
-                                   DP8_A126 * k6[i] + DP8_A127 * k7[i] + DP8_A128 * k8[i] +
-                                   DP8_A129 * k9[i] + DP8_A1210 * k10[i] + DP8_A1211 * k2[i]);
-              ysave[i] = yin[i];
-            }
-            tt = t + h;
-            break;
-          case 11: /* the redundant evaluation at the OLD time, src/dopri.c:400-403
-                      (SURVEY.md A.1#2): it counts, and its lag look-ups can fail */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = k5[i];
-            }
-            tt = t;
-            break;
-          case 12: /* dopri853_save_history, src/dopri_853.c:304 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = k5[i];
-            }
-            tt = t + h;
-            break;
-          case 13: /* src/dopri_853.c:330-335 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A141 * k1[i] + DP8_A147 * k7[i] + DP8_A148 * k8[i] +
-                                   DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
-                                   DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
-            }
-            tt = t + DP8_C14 * h;
-            break;
-          case 14: /* src/dopri_853.c:336-341 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
-                                   DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
-                                   DP8_A1513 * k4[i] + DP8_A1514 * k14[i]);
-            }
-            tt = t + DP8_C15 * h;
-            break;
-          default: /* 15, src/dopri_853.c:342-347 */
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              yin[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
-                                   DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
-                                   DP8_A1614 * k14[i] + DP8_A1615 * k15[i]);
-            }
-            tt = t + DP8_C16 * h;
-            break;
-        }
-      }
-
-      /* -- 2. dopri_eval, src/dopri.c:831-835: the one hot copy of the model -- */
+      /* -- 1. dopri_eval, src/dopri.c:831-835: the one hot copy of the model, on
+            the stage input `yin` at time `tt` that the previous trip through the
+            switch below (or the attempt's prologue) prepared -- */
       if (a.n_history > 0) {
         s_tt[s] = tt; /* lag look-ups learn their offset from it */
       }
@@ -460,8 +286,9 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       M::deriv((size_t) n, tt, yin, kt, p);
       ++n_eval;
 
-      /* -- 3. file the result; after the last stage of the attempt: error
-            estimate, controller, accept / reject -- */
+      /* -- 2. file the result and form the input of the next evaluation (one
+            warp-uniform switch per evaluation); after the last stage of the
+            attempt: error estimate, controller, accept / reject -- */
       bool attempt_done = false; /* all NST_STEP evaluations of the attempt are in */
       bool step_done = false;    /* ... and so are the accept-only ones */
       if (METHOD == 0) {
@@ -469,22 +296,56 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           case 0:
 #pragma unroll
             for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            /* input of evaluation 1 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
+            }
+            tt = t + DP5_C3 * h;
             break;
           case 1:
 #pragma unroll
             for (int i = 0; i < n; ++i) k3[i] = kt[i];
+            /* input of evaluation 2 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
+            }
+            tt = t + DP5_C4 * h;
             break;
           case 2:
 #pragma unroll
             for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            /* input of evaluation 3 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
+                                   DP5_A54 * k4[i]);
+            }
+            tt = t + DP5_C5 * h;
             break;
           case 3:
 #pragma unroll
             for (int i = 0; i < n; ++i) k5[i] = kt[i];
+            /* input of evaluation 4 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A61 * k1[i] + DP5_A62 * k2[i] + DP5_A63 * k3[i] +
+                                   DP5_A64 * k4[i] + DP5_A65 * k5[i]);
+              ysave[i] = yin[i];
+            }
+            tt = t + h;
             break;
           case 4:
 #pragma unroll
             for (int i = 0; i < n; ++i) k6[i] = kt[i];
+            /* input of evaluation 5 */ /* 5 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP5_A71 * k1[i] + DP5_A73 * k3[i] + DP5_A74 * k4[i] +
+                                   DP5_A75 * k5[i] + DP5_A76 * k6[i]);
+            }
+            tt = t + h;
             break;
           default: /* 5: k2 = f(t + h, y1); yin is y1 */
 #pragma unroll
@@ -497,42 +358,112 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           case 0:
 #pragma unroll
             for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            /* input of evaluation 1 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
+            }
+            tt = t + DP8_C3 * h;
             break;
           case 1:
 #pragma unroll
             for (int i = 0; i < n; ++i) k3[i] = kt[i];
+            /* input of evaluation 2 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
+            }
+            tt = t + DP8_C4 * h;
             break;
           case 2:
 #pragma unroll
             for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            /* input of evaluation 3 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
+            }
+            tt = t + DP8_C5 * h;
             break;
           case 3:
 #pragma unroll
             for (int i = 0; i < n; ++i) k5[i] = kt[i];
+            /* input of evaluation 4 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
+            }
+            tt = t + DP8_C6 * h;
             break;
           case 4:
 #pragma unroll
             for (int i = 0; i < n; ++i) k6[i] = kt[i];
+            /* input of evaluation 5 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
+                                   DP8_A76 * k6[i]);
+            }
+            tt = t + DP8_C7 * h;
             break;
           case 5:
 #pragma unroll
             for (int i = 0; i < n; ++i) k7[i] = kt[i];
+            /* input of evaluation 6 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
+                                   DP8_A86 * k6[i] + DP8_A87 * k7[i]);
+            }
+            tt = t + DP8_C8 * h;
             break;
           case 6:
 #pragma unroll
             for (int i = 0; i < n; ++i) k8[i] = kt[i];
+            /* input of evaluation 7 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
+                                   DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
+            }
+            tt = t + DP8_C9 * h;
             break;
           case 7:
 #pragma unroll
             for (int i = 0; i < n; ++i) k9[i] = kt[i];
+            /* input of evaluation 8 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A101 * k1[i] + DP8_A104 * k4[i] + DP8_A105 * k5[i] +
+                                   DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
+                                   DP8_A109 * k9[i]);
+            }
+            tt = t + DP8_C10 * h;
             break;
           case 8:
 #pragma unroll
             for (int i = 0; i < n; ++i) k10[i] = kt[i];
+            /* input of evaluation 9 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A111 * k1[i] + DP8_A114 * k4[i] + DP8_A115 * k5[i] +
+                                   DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
+                                   DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
+            }
+            tt = t + DP8_C11 * h;
             break;
           case 9:
 #pragma unroll
             for (int i = 0; i < n; ++i) k2[i] = kt[i];
+            /* input of evaluation 10 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A121 * k1[i] + DP8_A124 * k4[i] + DP8_A125 * k5[i] +
+                                   DP8_A126 * k6[i] + DP8_A127 * k7[i] + DP8_A128 * k8[i] +
+                                   DP8_A129 * k9[i] + DP8_A1210 * k10[i] + DP8_A1211 * k2[i]);
+              ysave[i] = yin[i];
+            }
+            tt = t + h;
             break;
           case 10: /* src/dopri_853.c:242-246 */
 #pragma unroll
@@ -547,23 +478,48 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           case 11: /* k4 = f(t_old, k5): only the stiffness test reads it */
 #pragma unroll
             for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            /* input of evaluation 12 */ /* dopri853_save_history, src/dopri_853.c:304 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = k5[i];
+            }
+            tt = t + h;
             break;
           case 12: /* k4 = f(t + h, k5), src/dopri_853.c:304 */
 #pragma unroll
             for (int i = 0; i < n; ++i) k4[i] = kt[i];
+            /* input of evaluation 13 */ /* src/dopri_853.c:330-335 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A141 * k1[i] + DP8_A147 * k7[i] + DP8_A148 * k8[i] +
+                                   DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
+                                   DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
+            }
+            tt = t + DP8_C14 * h;
             break;
-          /* The reference stores the three extra stages over k10, k2, k3 and
-             therefore forms half of each dense coefficient before them
-             (src/dopri_853.c:315-326,350-363).  Here they get registers of
-             their own, so all eight coefficients are formed in one place after
-             the last stage, from the same operands in the same order. */
           case 13:
 #pragma unroll
             for (int i = 0; i < n; ++i) k14[i] = kt[i];
+            /* input of evaluation 14 */ /* src/dopri_853.c:336-341 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A151 * k1[i] + DP8_A156 * k6[i] + DP8_A157 * k7[i] +
+                                   DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
+                                   DP8_A1513 * k4[i] + DP8_A1514 * k14[i]);
+            }
+            tt = t + DP8_C15 * h;
             break;
           case 14:
 #pragma unroll
             for (int i = 0; i < n; ++i) k15[i] = kt[i];
+            /* input of evaluation 15 */ /* 15, src/dopri_853.c:342-347 */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = y[i] + h * (DP8_A161 * k1[i] + DP8_A166 * k6[i] + DP8_A167 * k7[i] +
+                                   DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
+                                   DP8_A1614 * k14[i] + DP8_A1615 * k15[i]);
+            }
+            tt = t + DP8_C16 * h;
             break;
           default: /* 15, src/dopri_853.c:306-327,350-366 */
 #pragma unroll
@@ -650,6 +606,15 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           ++n_accept;
           if (METHOD == 0) {
             step_done = true;
+          } else {
+            /* input of evaluation 11: the redundant one at the OLD time,
+               src/dopri.c:400-403: it counts, and its lag
+               look-ups can fail */
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yin[i] = k5[i];
+            }
+            tt = t;
           }
         } else {
           /* rejected, src/dopri.c:495-509 */
