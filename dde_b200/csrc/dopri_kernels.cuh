@@ -267,9 +267,12 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       tt = t + (METHOD == 0 ? DP5_C2 : DP8_C2) * h;
     }
 
+    /* how many evaluations this lane takes part in: none, the attempt's, or --
+       once accepted -- the accept-only ones too */
+    int my_stages = run ? NST_STEP : 0;
 #pragma unroll 1
     for (int st = 0; st < NST; ++st) {
-      if (!(run && (st < NST_STEP || accepted))) {
+      if (st >= my_stages) {
         continue;
       }
       /* -- 1. dopri_eval, src/dopri.c:831-835: the one hot copy of the model, on
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       if (attempt_done) {
         if (s_error[s]) {
           done = true; /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
-          run = false;
+          my_stages = 0;
           continue;
         }
         double err;
@@ -602,6 +605,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
         h_new = h / fac;
         accepted = (err <= 1) || force_this_step;
         if (accepted) {
+          my_stages = NST;
           fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
           ++n_accept;
           if (METHOD == 0) {
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           s_error[s] = 1;
           s_code[s] = -7; /* ERR_STIFF */
           done = true;
-          run = false;
+          my_stages = 0;
           continue;
         }
       }
@@ -748,7 +752,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
         if (last) {
           s_code[s] = 1;           /* OK_COMPLETE */
           done = true;
-          run = false;
+          my_stages = 0;
           continue;
         }
         if (fabs(h_new) >= a.step_size_max) {
