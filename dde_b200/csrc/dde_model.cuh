@@ -66,18 +66,18 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
   DopriArgs args = args_in;
   /* stage the lag window's coefficients in shared memory when they fit */
   const size_t order = METHOD == 0 ? 5 : 8;
-  size_t dyn = 0;
+  size_t dyn = DDE_CTX_BYTES;
   args.win_staged = 0;
   if (args.n_history > 0) {
     const size_t bytes = sizeof(double) * DDE_WIN * order * (size_t) args.n * DDE_TPB;
     if (bytes <= DDE_WIN_COEF_BUDGET) {
-      dyn = bytes;
+      dyn += bytes;
       args.win_staged = 1;
     }
   }
   /* start-up of every trajectory (row 0, k1, first step size) */
   const long long init_grid = (args.n_traj + DDE_TPB - 1) / DDE_TPB;
-  dopri_init_kernel<M, METHOD><<<(unsigned) init_grid, DDE_TPB, 0, stream>>>(args);
+  dopri_init_kernel<M, METHOD><<<(unsigned) init_grid, DDE_TPB, DDE_CTX_BYTES, stream>>>(args);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     return err;
@@ -106,12 +106,12 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
                                int *n_launches) {
   DifeqArgs a = args_in;
   /* keep the history on chip when it fits: [slot][component][thread] doubles */
-  size_t dyn = 0;
+  size_t dyn = DDE_CTX_BYTES;
   a.staged = 0;
   if (a.n_history > 0) {
     const size_t bytes = sizeof(double) * (size_t) a.n_history * (size_t) a.n * DDE_TPB;
     if (bytes <= DDE_DIFEQ_STAGE_BUDGET) {
-      dyn = bytes;
+      dyn += bytes;
       a.staged = 1;
     }
   }

@@ -278,9 +278,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       /* -- 1. dopri_eval, src/dopri.c:831-835: the one hot copy of the model, on
             the stage input `yin` at time `tt` that the previous trip through the
             switch below (or the attempt's prologue) prepared -- */
-      if (a.n_history > 0) {
-        s_tt[s] = tt; /* lag look-ups learn their offset from it */
-      }
+      s_tt[s] = tt; /* lag look-ups learn their offset from it */
       if (NC > 0) {
         /* the lag functions read the method / width / staging flags from the
            thread's context: tell the optimiser what they will find */
@@ -635,8 +633,12 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
 
       /* dopri_test_stiff, src/dopri.c:668-693: after the redundant
          evaluation for dop853, right after acceptance for dopri5 */
-      if ((METHOD == 0 ? step_done : st == 11) && a.stiff_check != 0 &&
-          (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0)) {
+      bool stiff_due = false;
+      if (METHOD == 0 ? step_done : st == 11) { /* the warp-uniform test first */
+        stiff_due = a.stiff_check != 0 &&
+                    (stiff_n_stiff > 0 || (unsigned long long) n_accept % a.stiff_check == 0);
+      }
+      if (stiff_due) {
         double stnum = 0, stden = 0;
 #pragma unroll
         for (int i = 0; i < n; ++i) {

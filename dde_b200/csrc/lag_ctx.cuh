@@ -94,19 +94,28 @@ enum {
   DDE_FI_CFG,       /* per-thread copy of n | order << 16 | staged << 24 */
   DDE_FI_COUNT32
 };
-__shared__ double s_ctx64[DDE_F_COUNT64][DDE_TPB];
-__shared__ int s_ctx32[DDE_FI_COUNT32][DDE_TPB];
-#define s_ring ((double **) ::dde::s_ctx64[::dde::DDE_F_RING])
-#define s_y0 ((const double **) ::dde::s_ctx64[::dde::DDE_F_Y0])
-#define s_t0 (::dde::s_ctx64[::dde::DDE_F_T0])
-#define s_sign (::dde::s_ctx64[::dde::DDE_F_SIGN])
-#define s_cfg (::dde::s_ctx32[::dde::DDE_FI_CFG])
-#define s_step ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP])
-#define s_step0 ((long long *) ::dde::s_ctx64[::dde::DDE_F_STEP0])
-#define s_count ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_COUNT])
-#define s_head (::dde::s_ctx32[::dde::DDE_FI_HEAD])
-#define s_code (::dde::s_ctx32[::dde::DDE_FI_CODE])
-#define s_error (::dde::s_ctx32[::dde::DDE_FI_ERROR])
+/* The block lives at the start of the kernel's dynamic shared memory, followed
+ * by the 32-bit fields and then the staged coefficients (s_wc), so that the
+ * whole per-thread state hangs off ONE thread-dependent base address; every
+ * launch of a kernel that includes this file passes at least DDE_CTX_BYTES of
+ * dynamic shared memory. */
+extern __shared__ double dde_smem[];
+#define DDE_CTX_BYTES \
+  (sizeof(double) * ::dde::DDE_F_COUNT64 * DDE_TPB + sizeof(int) * ::dde::DDE_FI_COUNT32 * DDE_TPB)
+static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s_wc alignment");
+#define s_ctx64 ((double (*)[DDE_TPB]) ::dde::dde_smem)
+#define s_ctx32 ((int (*)[DDE_TPB]) (::dde::dde_smem + ::dde::DDE_F_COUNT64 * DDE_TPB))
+#define s_ring ((double **) s_ctx64[::dde::DDE_F_RING])
+#define s_y0 ((const double **) s_ctx64[::dde::DDE_F_Y0])
+#define s_t0 (s_ctx64[::dde::DDE_F_T0])
+#define s_sign (s_ctx64[::dde::DDE_F_SIGN])
+#define s_cfg (s_ctx32[::dde::DDE_FI_CFG])
+#define s_step ((long long *) s_ctx64[::dde::DDE_F_STEP])
+#define s_step0 ((long long *) s_ctx64[::dde::DDE_F_STEP0])
+#define s_count ((unsigned *) s_ctx32[::dde::DDE_FI_COUNT])
+#define s_head (s_ctx32[::dde::DDE_FI_HEAD])
+#define s_code (s_ctx32[::dde::DDE_FI_CODE])
+#define s_error (s_ctx32[::dde::DDE_FI_ERROR])
 
 /* The staged lag window ("shared-memory staging of the bracketing history
  * steps"): up to DDE_WIN consecutive committed entries base .. base + wn - 1
@@ -131,18 +140,19 @@ __shared__ int s_ctx32[DDE_FI_COUNT32][DDE_TPB];
  * A.2#11); the window then moves by one entry if it can, restarts at the
  * entry if it was far away, or stays put while the query is answered from the
  * ring directly (a range wider than the window would otherwise thrash it). */
-#define s_wt (&::dde::s_ctx64[::dde::DDE_F_WT])      /* [DDE_WIN][thread] sign-adjusted start times */
-#define s_wh (&::dde::s_ctx64[::dde::DDE_F_WH])      /* [DDE_WIN][thread] step sizes */
-#define s_wtop (::dde::s_ctx64[::dde::DDE_F_WTOP])
-#define s_wbase ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_WBASE])
-#define s_wn ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_WN])
-#define s_att_lo (::dde::s_ctx64[::dde::DDE_F_ATT_LO]) /* sign * t of the attempt in progress */
-#define s_att_hi (::dde::s_ctx64[::dde::DDE_F_ATT_HI]) /* sign * (t + h) of the attempt in progress */
-#define s_hint ((unsigned *) ::dde::s_ctx32[::dde::DDE_FI_HINT]) /* entry the last search ended at */
-#define s_tt (::dde::s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
-#define s_dq_lo (::dde::s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
-#define s_dq_hi (::dde::s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
-extern __shared__ double s_wc[];     /* [DDE_WIN][order * n][DDE_TPB] when staged */
+#define s_wt (&s_ctx64[::dde::DDE_F_WT])      /* [DDE_WIN][thread] sign-adjusted start times */
+#define s_wh (&s_ctx64[::dde::DDE_F_WH])      /* [DDE_WIN][thread] step sizes */
+#define s_wtop (s_ctx64[::dde::DDE_F_WTOP])
+#define s_wbase ((unsigned *) s_ctx32[::dde::DDE_FI_WBASE])
+#define s_wn ((unsigned *) s_ctx32[::dde::DDE_FI_WN])
+#define s_att_lo (s_ctx64[::dde::DDE_F_ATT_LO]) /* sign * t of the attempt in progress */
+#define s_att_hi (s_ctx64[::dde::DDE_F_ATT_HI]) /* sign * (t + h) of the attempt in progress */
+#define s_hint ((unsigned *) s_ctx32[::dde::DDE_FI_HINT]) /* entry the last search ended at */
+#define s_tt (s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
+#define s_dq_lo (s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
+#define s_dq_hi (s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
+/* [DDE_WIN][order * n][DDE_TPB] when staged (difeq: the on-chip history) */
+#define s_wc (::dde::dde_smem + DDE_CTX_BYTES / sizeof(double))
 
 #ifdef DDE_LAG_STATS
 /* debug build only: [0] misses above, [1] misses below, [2] misses on an empty
@@ -663,7 +673,7 @@ static __device__ __forceinline__ PrevHit dde_find_step(int s, int step) {
   }
   const int slot = dde::ring_slot_back(s_head[s], offset + 1, cap);
   if (hit.staged) {
-    hit.e = dde::s_wc + (size_t) slot * (cfg & 0xffff) * DDE_TPB + s;
+    hit.e = s_wc + (size_t) slot * (cfg & 0xffff) * DDE_TPB + s;
     hit.stride = DDE_TPB;
   } else {
     hit.e = s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
