@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       ++n_step;
       if (a.n_history > 0) {
         /* top up the staged lag window while the warp is in step */
-        lag_window_ensure<ORDER * NMAX>(s, sign * t, sign * (t + h));
+        lag_window_ensure<ORDER * NMAX, (NC > 0)>(s, sign * t, sign * (t + h));
       }
     }
 

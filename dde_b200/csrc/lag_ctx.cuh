@@ -212,22 +212,15 @@ __device__ __forceinline__ void lag_window_reset(int s) {
   s_dq_hi[s] = -pos_inf();
 }
 
-/* Copy committed entry idx from the ring into its window slot: all loads are
- * issued before the first store, one round trip.  Returns the sign-adjusted
- * start time of the entry after it, +inf if there is none. */
-template <int NCOEF_MAX>
-__device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
-  const int hl = s_lag_u.hl;
-  const int nc = hl - 2;
-  const double sign = s_lag_u.sign;
-  const unsigned count = s_count[s];
-  const double *e = ring_entry(s, idx);
-  const int w = (int) (idx % DDE_WIN);
-  DDE_CHECK(s_wn[s] <= DDE_WIN);
-  double top = pos_inf();
-  if (idx + 1 < count) {
-    top = sign * ring_entry(s, idx + 1)[nc];
-  }
+/* Copy one committed entry, at `e` in the ring, into window slot w: all loads
+ * are issued before the first store, one round trip.  EXACT: the entry holds
+ * exactly NCOEF_MAX coefficients (a model of compile-time width).  Returns
+ * the sign-adjusted time the entry ends at -- which is the start time of the
+ * entry after it, bit for bit: the integrator commits (t, h) and moves on to
+ * t + h (src/dopri.c:423,460). */
+template <int NCOEF_MAX, bool EXACT>
+__device__ __forceinline__ double lag_window_copy(int s, const double *e, int w) {
+  const int nc = EXACT ? NCOEF_MAX : s_lag_u.hl - 2;
   const double te = e[nc], he = e[nc + 1];
   if (s_lag_u.staged) {
     double *dst = s_wc + (size_t) w * nc * DDE_TPB + s;
@@ -252,9 +245,20 @@ __device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
       }
     }
   }
+  const double sign = s_lag_u.sign;
   s_wt[w][s] = sign * te;
   s_wh[w][s] = he;
-  return top;
+  return sign * (te + he);
+}
+
+/* Copy committed entry idx from the ring into its window slot.  Returns the
+ * sign-adjusted start time of the entry after it, +inf if there is none. */
+template <int NCOEF_MAX>
+__device__ __forceinline__ double lag_window_load(int s, unsigned idx) {
+  DDE_CHECK(s_wn[s] <= DDE_WIN);
+  const double top =
+      lag_window_copy<NCOEF_MAX, false>(s, ring_entry(s, idx), (int) (idx % DDE_WIN));
+  return idx + 1 < s_count[s] ? top : pos_inf();
 }
 
 /* drop the window's lowest entry */
@@ -268,54 +272,78 @@ __device__ __forceinline__ void lag_window_evict(int s, unsigned &base, unsigned
  * starts at the entry holding the lowest query expected and reaches the
  * highest one (or is full).  Purely a prefetch: any query it fails to
  * anticipate still finds its entry through the slow path. */
-template <int NCOEF_MAX>
+template <int NCOEF_MAX, bool EXACT>
 __device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double att_hi) {
   s_att_lo[s] = att_lo;
   s_att_hi[s] = att_hi;
   const double need_hi = att_hi + s_dq_hi[s];
   const double need_lo = att_lo + s_dq_lo[s];
-  if (!(need_lo <= need_hi)) {
-    return; /* nothing learnt yet */
-  }
   unsigned wn = s_wn[s];
-  if (wn == 0) {
-    return;
-  }
+  const bool live = need_lo <= need_hi && wn > 0; /* else: nothing learnt yet */
   unsigned base = s_wbase[s];
+  double wtop = s_wtop[s];
   /* 1. drop the entries no query of this step reaches (an entry ends where the
         next one starts); shared memory only */
+  if (live) {
 #pragma unroll 1
-  while (wn > 1 && s_wt[(base + 1) % DDE_WIN][s] <= need_lo) {
-    lag_window_evict(s, base, wn);
+    while (wn > 1 && s_wt[(base + 1) % DDE_WIN][s] <= need_lo) {
+      lag_window_evict(s, base, wn);
+    }
   }
-  /* 2. extend upwards; lanes load in the same iterations */
-  double wtop = s_wtop[s];
+  /* 2. extend upwards.  When any lane of the warp has to, every lane fills its
+        free slots with the entries that follow (it will want them within a
+        few steps): the lanes then load in the same few iterations instead of
+        one or two lanes in every attempt. */
+  const unsigned count = s_count[s];
+  if (__any_sync(__activemask(), live && need_hi >= wtop && wn < DDE_WIN)) {
+    unsigned idx = base + wn; /* the entry to append next */
+    if (live && idx < count && wn < DDE_WIN) {
+      const int cap = s_lag_u.cap;
+      const int hl = EXACT ? NCOEF_MAX + 2 : s_lag_u.hl;
+      const double *const ring = s_ring[s];
+      int slot = ring_slot_back(s_head[s], (int) (count - idx), cap);
+      const double *e = ring + (size_t) slot * (size_t) hl;
+      int w = (int) (idx % DDE_WIN);
 #pragma unroll 1
-  while (need_hi >= wtop && wn < DDE_WIN) {
-    DDE_LAG_COUNT(3);
-    wtop = lag_window_load<NCOEF_MAX>(s, base + wn);
-    ++wn;
+      do {
+        DDE_LAG_COUNT(3);
+        DDE_CHECK(slot >= 0 && slot < cap && count - idx <= (unsigned) cap);
+        wtop = lag_window_copy<NCOEF_MAX, EXACT>(s, e, w);
+        ++wn;
+        ++idx;
+        w = w + 1 == DDE_WIN ? 0 : w + 1;
+        e += hl;
+        if (++slot == cap) {
+          slot = 0;
+          e = ring;
+        }
+      } while (idx < count && wn < DDE_WIN);
+      if (idx >= count) {
+        wtop = pos_inf();
+      }
+    }
   }
   /* 3. the window starts too late (a restart, a step back): make room at the
         top and extend downwards */
-  const unsigned count = s_count[s];
-  const unsigned tail = count > (unsigned) s_lag_u.cap ? count - (unsigned) s_lag_u.cap : 0u;
+  if (live) {
+    const unsigned tail = count > (unsigned) s_lag_u.cap ? count - (unsigned) s_lag_u.cap : 0u;
 #pragma unroll 1
-  for (int it = 0; it < DDE_WIN && need_lo < s_wt[base % DDE_WIN][s] && base > tail; ++it) {
-    if (wn == DDE_WIN) {
-      const int top_slot = (int) ((base + wn - 1) % DDE_WIN);
-      wtop = s_wt[top_slot][s];
-      s_wt[top_slot][s] = pos_inf();
-      --wn;
+    for (int it = 0; it < DDE_WIN && need_lo < s_wt[base % DDE_WIN][s] && base > tail; ++it) {
+      if (wn == DDE_WIN) {
+        const int top_slot = (int) ((base + wn - 1) % DDE_WIN);
+        wtop = s_wt[top_slot][s];
+        s_wt[top_slot][s] = pos_inf();
+        --wn;
+      }
+      DDE_LAG_COUNT(3);
+      --base;
+      (void) lag_window_load<NCOEF_MAX>(s, base);
+      ++wn;
     }
-    DDE_LAG_COUNT(3);
-    --base;
-    (void) lag_window_load<NCOEF_MAX>(s, base);
-    ++wn;
+    s_wbase[s] = base;
+    s_wn[s] = wn;
+    s_wtop[s] = wtop;
   }
-  s_wbase[s] = base;
-  s_wn[s] = wn;
-  s_wtop[s] = wtop;
 }
 
 /* Bookkeeping after the integrating thread has written the head entry to
