@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
   double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
   bool stop = false, last = false, reject = false;
   int times_idx = 1, tcrit_idx = 0;
+  double t_out = 0.0; /* times[times_idx], read once per output row, not once per step */
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
 
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
          the host: times are shared by all trajectories) */
       t = a.times[0];
       times_idx = 1;
+      t_out = n_times > 1 ? a.times[1] : 0.0;
       tcrit_idx = a.tcrit_idx0;
       n_eval = n_step = n_accept = n_reject = 0;
       stiff_n_stiff = stiff_n_nonstiff = 0;
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           if (times_idx >= n_times) {
             break;
           }
-          const double tq = a.times[times_idx];
+          const double tq = t_out;
           if (!(last || sign * tq <= sign * t)) {
             break;
           }
@@ -736,6 +738,9 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
             }
           }
           ++times_idx;
+          if (times_idx < n_times) {
+            t_out = a.times[times_idx];
+          }
         }
 
         /* ring_buffer_head_advance, src/dopri.c:460: the head entry goes to
