@@ -172,7 +172,11 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
       n_eval = n_step = n_accept = n_reject = 0;
       stiff_n_stiff = stiff_n_nonstiff = 0;
       s_ring[s] = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) hl;
-      s_y0[s] = y0;
+      if (n == 1) {
+        s_y0_value[s] = y[0]; /* the value itself, see lag_ctx.cuh */
+      } else {
+        s_y0[s] = y0;
+      }
       const RingStart rs = ring_start(a, traj, s_ring[s], hl);
       s_t0[s] = rs.t0s;
       s_count[s] = rs.count;
@@ -874,7 +878,11 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
     y[i] = y0[i];
   }
   const double t = a.times[0];
-  s_y0[s] = y0;
+  if (n == 1) {
+    s_y0_value[s] = y[0];
+  } else {
+    s_y0[s] = y0;
+  }
   s_ring[s] = a.ring + (size_t) traj * (size_t) a.n_history * (size_t) (ORDER * n + 2);
   const RingStart rs = ring_start(a, traj, s_ring[s], ORDER * n + 2);
   s_t0[s] = rs.t0s;

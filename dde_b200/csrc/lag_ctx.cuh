@@ -107,6 +107,9 @@ static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s
 #define s_ctx32 ((int (*)[DDE_TPB]) (::dde::dde_smem + ::dde::DDE_F_COUNT64 * DDE_TPB))
 #define s_ring ((double **) s_ctx64[::dde::DDE_F_RING])
 #define s_y0 ((const double **) s_ctx64[::dde::DDE_F_Y0])
+/* dopri, n = 1: the pre-history VALUE itself sits in the Y0 field (no pointer
+   to chase while other lanes of the warp wait) */
+#define s_y0_value (s_ctx64[::dde::DDE_F_Y0])
 #define s_t0 (s_ctx64[::dde::DDE_F_T0])
 #define s_sign (s_ctx64[::dde::DDE_F_SIGN])
 #define s_cfg (s_ctx32[::dde::DDE_FI_CFG])
@@ -160,7 +163,12 @@ static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s
    probes of the search, [6] queries answered from the ring directly */
 static __device__ unsigned long long dde_lag_stats[16];
 #define DDE_LAG_COUNT(i) atomicAdd(&dde_lag_stats[i], 1ULL)
+#ifdef DDE_LAG_TRACE_PRINT
+#include <stdio.h>
+#define DDE_LAG_TRACE(...) printf(__VA_ARGS__)
+#else
 #define DDE_LAG_TRACE(...) ((void) 0)
+#endif
 /* the same build checks every ring / window index it forms (compute-sanitizer
    is not available on the GPU pool): violations are counted in slot [15] */
 #define DDE_CHECK(cond) ((cond) ? (void) 0 : (void) atomicAdd(&dde_lag_stats[15], 1ULL))
@@ -619,7 +627,7 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
   if (s_sign[s] * t <= s_t0[s]) {
-    return s_y0[s][i];
+    return (s_cfg[s] & 0xffff) == 1 ? s_y0_value[s] : s_y0[s][i];
   }
   const dde::LagHit hit = dde::find_time(s, t);
   if (!hit.ok) {
@@ -634,6 +642,10 @@ static __device__ __forceinline__ void ylag_all(double t, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
   if (s_sign[s] * t <= s_t0[s]) {
+    if (n == 1) {
+      y[0] = s_y0_value[s];
+      return;
+    }
     for (int i = 0; i < n; ++i) {
       y[i] = s_y0[s][i];
     }
@@ -650,6 +662,12 @@ static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *i
                                                         size_t nidx, double *y) {
   const int s = threadIdx.x;
   if (s_sign[s] * t <= s_t0[s]) {
+    if ((s_cfg[s] & 0xffff) == 1) {
+      for (size_t i = 0; i < nidx; ++i) {
+        y[i] = s_y0_value[s];
+      }
+      return;
+    }
     for (size_t i = 0; i < nidx; ++i) {
       y[i] = s_y0[s][idx[i]];
     }
