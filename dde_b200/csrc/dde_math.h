@@ -46,15 +46,21 @@
  * lanes index them divergently, which a __constant__ bank would serialise)
  * and in .rodata on the host. */
 #if defined(__CUDACC__)
-static __device__ const double dde_pow_log_tab_d[3 * 128] = {DDE_POW_LOG_TABLE};
-static __device__ const unsigned long long dde_exp_tab_d[2 * 128] = {DDE_EXP_TABLE};
+/* device copies: one entry = one 32-byte (log) / 16-byte (exp) aligned record,
+   fetched with one vector load (plus one scalar load for the log tail): a
+   divergent gather pays per load instruction and distinct line */
+struct __align__(32) DdePowLogEntry {
+  double2 invc_logc;
+  double logctail;
+  double pad;
+};
+static __device__ const DdePowLogEntry dde_pow_log_tab_d[128] = {DDE_POW_LOG_TABLE4};
+static __device__ const ulonglong2 dde_exp_tab_d[128] = {DDE_EXP_TABLE};
 #endif
 static const double dde_pow_log_tab_h[3 * 128] = {DDE_POW_LOG_TABLE};
 static const unsigned long long dde_exp_tab_h[2 * 128] = {DDE_EXP_TABLE};
 
 #if defined(__CUDA_ARCH__)
-#define DDE_POW_LOG_TAB(i) __ldg(&dde_pow_log_tab_d[i])
-#define DDE_EXP_TAB(i) ((uint64_t) __ldg(&dde_exp_tab_d[i]))
 #define DDE_FMA(a, b, c) fma((a), (b), (c))
 #else
 #define DDE_POW_LOG_TAB(i) dde_pow_log_tab_h[i]
@@ -146,8 +152,15 @@ DDE_HD double dde_exp_inline(double x, double xtail, uint32_t sign_bias, int has
   /* 2^(k/128) ~= scale * (1 + tail) */
   const uint64_t idx = 2 * (ki % 128);
   const uint64_t top = (ki + sign_bias) << 45;
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 entry = __ldg(&dde_exp_tab_d[ki % 128]);
+  const double tail = dde_asdouble((uint64_t) entry.x);
+  const uint64_t sbits = (uint64_t) entry.y + top;
+  (void) idx;
+#else
   const double tail = dde_asdouble(DDE_EXP_TAB(idx));
   const uint64_t sbits = DDE_EXP_TAB(idx + 1) + top;
+#endif
   const double r2 = r * r;
   const double p23 = DDE_FMA(r, DDE_EXP_C3, DDE_EXP_C2);
   const double p45 = DDE_FMA(r, DDE_EXP_C5, DDE_EXP_C4);
@@ -183,9 +196,15 @@ DDE_HD double dde_pow_log_inline(uint64_t ix, double *tail) {
   const double z = dde_asdouble(iz);
   const double kd = (double) k;
 
+#if defined(__CUDA_ARCH__)
+  const double2 invc_logc = __ldg(&dde_pow_log_tab_d[i].invc_logc);
+  const double invc = invc_logc.x, logc = invc_logc.y;
+  const double logctail = __ldg(&dde_pow_log_tab_d[i].logctail);
+#else
   const double invc = DDE_POW_LOG_TAB(3 * i);
   const double logc = DDE_POW_LOG_TAB(3 * i + 1);
   const double logctail = DDE_POW_LOG_TAB(3 * i + 2);
+#endif
 
   /* r = z/c - 1 is exactly representable */
   const double r = DDE_FMA(z, invc, -1.0);

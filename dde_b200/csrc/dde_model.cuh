@@ -77,8 +77,14 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
   }
   /* start-up of every trajectory (row 0, k1, first step size) */
   const long long init_grid = (args.n_traj + DDE_TPB - 1) / DDE_TPB;
+  cudaError_t err = cudaFuncSetAttribute(dopri_init_kernel<M, METHOD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) DDE_CTX_BYTES);
+  if (err != cudaSuccess) {
+    return err;
+  }
   dopri_init_kernel<M, METHOD><<<(unsigned) init_grid, DDE_TPB, DDE_CTX_BYTES, stream>>>(args);
-  cudaError_t err = cudaGetLastError();
+  err = cudaGetLastError();
   if (err != cudaSuccess) {
     return err;
   }

@@ -541,13 +541,23 @@ __device__ __forceinline__ LagHit find_time(int s, double t) {
   /* Entries in the window are consecutive and unused slots hold +inf, so the
      number of slots (in any order) that start at or before st locates the
      entry: no search, no slot arithmetic. */
-  unsigned below = 0;
+  const double wtop = s_wtop[s]; /* everything the hit path reads is requested up front */
+  const unsigned wbase = s_wbase[s];
+  unsigned part[DDE_WIN];
 #pragma unroll
   for (int k = 0; k < DDE_WIN; ++k) {
-    below += st >= s_wt[k][s] ? 1u : 0u;
+    part[k] = st >= s_wt[k][s] ? 1u : 0u;
   }
-  if (below > 0 && st < s_wtop[s]) {
-    hit.idx = s_wbase[s] + below - 1;
+#pragma unroll
+  for (int span = 1; span < DDE_WIN; span *= 2) { /* pairwise: a short dependency chain */
+#pragma unroll
+    for (int k = 0; k + span < DDE_WIN; k += 2 * span) {
+      part[k] += part[k + span];
+    }
+  }
+  const unsigned below = part[0];
+  if ((below > 0) & (st < wtop)) {
+    hit.idx = wbase + below - 1;
     hit.slot = (int) (hit.idx % DDE_WIN);
     DDE_CHECK(below <= s_wn[s] && hit.idx < s_count[s] &&
               s_count[s] - hit.idx <= (unsigned) s_lag_u.cap);
