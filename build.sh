@@ -22,3 +22,5 @@ grep -i -B2 -A6 "error" build/ptxas_coop$TAG.log || true
 test -f build/capi$TAG.o -a -f build/models_builtin$TAG.o -a -f build/models_coop$TAG.o || { echo "build failed" >&2; exit 1; }
 "$NVCC" -shared -o "$OUT" build/capi$TAG.o build/models_builtin$TAG.o build/models_coop$TAG.o -lcudart
 echo "built $OUT"
+# variant objects are not worth keeping (they would travel to the GPU box)
+if [ -n "$TAG" ]; then rm -f build/capi$TAG.o build/models_builtin$TAG.o build/models_coop$TAG.o; fi
