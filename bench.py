@@ -10,9 +10,10 @@ batch (every trajectory integrated from t = 0 to t = 500).
   value  trajectories/s, whole job, inputs already resident in HBM, timed with
          CUDA events on the launching stream, max over ranks.
   e2e    the same metric through the reference-facing C-ABI with HOST
-         (pinned) buffers: per step H2D of y0/parms, the solve, and D2H of
-         y_out, statistics, codes, t_last, step_size, wall clock between
-         device synchronisations.
+         (pinned) buffers: per step H2D of y0/parms, then
+         dde_dopri_batch_run_download (the solve with the D2H of y_out,
+         statistics, codes, t_last, step_size streamed block by block behind
+         it), wall clock between device synchronisations.
   --impl reference   the reference's own CPU code (oracle/_ref: unmodified
          src/dopri*.c, one forked process per host core) on a bounded sample
          of the same workload.
@@ -242,14 +243,12 @@ def main():
     # ---- end to end through the C-ABI with host buffers ------------------------
     for _ in range(1):
         b.upload(h_y0, h_parms)
-        b.run()
-        b.download_into(h_y, None, h_stats, h_code, h_t, h_h)
+        b.run_download_into(h_y, None, h_stats, h_code, h_t, h_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         b.upload(h_y0, h_parms)
-        b.run()
-        b.download_into(h_y, None, h_stats, h_code, h_t, h_h)  # synchronises
+        b.run_download_into(h_y, None, h_stats, h_code, h_t, h_h)  # blocking
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -68,6 +68,8 @@ SYMBOLS = [
     ("dde_dopri_batch_sync", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dde_dopri_batch_run_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dde_dopri_batch_last_ms", C.c_double, [C.c_void_p]),
     ("dde_dopri_batch_last_launches", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_history", C.c_long, [C.c_void_p, _SZ, c_double_p, _SZ]),

@@ -112,6 +112,14 @@ class DopriBatch:
         self._check(self._lib.dde_dopri_batch_download(self._h, _ptr(y_out), _ptr(out), _ptr(stats),
                                                        _ptr(code), _ptr(t_last), _ptr(step_size)))
 
+    def run_download_into(self, y_out=None, out=None, stats=None, code=None, t_last=None,
+                          step_size=None):
+        """run() and download_into() in one blocking call, overlapped: results are copied
+        to the host block by block while later trajectories are still being integrated."""
+        self._check(self._lib.dde_dopri_batch_run_download(
+            self._h, _ptr(y_out), _ptr(out), _ptr(stats), _ptr(code), _ptr(t_last),
+            _ptr(step_size)))
+
     def download(self, want_y=True):
         y_out = np.empty((self.n_traj, self.nt, self.n)) if want_y else None
         out = np.empty((self.n_traj, self.nt, self.n_out)) if (self.n_out > 0 and want_y) else None

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -23,6 +24,11 @@
 #include "difeq_kernels.cuh"
 #include "dopri_kernels.cuh"
 #include "registry.h"
+
+/* trajectories per chunk of a streamed download: 2^15 (a few MB of results) */
+#ifndef DDE_CHUNK_SHIFT
+#define DDE_CHUNK_SHIFT 15
+#endif
 
 namespace {
 
@@ -173,6 +179,13 @@ struct dde_dopri_batch_s {
   bool have_events = false;
   unsigned *d_ring_count = nullptr;
   unsigned long long *d_next = nullptr;
+  /* streamed download (dde_dopri_batch_run_download), allocated on first use */
+  cudaStream_t copy_stream = nullptr;
+  unsigned *d_chunk_done = nullptr;
+  int *h_chunk_flag = nullptr; /* pinned + mapped */
+  int *d_chunk_flag = nullptr; /* its device address */
+  size_t n_chunks = 0;
+  bool streaming = false;      /* the run in flight raises chunk flags */
 };
 
 struct dde_difeq_batch_s {
@@ -387,6 +400,9 @@ void dde_dopri_batch_free(dde_dopri_batch_t *b) {
   free_dev(b->d_event);
   free_dev(b->d_ring_count);
   free_dev(b->d_next);
+  free_dev(b->d_chunk_done);
+  if (b->h_chunk_flag) cudaFreeHost(b->h_chunk_flag);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -663,6 +679,12 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
     a.restart = restart;
     a.y_final = b->d_y_final;
     a.next_traj = b->d_next;
+    if (b->streaming) {
+      DDE_CUDA(cudaMemsetAsync(b->d_chunk_done, 0, sizeof(unsigned) * b->n_chunks, b->stream));
+      a.chunk_done = b->d_chunk_done;
+      a.chunk_flag = b->d_chunk_flag;
+      a.chunk_shift = DDE_CHUNK_SHIFT;
+    }
     int launches = 0;
     cudaError_t err = b->model->launch_dopri(b->ctl.method, a, b->device_sms, b->stream, &launches);
     if (err != cudaSuccess) {
@@ -681,6 +703,85 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
 extern "C" {
 
 int dde_dopri_batch_run(dde_dopri_batch_t *b) { return dopri_run_impl(b, 0); }
+
+/* Run and download in one call, overlapping the two: see DopriArgs::chunk_done.
+ * The copies of a chunk start as soon as the kernel reports it complete, on a
+ * second stream; what is left when the kernel ends is copied then. */
+int dde_dopri_batch_run_download(dde_dopri_batch_t *b, double *y_out, double *out,
+                                 int32_t *stats, int32_t *code, double *t_last,
+                                 double *step_size) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  const size_t chunk = (size_t) 1 << DDE_CHUNK_SHIFT;
+  const size_t n_chunks = (b->n_traj + chunk - 1) / chunk;
+  if (b->copy_stream == nullptr) {
+    DDE_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  }
+  if (b->n_chunks != n_chunks) {
+    free_dev(b->d_chunk_done);
+    if (b->h_chunk_flag) {
+      cudaFreeHost(b->h_chunk_flag);
+      b->h_chunk_flag = nullptr;
+    }
+    DDE_CUDA(cudaMalloc(&b->d_chunk_done, sizeof(unsigned) * n_chunks));
+    DDE_CUDA(cudaHostAlloc(&b->h_chunk_flag, sizeof(int) * n_chunks, cudaHostAllocMapped));
+    DDE_CUDA(cudaHostGetDevicePointer(&b->d_chunk_flag, b->h_chunk_flag, 0));
+    b->n_chunks = n_chunks;
+  }
+  /* no earlier run of this handle may still be raising flags */
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  volatile int *flag = b->h_chunk_flag;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    flag[c] = 0;
+  }
+  b->streaming = true;
+  const int rc = dopri_run_impl(b, 0);
+  b->streaming = false;
+  if (rc != 0) {
+    return rc;
+  }
+  std::vector<char> copied(n_chunks, 0);
+  size_t left = n_chunks;
+  auto copy_chunk = [&](size_t c) -> cudaError_t {
+    const size_t j0 = c * chunk;
+    const size_t nj = (j0 + chunk < b->n_traj ? j0 + chunk : b->n_traj) - j0;
+    cudaError_t err = cudaSuccess;
+    auto d2h = [&](void *dst, const void *src, size_t elem_bytes) {
+      if (dst != nullptr && src != nullptr && err == cudaSuccess) {
+        err = cudaMemcpyAsync((char *) dst + j0 * elem_bytes, (const char *) src + j0 * elem_bytes,
+                              nj * elem_bytes, cudaMemcpyDeviceToHost, b->copy_stream);
+      }
+    };
+    d2h(y_out, b->d_y_out, sizeof(double) * b->n * b->nt);
+    d2h(b->n_out > 0 ? out : nullptr, b->d_out, sizeof(double) * b->n_out * b->nt);
+    d2h(stats, b->d_stats, sizeof(int) * 4);
+    d2h(code, b->d_code, sizeof(int));
+    d2h(t_last, b->d_t_last, sizeof(double));
+    d2h(step_size, b->d_step_size, sizeof(double));
+    copied[c] = 1;
+    --left;
+    return err;
+  };
+  while (left > 0) {
+    const cudaError_t q = cudaEventQuery(b->ev1);
+    if (q != cudaSuccess && q != cudaErrorNotReady) {
+      return fail("CUDA error while the batch was running: %s", cudaGetErrorString(q));
+    }
+    for (size_t c = 0; c < n_chunks; ++c) {
+      if (!copied[c] && (q == cudaSuccess || flag[c] != 0)) {
+        DDE_CUDA(copy_chunk(c));
+      }
+    }
+    if (left > 0) {
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+  }
+  DDE_CUDA(cudaStreamSynchronize(b->copy_stream));
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
 
 /* is_event / events of dopri_integrate, src/dopri.h:170-171, src/r_dopri.c:77-103 */
 int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event, size_t n_tcrit) {
@@ -953,8 +1054,7 @@ int dde_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, s
   }
   int rc = dde_dopri_batch_upload(b, y0, parms, parms_stride);
   rc = rc ? rc : dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
-  rc = rc ? rc : dde_dopri_batch_run(b);
-  rc = rc ? rc : dde_dopri_batch_download(b, y_out, out, stats, code, t_last, step_size);
+  rc = rc ? rc : dde_dopri_batch_run_download(b, y_out, out, stats, code, t_last, step_size);
   dde_dopri_batch_free(b);
   return rc;
 }

@@ -51,7 +51,34 @@ struct DopriArgs {
   double *y_final;       /* [n x n_traj] obj->y on return */
   /* work distribution: next trajectory index to hand out */
   unsigned long long *next_traj;
+  /* streamed download (dde_dopri_batch_run_download): trajectories are handed
+     out in index order, so the results of chunk c = [c << chunk_shift,
+     (c + 1) << chunk_shift) are complete long before the kernel ends.  The
+     thread that retires the last trajectory of a chunk raises chunk_flag[c]
+     (pinned, mapped host memory) and the host starts that chunk's
+     device-to-host copies while the kernel is still running.  NULL: off. */
+  unsigned *chunk_done; /* [n_chunks] trajectories retired so far */
+  int *chunk_flag;      /* [n_chunks] host-visible */
+  int chunk_shift;
 };
+
+#ifdef __CUDACC__
+/* called by the one thread that has written a trajectory's last result */
+__device__ __forceinline__ void chunk_retire(const DopriArgs &a, long long traj) {
+  if (a.chunk_done == nullptr) {
+    return;
+  }
+  __threadfence(); /* the results before the count */
+  const long long c = traj >> a.chunk_shift;
+  const long long first = c << a.chunk_shift;
+  const long long end = first + (1LL << a.chunk_shift) < a.n_traj ? first + (1LL << a.chunk_shift)
+                                                                 : a.n_traj;
+  if (atomicAdd(&a.chunk_done[c], 1u) + 1u == (unsigned) (end - first)) {
+    __threadfence_system();
+    *(volatile int *) &a.chunk_flag[c] = 1;
+  }
+}
+#endif
 
 } /* namespace dde */
 

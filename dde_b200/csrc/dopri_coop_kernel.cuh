@@ -878,6 +878,13 @@ __global__ void __launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 
     if (a.y_final != nullptr) {
       DDE_EACH(i) { a.y_final[traj * n + i] = Y[i]; }
     }
+    if (a.chunk_done != nullptr) { /* every thread of the block wrote result rows */
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        chunk_retire(a, traj);
+      }
+    }
 #undef DDE_COOP_EVAL
 #undef DDE_COOP_STAGE
   }

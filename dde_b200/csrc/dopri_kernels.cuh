@@ -815,6 +815,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
         }
       }
       a.ring_count[traj] = s_count[s];
+      chunk_retire(a, traj);
       active = false;
     }
   }

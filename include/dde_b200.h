@@ -194,6 +194,15 @@ int dde_dopri_batch_sync(dde_dopri_batch_t *b);
 int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out,
                              int32_t *stats, int32_t *code, double *t_last,
                              double *step_size);
+/* dde_dopri_batch_run + dde_dopri_batch_download in one blocking call, the
+ * two overlapped: trajectories are integrated in index order, so the results
+ * of each block of 32768 are copied to the host (on a second stream) as soon
+ * as the kernel reports the block complete, while later ones are still being
+ * integrated.  Same results as run + download; this is what the one-shot
+ * dde_dopri_batch uses.  Pinned host buffers make the copies asynchronous. */
+int dde_dopri_batch_run_download(dde_dopri_batch_t *b, double *y_out, double *out,
+                                 int32_t *stats, int32_t *code, double *t_last,
+                                 double *step_size);
 /* Milliseconds the last dde_dopri_batch_run spent on the device (CUDA
  * events on the handle's stream); < 0 if none has completed. */
 double dde_dopri_batch_last_ms(dde_dopri_batch_t *b);

@@ -581,3 +581,51 @@ def test_dopri_continue_r_style(backend):
     assert_bits_equal(np.asarray(third), np.asarray(second), "in place")
     fourth = dde_b200.dopri_continue(first, np.linspace(4, 5, 6), restartable=True)
     assert fourth.ptr is not None and np.asarray(fourth)[0, 0] == 4.0
+
+
+@pytest.mark.parametrize("n_traj", [100, 32768, 100000])
+def test_streamed_download_equals_run_then_download(backend, n_traj):
+    """dde_dopri_batch_run_download copies results block by block while the kernel runs:
+    same bits as run + download (several blocks, a ragged last one, failed trajectories);
+    a second streamed run on the same handle starts from clean flags."""
+    model, y0, parms, times, kw = workloads.mackey_glass(n_traj, first=1000)
+    b = dde_b200.DopriBatch(model, 1, n_traj, n_parms=3, **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    want = b.download()
+    for _ in range(2):
+        y = np.full((n_traj, b.nt, 1), -1.0)
+        stats = np.full((n_traj, 4), -1, dtype=np.int32)
+        code = np.full((n_traj,), -99, dtype=np.int32)
+        t_last = np.full((n_traj,), -1.0)
+        step_size = np.full((n_traj,), -1.0)
+        b.run_download_into(y, None, stats, code, t_last, step_size)
+        np.testing.assert_array_equal(code, want.code)
+        np.testing.assert_array_equal(stats, want.statistics)
+        assert_bits_equal(y, want.y, "y")
+        assert_bits_equal(t_last, want.t_last, "t_last")
+        assert_bits_equal(step_size, want.step_size, "step_size")
+    b.close()
+    if n_traj == 100:  # against the reference itself, and the one-shot call uses the same path
+        ref = pyoracle.dopri_batch(backend, model, y0, times, parms, **kw)
+        np.testing.assert_array_equal(code, ref.code)
+        assert_bits_equal(y, ref.y, "y vs reference")
+        got = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+        assert_bits_equal(got.y, ref.y, "one-shot y vs reference")
+
+
+def test_streamed_download_large_model(backend):
+    """the block-per-trajectory kernel raises the same completion flags"""
+    model, y0, parms, times, kw = workloads.seir_age(8)
+    b = dde_b200.DopriBatch(model, y0.shape[1], 8, n_parms=parms.shape[1], **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    want = b.download()
+    y = np.empty_like(want.y)
+    code = np.empty((8,), dtype=np.int32)
+    b.run_download_into(y, None, None, code, None, None)
+    np.testing.assert_array_equal(code, want.code)
+    assert_bits_equal(y, want.y, "y")
+    b.close()
