@@ -70,6 +70,7 @@ SYMBOLS = [
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dde_dopri_batch_run_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dde_dopri_batch_n_history", C.c_uint64, [C.c_void_p]),
     ("dde_dopri_batch_last_ms", C.c_double, [C.c_void_p]),
     ("dde_dopri_batch_last_launches", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_history", C.c_long, [C.c_void_p, _SZ, c_double_p, _SZ]),
@@ -88,6 +89,7 @@ SYMBOLS = [
     ("dde_difeq_batch_sync", C.c_int, [C.c_void_p]),
     ("dde_difeq_batch_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    ("dde_difeq_batch_history", C.c_long, [C.c_void_p, _SZ, c_double_p, _SZ]),
     ("dde_difeq_batch_last_ms", C.c_double, [C.c_void_p]),
     ("dde_device_count", C.c_int, []),
     ("dde_dopri_batch_sharded", C.c_int, _DOPRI_BATCH_ARGS + [c_int32_p, _SZ]),

@@ -326,7 +326,7 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
         if return_history:
             order = 5 if ctl.method == DOPRI_5 else 8
             hl = order * n + 2
-            cap = max(int(n_history), 1)
+            cap = max(int(lib.dde_dopri_batch_n_history(h)), 1)  # grow_history may enlarge it
             buf = np.empty((cap, hl))
             used = lib.dde_dopri_batch_history(h, 0, _dp(buf), cap)
             if used < 0:
@@ -465,12 +465,14 @@ def dopri_interpolate(h, t):
 class DifeqResult(np.ndarray):
     output = None
     code = None
+    history = None
 
     def __array_finalize__(self, obj):
         if obj is None:
             return
         self.output = getattr(obj, "output", None)
         self.code = getattr(obj, "code", None)
+        self.history = getattr(obj, "history", None)
 
 
 def _steps(steps):
@@ -506,28 +508,58 @@ def _difeq_call(y2d, steps, target, parms_arr, n_parms, stride, n_out, n_history
     return y_out, out, code, y_final
 
 
+def _grown_history(n_history, grow_history, st):
+    """grow_history for a difference equation: a ring that never overwrites is a ring
+    with room for every step of the run plus the initial state (src/difeq.c:49-56)."""
+    if grow_history and n_history > 0:
+        return max(int(n_history), int(st[-1] - st[0]) + 1)
+    return int(n_history)
+
+
 def difeq(y, steps, target, parms=None, *, n_out=0, n_history=0, grow_history=False,
-          return_by_column=True, return_initial=True, return_step=True,
+          return_history=None, return_by_column=True, return_initial=True, return_step=True,
           return_output_with_y=True, return_minimal=False):
-    """Iterate a difference equation; R/difeq.R:71-141."""
+    """Iterate a difference equation; R/difeq.R:71-141.  `return_history` (default:
+    n_history > 0) attaches the `history` attribute, [entries, 1 + n + n_out] = step, y,
+    out, oldest first (src/r_difeq.c:178-186; its out columns are NA, see
+    dde_difeq_batch_history)."""
+    if return_history is None:
+        return_history = n_history > 0
     if return_minimal:
         return_by_column = False
         return_initial = False
         return_step = False
         return_output_with_y = False
-    if grow_history:
-        raise DdeError("grow_history is not supported on the device: pre-size n_history")
     y = _f64(y, "y").ravel()
     st = _steps(steps)
+    n_history = _grown_history(n_history, grow_history, st)
     y2d, parms_arr, _, _, n_parms, stride = _prep_batch_inputs(y[None, :], parms)
-    y_out, out, code, _ = _difeq_call(y2d, st, target, parms_arr, n_parms, stride, n_out,
-                                      n_history, return_initial)
+    history = None
+    if return_history and n_history > 0:
+        from .batch import DifeqBatch
+        if n_history < 2:
+            raise DdeError("If given, n_history must be at least 2")  # R/difeq.R:119-121
+        b = DifeqBatch(target, y.shape[0], 1, n_parms=n_parms, n_out=n_out, n_history=n_history,
+                       restartable=True)
+        try:
+            b.upload(y2d, parms_arr if n_parms else None)
+            b.set_steps(st, return_initial)
+            b.run()
+            y_out, out, code, _ = b.download()
+            if code[0] == OK_COMPLETE:
+                history = b.history(0)
+        finally:
+            b.close()
+    else:
+        y_out, out, code, _ = _difeq_call(y2d, st, target, parms_arr, n_parms, stride, n_out,
+                                          n_history, return_initial)
     if code[0] != OK_COMPLETE:
         raise DdeError(strerror(code[0]))
     ret, output_attr = _bind(st.astype(np.float64), y_out[0], None if out is None else out[0],
                              return_step, return_output_with_y, return_by_column, return_initial)
     ret = np.ascontiguousarray(ret).view(DifeqResult)
     ret.output = output_attr if (output_attr is None or return_by_column) else output_attr.T
+    ret.history = history
     return ret
 
 
@@ -550,8 +582,6 @@ def difeq_replicate(n, y, steps, target, parms=None, *, n_out=0, n_history=0, gr
         return_initial = False
         return_step = False
         return_output_with_y = False
-    if grow_history:
-        raise DdeError("grow_history is not supported on the device: pre-size n_history")
     y = _f64(y, "y")
     if y.ndim == 1:
         y2d = np.ascontiguousarray(np.broadcast_to(y, (n, y.shape[0])))
@@ -560,6 +590,7 @@ def difeq_replicate(n, y, steps, target, parms=None, *, n_out=0, n_history=0, gr
     else:
         raise DdeError("'y' must have n rows")  # R/difeq_replicate.R:70-72
     st = _steps(steps)
+    n_history = _grown_history(n_history, grow_history, st)
     y2d, parms_arr, _, n_eq, n_parms, stride = _prep_batch_inputs(y2d, parms)
     y_out, out, code, _ = _difeq_call(y2d, st, target, parms_arr, n_parms, stride, n_out,
                                       n_history, return_initial, devices)

@@ -27,10 +27,10 @@ class DopriBatch:
     def __init__(self, func, n, n_traj, *, n_parms=0, n_out=0, method="dopri5", rtol=1e-6,
                  atol=1e-6, step_size_min=0.0, step_size_max=float("inf"), step_size_initial=0.0,
                  step_max_n=100000, step_size_min_allow=False, stiff_check=0, n_history=0,
-                 return_initial=True):
+                 grow_history=False, return_initial=True):
         self._lib = _lib.load()
         self.ctl = _control(method, rtol, atol, step_size_min, step_size_max, step_size_initial,
-                            step_max_n, step_size_min_allow, stiff_check, n_history, False,
+                            step_max_n, step_size_min_allow, stiff_check, n_history, grow_history,
                             return_initial)
         self.n, self.n_traj, self.n_parms, self.n_out = int(n), int(n_traj), int(n_parms), int(n_out)
         self.n_history = int(n_history)
@@ -134,6 +134,8 @@ class DopriBatch:
     def history(self, j):
         order = 5 if self.ctl.method == 0 else 8
         hl = order * self.n + 2
+        # the capacity as it is now: grow_history may have enlarged the rings
+        self.n_history = int(self._lib.dde_dopri_batch_n_history(self._h))
         cap = max(self.n_history, 1)
         buf = np.empty((cap, hl))
         used = self._lib.dde_dopri_batch_history(self._h, int(j), buf.ctypes.data_as(c_double_p), cap)
@@ -208,6 +210,18 @@ class DifeqBatch:
         other.__dict__.update(self.__dict__)
         other._h = h
         return other
+
+    def history(self, j):
+        """The `history` attribute of replicate j: [entries, 1 + n + n_out] = step, y, out
+        (out columns NA), oldest first.  The run must have been restartable."""
+        hl = 1 + self.n + self.n_out
+        cap = max(self.n_history, 1)
+        buf = np.empty((cap, hl))
+        used = self._lib.dde_difeq_batch_history(self._h, int(j), buf.ctypes.data_as(c_double_p),
+                                                 cap)
+        if used < 0:
+            raise DdeError(_lib.last_error())
+        return buf[:used].copy()
 
     def sync(self):
         self._check(self._lib.dde_difeq_batch_sync(self._h))

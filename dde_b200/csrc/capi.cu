@@ -102,6 +102,18 @@ int check_model_shape(const dde::ModelDesc *m, size_t n, size_t n_parms, size_t 
   return 0;
 }
 
+__global__ void max_uint_kernel(const unsigned *x, long long n, unsigned *out) {
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  unsigned v = i < n ? x[i] : 0u;
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned o = __shfl_down_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  if ((threadIdx.x & 31) == 0 && v > 0) {
+    atomicMax(out, v);
+  }
+}
+
 __global__ void fill_int_kernel(int *x, long long n, int value) {
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if (i < n) {
@@ -432,11 +444,6 @@ dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model, const dde_dopri_cont
     fail("unknown method %d", (int) ctl->method);
     return nullptr;
   }
-  if (ctl->grow_history) {
-    fail("grow_history is not supported on the device (no allocation inside kernels): "
-         "pre-size n_history");
-    return nullptr;
-  }
   if (n_traj == 0) {
     fail("n_traj must be positive");
     return nullptr;
@@ -702,7 +709,57 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
 
 extern "C" {
 
-int dde_dopri_batch_run(dde_dopri_batch_t *b) { return dopri_run_impl(b, 0); }
+/* grow_history (dopri_data_alloc's argument, src/dopri.c:92-95: a ring that
+ * grows instead of overwriting).  Nothing is allocated inside a kernel: the run
+ * is repeated with a larger ring until no trajectory's ring has wrapped -- the
+ * results are then what an unbounded ring gives.  Blocking. */
+static int dopri_run_grow(dde_dopri_batch_t *b) {
+  for (;;) {
+    const int rc = dopri_run_impl(b, 0);
+    if (rc != 0) {
+      return rc;
+    }
+    const size_t cap = (size_t) b->ctl.n_history;
+    if (!b->ctl.grow_history || cap == 0 || b->reset_code != 0) {
+      return 0;
+    }
+    unsigned *d_max = reinterpret_cast<unsigned *>(b->d_next); /* free once the run is over */
+    DDE_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned), b->stream));
+    const int threads = 256;
+    const long long blocks = ((long long) b->n_traj + threads - 1) / threads;
+    max_uint_kernel<<<(unsigned) blocks, threads, 0, b->stream>>>(b->d_ring_count,
+                                                                  (long long) b->n_traj, d_max);
+    DDE_CUDA(cudaGetLastError());
+    unsigned most = 0;
+    DDE_CUDA(cudaMemcpyAsync(&most, d_max, sizeof most, cudaMemcpyDeviceToHost, b->stream));
+    DDE_CUDA(cudaStreamSynchronize(b->stream));
+    if ((size_t) most <= cap) {
+      return 0;
+    }
+    const size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
+    const size_t hl = (size_t) b->order * b->n + 2;
+    free_dev(b->d_ring);
+    if (cudaMalloc(&b->d_ring, sizeof(double) * hl * bigger * b->n_traj) != cudaSuccess) {
+      (void) cudaGetLastError();
+      b->d_ring = nullptr;
+      b->ran = false;
+      return fail("grow_history: cannot allocate %.2f GB of history rings (%zu entries per "
+                  "trajectory)", (double) (sizeof(double) * hl * bigger * b->n_traj) / 1e9, bigger);
+    }
+    b->ctl.n_history = bigger;
+  }
+}
+
+int dde_dopri_batch_run(dde_dopri_batch_t *b) {
+  if (b != nullptr && b->ctl.grow_history) {
+    return dopri_run_grow(b);
+  }
+  return dopri_run_impl(b, 0);
+}
+
+uint64_t dde_dopri_batch_n_history(dde_dopri_batch_t *b) {
+  return b == nullptr ? 0 : b->ctl.n_history;
+}
 
 /* Run and download in one call, overlapping the two: see DopriArgs::chunk_done.
  * The copies of a chunk start as soon as the kernel reports it complete, on a
@@ -712,6 +769,10 @@ int dde_dopri_batch_run_download(dde_dopri_batch_t *b, double *y_out, double *ou
                                  double *step_size) {
   if (b == nullptr) {
     return fail("NULL handle");
+  }
+  if (b->ctl.grow_history) { /* the run may have to be repeated: no streaming */
+    const int rc = dopri_run_grow(b);
+    return rc ? rc : dde_dopri_batch_download(b, y_out, out, stats, code, t_last, step_size);
   }
   DDE_CUDA(cudaSetDevice(b->device));
   const size_t chunk = (size_t) 1 << DDE_CHUNK_SHIFT;
@@ -820,6 +881,10 @@ int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double
   }
   if (!b->ran) {
     return fail("nothing has been run on this handle: there is nothing to continue");
+  }
+  if (b->ctl.grow_history) {
+    return fail("a batch with grow_history cannot be continued (a run that outgrows its rings "
+                "is repeated from its start): pre-size n_history instead");
   }
   if (times == nullptr || n_times < 2) {
     return fail("At least two times must be given"); /* src/r_dopri.c:211-213 */
@@ -1533,6 +1598,62 @@ int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out, i
   }
   DDE_CUDA(cudaStreamSynchronize(b->stream));
   return 0;
+}
+
+/* The `history` attribute of a difference equation (src/r_difeq.c:178-186,
+ * ring_buffer_read from the tail): entries {step, y[n], out[n_out]}, oldest
+ * first.  The run must have been restartable (its history is then in HBM). */
+long dde_difeq_batch_history(dde_difeq_batch_t *b, size_t j, double *history,
+                             size_t max_entries) {
+  if (b == nullptr || !b->ran || j >= b->n_rep) {
+    fail("bad handle or replicate index");
+    return -1;
+  }
+  const size_t cap = b->n_history;
+  if (cap == 0) {
+    return 0;
+  }
+  if (!b->kept_history) {
+    fail("the last run was not restartable: call dde_difeq_batch_restartable(b, 1) before "
+         "running to keep its history");
+    return -1;
+  }
+  if (cudaSetDevice(b->device) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    fail("CUDA error in history export");
+    return -1;
+  }
+  unsigned count = 0;
+  if (cudaMemcpy(&count, b->d_ring_count + j, sizeof count, cudaMemcpyDeviceToHost) !=
+      cudaSuccess) {
+    fail("CUDA error in history export");
+    return -1;
+  }
+  const size_t hl = 1 + b->n + b->n_out;
+  const size_t used = count < cap ? count : cap;
+  if (history != nullptr && used > 0) {
+    std::vector<double> ring(cap * hl);
+    if (cudaMemcpy(ring.data(), b->d_ring + j * cap * hl, sizeof(double) * cap * hl,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fail("CUDA error in history export");
+      return -1;
+    }
+    const size_t first = count - used;
+    for (size_t e = 0; e < used && e < max_entries; ++e) {
+      const size_t slot = (first + e) % cap;
+      double *dst = history + e * hl;
+      /* entry idx holds the state after idx steps from the handle's first step */
+      dst[0] = (double) (b->step_origin + first + e);
+      memcpy(dst + 1, ring.data() + slot * hl + 1, sizeof(double) * b->n);
+      /* the output columns are not reproduced: the reference writes them
+         through a pointer that lags the ring head (src/difeq.c:203-206,
+         out_next), NA_real_ here */
+      const unsigned long long na_bits = 0x7FF00000000007A2ULL;
+      for (size_t i = 0; i < b->n_out; ++i) {
+        memcpy(dst + 1 + b->n + i, &na_bits, sizeof(double));
+      }
+    }
+  }
+  return (long) used;
 }
 
 double dde_difeq_batch_last_ms(dde_difeq_batch_t *b) {

@@ -79,7 +79,8 @@ typedef struct dde_dopri_control {
   uint64_t n_history;       /* ring capacity in accepted steps, src/dopri.c:53 */
   int32_t method;           /* DDE_DOPRI_5 | DDE_DOPRI_853 */
   int32_t step_size_min_allow; /* src/dopri.c:351-354 */
-  int32_t grow_history;     /* must be 0: no allocation inside kernels */
+  int32_t grow_history;     /* grow the ring instead of overwriting (src/dopri.c:92-95): the run
+                               is repeated with larger rings until none has wrapped */
   int32_t return_initial;   /* src/dopri.c:320-327 */
 } dde_dopri_control;
 
@@ -171,7 +172,7 @@ int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times,
 int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event,
                                size_t n_tcrit);
 /* dopri_integrate for every trajectory, from the resident y0/parms.
- * Asynchronous on the handle's stream. */
+ * Asynchronous on the handle's stream (blocking with ctl.grow_history). */
 int dde_dopri_batch_run(dde_dopri_batch_t *b);
 /* dopri_continue (R/dopri.R:469-511, src/r_dopri.c:193-262): integrate on from
  * where the last run of this handle ended -- the checkpoint/resume of the
@@ -203,6 +204,8 @@ int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out,
 int dde_dopri_batch_run_download(dde_dopri_batch_t *b, double *y_out, double *out,
                                  int32_t *stats, int32_t *code, double *t_last,
                                  double *step_size);
+/* Ring capacity in entries: ctl.n_history, or what grow_history made of it. */
+uint64_t dde_dopri_batch_n_history(dde_dopri_batch_t *b);
 /* Milliseconds the last dde_dopri_batch_run spent on the device (CUDA
  * events on the handle's stream); < 0 if none has completed. */
 double dde_dopri_batch_last_ms(dde_dopri_batch_t *b);
@@ -279,6 +282,14 @@ dde_difeq_batch_t *dde_difeq_batch_copy(dde_difeq_batch_t *b);
 int dde_difeq_batch_sync(dde_difeq_batch_t *b);
 int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
                              int32_t *code, double *y_final);
+/* The `history` attribute for replicate j (src/r_difeq.c:178-186): entries
+ * {step, y[n], out[n_out]} oldest first, [max_entries x (1 + n + n_out)];
+ * returns the number of entries the ring holds, < 0 on error.  Needs a
+ * restartable run (dde_difeq_batch_restartable), which keeps the history in
+ * HBM.  The out columns are NA_real_: the reference fills them through a
+ * pointer that lags the ring head, which is not reproduced. */
+long dde_difeq_batch_history(dde_difeq_batch_t *b, size_t j, double *history,
+                             size_t max_entries);
 double dde_difeq_batch_last_ms(dde_difeq_batch_t *b);
 
 /* ---- multi-GPU ---------------------------------------------------------------- */

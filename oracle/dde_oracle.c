@@ -238,6 +238,7 @@ typedef struct {
   size_t len;      /* doubles per entry */
   size_t first;    /* slot of the oldest committed entry */
   size_t used;     /* committed entries */
+  int grow;        /* enlarge instead of losing the oldest entry (OVERFLOW_GROW) */
   double *slots;   /* cap + 1 slots: one spare so the head is always writable */
 } hist;
 
@@ -246,6 +247,7 @@ static void hist_init(hist *h, size_t cap, size_t len) {
   h->len = len;
   h->first = 0;
   h->used = 0;
+  h->grow = 0;
   h->slots = (double *) calloc((cap + 1) * len, sizeof(double));
 }
 
@@ -255,7 +257,15 @@ static double *hist_slot(const hist *h, size_t k) { /* k-th oldest committed; k 
 
 static double *hist_head(const hist *h) { return hist_slot(h, h->used); }
 
-static void hist_commit(hist *h) { /* ring_buffer_head_advance, overwrite policy */
+static void hist_commit(hist *h) { /* ring_buffer_head_advance */
+  if (h->used == h->cap && h->grow && h->cap > 0) {
+    /* grow policy: nothing was ever dropped, so first == 0 and the entries are
+       contiguous; double the storage and carry on */
+    const size_t bigger = 2 * h->cap;
+    h->slots = (double *) realloc(h->slots, (bigger + 1) * h->len * sizeof(double));
+    memset(h->slots + (h->cap + 1) * h->len, 0, (bigger - h->cap) * h->len * sizeof(double));
+    h->cap = bigger;
+  }
   if (h->used == h->cap) {
     if (h->cap > 0) {
       h->first = (h->first + 1) % (h->cap + 1);
@@ -802,6 +812,7 @@ static void solver_setup(solver *s, const model_entry *m, const dde_dopri_contro
     s->k[j] = block + (4 + j) * n;
   }
   hist_init(&s->history, (size_t) ctl->n_history, (size_t) s->order * n + 2);
+  s->history.grow = ctl->grow_history != 0;
 }
 
 static void solver_release(solver *s) {
@@ -1111,6 +1122,41 @@ static int iterate(target_fn *target, size_t n, size_t n_out, const double *y0,
                                      y_out, out, y_final);
   iterator_release(&it);
   return failed;
+}
+
+/* One replicate, also returning the `history` attribute (src/r_difeq.c:178-186):
+ * entries {step, y[n], out[n_out]} oldest first; the out columns are NA here (the
+ * reference fills them through a pointer that lags the head, not restated). */
+long oracle_difeq_history(const char *model, size_t n, size_t n_out, const double *y0,
+                          const double *parms, const uint64_t *steps, size_t n_steps,
+                          size_t n_history, int32_t grow_history, int32_t return_initial,
+                          double *y_out, double *out, int32_t *code, double *history,
+                          size_t max_entries) {
+  const model_entry *m = find_model(model);
+  if (m == NULL || m->target == NULL) {
+    return -1;
+  }
+  const size_t nt = return_initial ? n_steps : n_steps - 1;
+  double *scratch = (double *) calloc(n_out * nt + 1, sizeof(double));
+  iterator it;
+  iterator_setup(&it, n, n_out, n_history);
+  if (it.have_history) {
+    it.history.grow = grow_history != 0;
+  }
+  const int failed = iterate_segment(&it, m->target, y0, parms, steps, n_steps,
+                                     return_initial != 0, 0, y_out, out ? out : scratch, NULL);
+  *code = failed ? DDE_ERR_DIFEQ_HISTORY : DDE_OK_COMPLETE;
+  long used = 0;
+  if (it.have_history) {
+    used = (long) it.history.used;
+    for (size_t k = 0; history && k < it.history.used && k < max_entries; ++k) {
+      memcpy(history + k * it.history.len, hist_slot(&it.history, k),
+             it.history.len * sizeof(double));
+    }
+  }
+  iterator_release(&it);
+  free(scratch);
+  return used;
 }
 
 /* difeq_continue, src/r_difeq.c:114-165: steps1 then steps2 on the same

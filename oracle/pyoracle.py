@@ -197,7 +197,37 @@ def dopri_continue(backend, model, y, times1, times2, parms=None, *, y_new=None,
     return r
 
 
-def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, **ctl_kwargs):
+def difeq_history(backend, model, y, steps, parms=None, *, n_out=0, n_history=0,
+                  grow_history=False, return_initial=True, max_entries=None):
+    """One replicate, also returning the `history` attribute [n_entries, 1 + n + n_out]."""
+    lib = load(backend)
+    pre = "ref" if backend == "ref" else "oracle"
+    y, p, n_rep, n, n_parms, stride = _prep(y, parms)
+    assert n_rep == 1
+    steps = np.ascontiguousarray(steps, dtype=np.uint64)
+    nt = steps.shape[0] if return_initial else steps.shape[0] - 1
+    hl = 1 + n + n_out
+    cap = max(int(max_entries or n_history), 1)
+    r = Result()
+    r.y = np.zeros((nt, n))
+    r.output = np.zeros((nt, n_out)) if n_out > 0 else None
+    r.code = np.zeros((1,), dtype=np.int32)
+    hist = np.zeros((cap, hl))
+    fn = getattr(lib, pre + "_difeq_history")
+    fn.restype = C.c_long
+    used = fn(model.encode(), C.c_size_t(n), C.c_size_t(n_out), _dp(y), _dp(p),
+              steps.ctypes.data_as(c_uint64_p), C.c_size_t(steps.shape[0]),
+              C.c_size_t(n_history), C.c_int32(int(grow_history)), C.c_int32(int(return_initial)),
+              _dp(r.y), _dp(r.output), _ip(r.code), _dp(hist), C.c_size_t(cap))
+    if used < 0:
+        raise RuntimeError("difeq_history failed")
+    r.n_entries = int(used)
+    r.history = hist[:min(used, cap)].copy()
+    return r
+
+
+def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, max_entries=None,
+                  **ctl_kwargs):
     """One trajectory, also returning the `history` attribute [n_entries, order*n + 2]."""
     lib = load(backend)
     pre = "ref" if backend == "ref" else "oracle"
@@ -209,7 +239,7 @@ def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, 
     nt = times.shape[0] if ctl.return_initial else times.shape[0] - 1
     order = 5 if ctl.method == 0 else 8
     hl = order * n + 2
-    cap = max(int(ctl.n_history), 1)
+    cap = max(int(max_entries or ctl.n_history), 1)
     r = Result()
     r.y = np.zeros((nt, n))
     r.output = np.zeros((nt, n_out)) if n_out > 0 else None
@@ -224,7 +254,8 @@ def dopri_history(backend, model, y, times, parms=None, *, n_out=0, tcrit=None, 
         _ip(r.code), _dp(r.t_last), _dp(r.step_size), _dp(hist), cap)
     if used < 0:
         raise RuntimeError(getattr(lib, pre + "_last_message")().decode())
-    r.history = hist[:used].copy()
+    r.n_entries = int(used)
+    r.history = hist[:min(used, cap)].copy()
     return r
 
 

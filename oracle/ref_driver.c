@@ -659,6 +659,40 @@ int ref_difeq_batch(const char *model, size_t n, size_t n_out, size_t n_rep,
                             return_initial, y_out, out, code, y_final, 0);
 }
 
+/* One replicate, also returning the `history` attribute as r_difeq does
+ * (ring_buffer_read from the tail, src/r_difeq.c:178-186). */
+long ref_difeq_history(const char *model, size_t n, size_t n_out, const double *y0,
+                       const double *parms, const uint64_t *steps, size_t n_steps,
+                       size_t n_history, int32_t grow_history, int32_t return_initial,
+                       double *y_out, double *out, int32_t *code, double *history,
+                       size_t max_entries) {
+  model_entry m;
+  if (find_model(model, &m) != 0 || !m.target) {
+    return -1;
+  }
+  const size_t nt = return_initial ? n_steps : n_steps - 1;
+  size_t *st = (size_t *) calloc(n_steps, sizeof(size_t));
+  for (size_t i = 0; i < n_steps; ++i) {
+    st[i] = (size_t) steps[i];
+  }
+  double *scratch_out = (double *) calloc(n_out * nt + 1, sizeof(double));
+  difeq_data *obj = difeq_data_alloc(m.target, n, n_out, parms, n_history, grow_history != 0);
+  *code = run_one_difeq(obj, n, y0, st, n_steps, y_out,
+                        n_out > 0 ? (out ? out : scratch_out) : NULL, return_initial, NULL);
+  long used = 0;
+  if (n_history > 0) {
+    used = (long) ring_buffer_used(obj->history, false);
+    if (history) {
+      const size_t take = (size_t) used < max_entries ? (size_t) used : max_entries;
+      ring_buffer_read(obj->history, history, take);
+    }
+  }
+  difeq_data_free(obj);
+  free(st);
+  free(scratch_out);
+  return used;
+}
+
 /* difeq_continue (src/r_difeq.c:114-165): steps1, then -- same difeq_data
  * object -- steps2 from y_new, or from obj->y1 when y_new is NULL.  Results of
  * the second segment; a replicate whose first segment failed gets

@@ -113,5 +113,8 @@ def test_argument_validation_matches_the_reference():
         dde_b200.difeq([0.1], [-1, 3], "logistic", [1.5])
     with pytest.raises(dde_b200.DdeError):
         dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "no_such_model", [[1.0]])
-    with pytest.raises(dde_b200.DdeError, match="grow_history"):
-        dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[1.0]], grow_history=True)
+    # and the product path has no CPU fallback: without a device it fails loudly
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(dde_b200.DdeError, match="no CUDA device"):
+            dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[1.0]], grow_history=True)

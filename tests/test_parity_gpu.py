@@ -629,3 +629,74 @@ def test_streamed_download_large_model(backend):
     np.testing.assert_array_equal(code, want.code)
     assert_bits_equal(y, want.y, "y")
     b.close()
+
+
+def test_grow_history_dopri(backend):
+    """grow_history (src/dopri.c:92-95): a ring that grows instead of overwriting.  On
+    the device the run is repeated with larger rings until none has wrapped; results,
+    statistics and the full history are those of the reference's growing ring."""
+    model, y0, parms, times, kw = workloads.mackey_glass(48, first=300)
+    kw = dict(kw, n_history=10)
+    want = pyoracle.dopri_batch(backend, model, y0, times, parms, grow_history=True, **kw)
+    got = dde_b200.dopri_batch(y0, times, model, parms, grow_history=True, **kw)
+    np.testing.assert_array_equal(got.code, want.code)
+    np.testing.assert_array_equal(got.statistics, want.statistics)
+    assert_bits_equal(got.y, want.y, "y")
+    # without growing, ten entries lose the lagged history: the results differ
+    lost = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+    assert (lost.code != 1).any()
+    b = dde_b200.DopriBatch(model, 1, 48, n_parms=3, grow_history=True, **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    res = b.download()
+    np.testing.assert_array_equal(res.statistics, want.statistics)
+    for j in (0, 17, 47):
+        ref = pyoracle.dopri_history(backend, model, y0[j:j + 1], times, parms[j:j + 1],
+                                     grow_history=True, max_entries=2000, **kw)
+        h = b.history(j)
+        assert h.shape[0] == ref.n_entries == want.statistics[j, 2]
+        assert_bits_equal(h, ref.history, "history %d" % j)
+    assert b.n_history >= want.statistics[:, 2].max()
+    with pytest.raises(dde_b200.DdeError, match="grow_history"):
+        b.continue_(np.linspace(500, 600, 3))
+    b.close()
+    # the single-trajectory interface, history attribute included
+    one = dde_b200.dopri(y0[5], times, model, parms[5], grow_history=True, return_history=True,
+                         return_statistics=True, **kw)
+    ref = pyoracle.dopri_history(backend, model, y0[5:6], times, parms[5:6], grow_history=True,
+                                 max_entries=2000, **kw)
+    assert_bits_equal(np.asarray(one.history), ref.history, "dopri(...).history")
+
+
+@pytest.mark.parametrize("grow", [False, True])
+def test_difeq_history(backend, grow):
+    """the `history` attribute of a difference equation (src/r_difeq.c:178-186) and
+    grow_history for difference equations"""
+    steps = np.arange(0, 41)
+    got = dde_b200.difeq([0.1], steps, "logistic", [1.5], n_history=5, grow_history=grow)
+    ref = pyoracle.difeq_history(backend, "logistic", [[0.1]], steps, [1.5], n_history=5,
+                                 grow_history=grow, max_entries=64)
+    assert got.history.shape[0] == ref.n_entries == (41 if grow else 5)
+    assert_bits_equal(got.history, ref.history, "history")
+    # a delay model with gaps between the stored steps, many replicates in one batch
+    model, y0, parms, st, kw = workloads.sir_delay(8, n_steps=300)
+    b = dde_b200.DifeqBatch(model, 3, 8, n_parms=2, restartable=True,
+                            n_history=301 if grow else 16)
+    b.upload(y0, parms)
+    b.set_steps(st, return_initial=False)
+    b.run()
+    y, _, code, _ = b.download()
+    assert (code == 1).all()
+    for j in (0, 7):
+        ref = pyoracle.difeq_history(backend, model, y0[j:j + 1], st, parms[j:j + 1], n_history=16,
+                                     grow_history=grow, return_initial=False, max_entries=512)
+        assert_bits_equal(y[j], ref.y, "y")
+        assert_bits_equal(b.history(j), ref.history, "history %d" % j)
+    b.close()
+    # with outputs: steps and states as the reference's, the out columns are NA
+    got = dde_b200.difeq([1.0], 12, "fib_out", None, n_out=1, n_history=4)
+    ref = pyoracle.difeq_history(backend, "fib_out", [[1.0]], np.arange(0, 13), None, n_out=1,
+                                 n_history=4, max_entries=16)
+    assert_bits_equal(got.history[:, :2], ref.history[:, :2], "history step, y")
+    assert np.isnan(got.history[:, 2]).all()
