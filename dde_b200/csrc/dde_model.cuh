@@ -112,7 +112,7 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
                                int *n_launches) {
   DifeqArgs a = args_in;
   /* keep the history on chip when it fits: [slot][component][thread] doubles */
-  size_t dyn = DDE_CTX_BYTES;
+  size_t dyn = 0; /* the difeq context is static shared memory, lag_ctx.cuh */
   a.staged = 0;
   if (a.n_history > 0) {
     const size_t bytes = sizeof(double) * (size_t) a.n_history * (size_t) a.n * DDE_TPB;

@@ -117,13 +117,13 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     unsigned long long step = step_first;
     int steps_idx = 1;
     double *ring = a.ring + (size_t) rep * (size_t) cap * (size_t) hl;
-    s_ring[s] = ring;
-    s_y0[s] = y0;
-    s_step0[s] = (long long) step_first;
-    s_step[s] = (long long) step;
-    s_code[s] = 0;
-    s_error[s] = 0;
-    s_cfg[s] = cfg;
+    sd_ring[s] = ring;
+    sd_y0[s] = y0;
+    sd_step0[s] = (long long) step_first;
+    sd_step[s] = (long long) step;
+    sd_code[s] = 0;
+    sd_error[s] = 0;
+    sd_cfg[s] = cfg;
 
     int head = 0;
     unsigned count = 0;
@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       head = (int) (count % (unsigned) cap);
       const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
       if (count > 0) {
-        s_step0[s] = (long long) (a.step_origin + (count - used));
+        sd_step0[s] = (long long) (a.step_origin + (count - used));
       }
       if (a.staged) { /* back on chip */
         for (unsigned k = 0; k < used; ++k) {
           const double *src = ring + (size_t) k * (size_t) hl + 1;
-          double *dst = s_wc + (size_t) k * n * DDE_TPB + s;
+          double *dst = sd_hist + (size_t) k * n * DDE_TPB + s;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             dst[(size_t) i * DDE_TPB] = src[i];
@@ -147,14 +147,14 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         }
       }
     }
-    s_count[s] = count;
-    s_head[s] = head;
+    sd_count[s] = count;
+    sd_head[s] = head;
 #define DDE_DIFEQ_COMMIT(yy)                                  \
   do {                                                        \
     if (cap > 0) {                                            \
       if (a.staged) {                                         \
         /* on-chip history: only y is ever read back */       \
-        double *dst = s_wc + (size_t) head * n * DDE_TPB + s; \
+        double *dst = sd_hist + (size_t) head * n * DDE_TPB + s; \
         _Pragma("unroll") for (int i = 0; i < n; ++i) {       \
           dst[(size_t) i * DDE_TPB] = (yy)[i];                \
         }                                                     \
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       }                                                       \
       head = head + 1 == cap ? 0 : head + 1;                  \
       ++count;                                                \
-      s_head[s] = head;                                       \
-      s_count[s] = count;                                     \
+      sd_head[s] = head;                                       \
+      sd_count[s] = count;                                     \
     }                                                         \
   } while (0)
 
@@ -196,12 +196,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
 
     bool failed = false;
     for (;;) {
-      s_step[s] = (long long) step;
+      sd_step[s] = (long long) step;
       if (NC > 0) { /* what yprev_* will read: lets the optimiser drop the other path */
-        __builtin_assume(s_cfg[s] == cfg);
+        __builtin_assume(sd_cfg[s] == cfg);
       }
       M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
-      if (s_error[s]) {
+      if (sd_error[s]) {
         failed = true; /* Rf_error in difeq_find_step, src/difeq.c:267-270 */
         break;
       }
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     if (!failed && has_output && store_next_output) {
       /* trailing call for the outputs of the last stored row,
          src/difeq.c:249-255 */
-      s_step[s] = (long long) step;
+      sd_step[s] = (long long) step;
       M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
-      if (s_error[s]) {
+      if (sd_error[s]) {
         failed = true;
       } else {
 #pragma unroll
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       }
     }
 #undef DDE_DIFEQ_COMMIT
-    a.code[rep] = failed ? s_code[s] : 1; /* OK_COMPLETE */
+    a.code[rep] = failed ? sd_code[s] : 1; /* OK_COMPLETE */
     if (RESTART && cap > 0 && a.restartable) {
       /* what a later difeq_continue needs: the count, and an on-chip history
          written back to the replicate's ring (slot order is the same) */
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
         for (unsigned k = 0; k < used; ++k) {
           double *dst = ring + (size_t) k * (size_t) hl + 1;
-          const double *src = s_wc + (size_t) k * n * DDE_TPB + s;
+          const double *src = sd_hist + (size_t) k * n * DDE_TPB + s;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             dst[i] = src[(size_t) i * DDE_TPB];

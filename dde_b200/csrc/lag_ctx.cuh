@@ -78,9 +78,6 @@ enum {
   DDE_F_WT,       /* DDE_WIN rows */
   DDE_F_WH = DDE_F_WT + DDE_WIN,
   DDE_F_COUNT64 = DDE_F_WH + DDE_WIN,
-  /* difeq has no lag window: obj->step, obj->step0 share its fields */
-  DDE_F_STEP = DDE_F_ATT_LO,
-  DDE_F_STEP0 = DDE_F_ATT_HI
 };
 /* 32-bit fields: */
 enum {
@@ -113,12 +110,30 @@ static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s
 #define s_t0 (s_ctx64[::dde::DDE_F_T0])
 #define s_sign (s_ctx64[::dde::DDE_F_SIGN])
 #define s_cfg (s_ctx32[::dde::DDE_FI_CFG])
-#define s_step ((long long *) s_ctx64[::dde::DDE_F_STEP])
-#define s_step0 ((long long *) s_ctx64[::dde::DDE_F_STEP0])
 #define s_count ((unsigned *) s_ctx32[::dde::DDE_FI_COUNT])
 #define s_head (s_ctx32[::dde::DDE_FI_HEAD])
 #define s_code (s_ctx32[::dde::DDE_FI_CODE])
 #define s_error (s_ctx32[::dde::DDE_FI_ERROR])
+
+/* A difference equation needs far less -- no lag window, no times -- and its
+ * on-chip history is written every step: its context is a block of its own in
+ * STATIC shared memory, so that the compiler can tell a history store from a
+ * context field (it cannot inside one array) and keeps the fields in registers
+ * across the step.  The history then starts at the dynamic base. */
+enum { DDE_D_RING = 0, DDE_D_Y0, DDE_D_STEP, DDE_D_STEP0, DDE_D_COUNT64 };
+enum { DDE_DI_COUNT = 0, DDE_DI_HEAD, DDE_DI_CODE, DDE_DI_ERROR, DDE_DI_CFG, DDE_DI_COUNT32 };
+__shared__ double s_dctx64[DDE_D_COUNT64][DDE_TPB];
+__shared__ int s_dctx32[DDE_DI_COUNT32][DDE_TPB];
+#define sd_ring ((double **) ::dde::s_dctx64[::dde::DDE_D_RING])
+#define sd_y0 ((const double **) ::dde::s_dctx64[::dde::DDE_D_Y0])
+#define sd_step ((long long *) ::dde::s_dctx64[::dde::DDE_D_STEP])   /* obj->step */
+#define sd_step0 ((long long *) ::dde::s_dctx64[::dde::DDE_D_STEP0]) /* obj->step0 */
+#define sd_count ((unsigned *) ::dde::s_dctx32[::dde::DDE_DI_COUNT])
+#define sd_head (::dde::s_dctx32[::dde::DDE_DI_HEAD])
+#define sd_code (::dde::s_dctx32[::dde::DDE_DI_CODE])
+#define sd_error (::dde::s_dctx32[::dde::DDE_DI_ERROR])
+#define sd_cfg (::dde::s_dctx32[::dde::DDE_DI_CFG])
+#define sd_hist (::dde::dde_smem) /* [slot][component][thread] when staged */
 
 /* The staged lag window ("shared-memory staging of the bracketing history
  * steps"): up to DDE_WIN consecutive committed entries base .. base + wn - 1
@@ -713,26 +728,26 @@ struct PrevHit {
 
 static __device__ __forceinline__ PrevHit dde_find_step(int s, int step) {
   PrevHit hit;
-  const int cfg = s_cfg[s];
-  const int offset = (int) s_step[s] - step;
+  const int cfg = sd_cfg[s];
+  const int offset = (int) sd_step[s] - step;
   const int cap = dde::s_lag_u.cap;
-  const unsigned count = s_count[s];
+  const unsigned count = sd_count[s];
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   hit.staged = (cfg >> 24) != 0;
   hit.ok = !(cap == 0 || offset < 0 || (unsigned) offset >= used);
   hit.e = nullptr;
   hit.stride = 1;
   if (!hit.ok) {
-    s_error[s] = 1;
-    s_code[s] = -9; /* DDE_ERR_DIFEQ_HISTORY */
+    sd_error[s] = 1;
+    sd_code[s] = -9; /* DDE_ERR_DIFEQ_HISTORY */
     return hit;
   }
-  const int slot = dde::ring_slot_back(s_head[s], offset + 1, cap);
+  const int slot = dde::ring_slot_back(sd_head[s], offset + 1, cap);
   if (hit.staged) {
-    hit.e = s_wc + (size_t) slot * (cfg & 0xffff) * DDE_TPB + s;
+    hit.e = sd_hist + (size_t) slot * (cfg & 0xffff) * DDE_TPB + s;
     hit.stride = DDE_TPB;
   } else {
-    hit.e = s_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
+    hit.e = sd_ring[s] + (size_t) slot * dde::s_lag_u.hl + 1;
   }
   return hit;
 }
@@ -750,8 +765,8 @@ static __device__ __forceinline__ PrevHit dde_find_step(int s, int step) {
 
 static __device__ __forceinline__ double yprev_1(int step, size_t i) {
   const int s = threadIdx.x;
-  if (step <= (int) s_step0[s]) {
-    return s_y0[s][i];
+  if (step <= (int) sd_step0[s]) {
+    return sd_y0[s][i];
   }
   const PrevHit hit = dde_find_step(s, step);
   double ret = dde::na_real();
@@ -764,9 +779,9 @@ static __device__ __forceinline__ double yprev_1(int step, size_t i) {
 static __device__ __forceinline__ void yprev_all(int step, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
-  if (step <= (int) s_step0[s]) {
+  if (step <= (int) sd_step0[s]) {
     for (int i = 0; i < n; ++i) {
-      y[i] = s_y0[s][i];
+      y[i] = sd_y0[s][i];
     }
     return;
   }
@@ -782,9 +797,9 @@ template <class Index>
 static __device__ __forceinline__ void dde_yprev_indexed(int step, const Index *idx,
                                                          size_t nidx, double *y) {
   const int s = threadIdx.x;
-  if (step <= (int) s_step0[s]) {
+  if (step <= (int) sd_step0[s]) {
     for (size_t i = 0; i < nidx; ++i) {
-      y[i] = s_y0[s][idx[i]];
+      y[i] = sd_y0[s][idx[i]];
     }
     return;
   }
