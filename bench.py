@@ -55,7 +55,9 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread
+    (every 10 ms; an nvidia-smi process per rank is too slow to answer inside a
+    sub-second region on an 8-GPU box), nvidia-smi as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -65,8 +67,21 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.nvml = None
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
@@ -77,11 +92,47 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        masks = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            bit = getattr(nv, attr, None)
+            if bit is None:
+                bit = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if bit is not None:
+                masks.append((name, bit))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        try:
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            smax = None
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                if smax is not None:
+                    self.smax.append(smax)
+                if get_reasons is not None:
+                    r = get_reasons(self.handle)
+                    for name, bit in masks:
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return self._summary(self.sm, self.smax, self.reasons, "nvml")
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,12 +154,16 @@ class ClockSampler:
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+        return self._summary(sm, smax, reasons, "nvidia-smi")
+
+    @staticmethod
+    def _summary(sm, smax, reasons, source):
         # "under load": the upper half of the samples (idle gaps between steps drop the clock)
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": float(np.median(load)) if load else None,
                 "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": source}
 
 
 def algorithmic_work(stats, n=1, n_parms=3, n_lags=1, n_lag_idx=1, nt=11, order=8):
