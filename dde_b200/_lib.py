@@ -68,6 +68,8 @@ SYMBOLS = [
     ("dde_dopri_batch_sync", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dde_dopri_batch_download_range", C.c_int, [C.c_void_p, _SZ, _SZ, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dde_dopri_batch_run_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dde_dopri_batch_n_history", C.c_uint64, [C.c_void_p]),

@@ -112,6 +112,21 @@ class DopriBatch:
         self._check(self._lib.dde_dopri_batch_download(self._h, _ptr(y_out), _ptr(out), _ptr(stats),
                                                        _ptr(code), _ptr(t_last), _ptr(step_size)))
 
+    def download_range(self, first, count, want_y=True):
+        """Results of trajectories first .. first + count - 1 only."""
+        first, count = int(first), int(count)
+        y_out = np.empty((count, self.nt, self.n)) if want_y else None
+        out = np.empty((count, self.nt, self.n_out)) if (self.n_out > 0 and want_y) else None
+        stats = np.empty((count, 4), dtype=np.int32)
+        code = np.empty((count,), dtype=np.int32)
+        t_last = np.empty((count,))
+        step_size = np.empty((count,))
+        self._check(self._lib.dde_dopri_batch_download_range(
+            self._h, first, count, _ptr(y_out), _ptr(out), _ptr(stats), _ptr(code), _ptr(t_last),
+            _ptr(step_size)))
+        return DopriBatchResult(y_out, out, stats, code, t_last, step_size, self.times,
+                                self.n_history)
+
     def run_download_into(self, y_out=None, out=None, stats=None, code=None, t_last=None,
                           step_size=None):
         """run() and download_into() in one blocking call, overlapped: results are copied

@@ -1025,6 +1025,39 @@ int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out, i
   return 0;
 }
 
+/* Results of trajectories first .. first + count - 1 only (host arrays sized for
+ * `count` trajectories).  Synchronises. */
+int dde_dopri_batch_download_range(dde_dopri_batch_t *b, size_t first, size_t count,
+                                   double *y_out, double *out, int32_t *stats, int32_t *code,
+                                   double *t_last, double *step_size) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle");
+  }
+  if (first > b->n_traj || count > b->n_traj - first) {
+    return fail("trajectory range %zu + %zu exceeds the batch (%zu)", first, count, b->n_traj);
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  cudaError_t err = cudaSuccess;
+  auto d2h = [&](void *dst, const void *src, size_t elem_bytes) {
+    if (dst != nullptr && src != nullptr && err == cudaSuccess && count > 0) {
+      err = cudaMemcpyAsync(dst, (const char *) src + first * elem_bytes, count * elem_bytes,
+                            cudaMemcpyDeviceToHost, b->stream);
+    }
+  };
+  d2h(y_out, b->d_y_out, sizeof(double) * b->n * b->nt);
+  d2h(b->n_out > 0 ? out : nullptr, b->d_out, sizeof(double) * b->n_out * b->nt);
+  d2h(stats, b->d_stats, sizeof(int) * 4);
+  d2h(code, b->d_code, sizeof(int));
+  d2h(t_last, b->d_t_last, sizeof(double));
+  d2h(step_size, b->d_step_size, sizeof(double));
+  DDE_CUDA(err);
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
 double dde_dopri_batch_last_ms(dde_dopri_batch_t *b) {
   if (b == nullptr || !b->ran) {
     return -1.0;

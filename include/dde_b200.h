@@ -195,6 +195,11 @@ int dde_dopri_batch_sync(dde_dopri_batch_t *b);
 int dde_dopri_batch_download(dde_dopri_batch_t *b, double *y_out, double *out,
                              int32_t *stats, int32_t *code, double *t_last,
                              double *step_size);
+/* The same for trajectories first .. first + count - 1 only; the host arrays
+ * hold `count` trajectories. */
+int dde_dopri_batch_download_range(dde_dopri_batch_t *b, size_t first, size_t count,
+                                   double *y_out, double *out, int32_t *stats,
+                                   int32_t *code, double *t_last, double *step_size);
 /* dde_dopri_batch_run + dde_dopri_batch_download in one blocking call, the
  * two overlapped: trajectories are integrated in index order, so the results
  * of each block of 32768 are copied to the host (on a second stream) as soon
