@@ -279,8 +279,6 @@ def dopri(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, step_siz
     times_arr = _f64(times, "times").ravel()
     if times_arr.shape[0] < 2:
         raise DdeError("At least two times must be given")
-    if n_out == 0 and False:
-        pass
     lib = _lib.load()
     ctl = _control(method, rtol, atol, step_size_min, step_size_max, step_size_initial, step_max_n,
                    step_size_min_allow, stiff_check, n_history, grow_history, return_initial)

@@ -1,3 +1,5 @@
+"""Debug: run 128 Mackey-Glass trajectories under the tracing build (variants/libdde_trace.so,
+DDE_NVCC_EXTRA="-DDDE_LAG_STATS -DDDE_LAG_TRACE_PRINT"), which prints one line per lag-window miss."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 os.environ["DDE_B200_LIB"] = os.path.abspath("variants/libdde_trace.so")
