@@ -63,6 +63,12 @@ struct CoopCtx {
   /* start time (sign-adjusted) and step of every ring slot, in shared memory
      when the ring is short enough: a look-up is then a block-wide scan */
   double *tab_t, *tab_h;
+  /* the entries the last few look-ups ended at (logical indices): a step's
+     evaluations query each lag within an entry or two, so most look-ups are
+     answered by testing these, identically in every thread, without a scan */
+  unsigned hint[4];
+  int hint_slot[4]; /* their ring slots (no division on the fast path) */
+  unsigned hint_next;
   /* cached bracket: entry c_idx covers [c_ts, c_tn) in sign-adjusted time */
   unsigned c_idx;
   int c_valid;
@@ -104,6 +110,21 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
     const unsigned cap = (unsigned) s_cc.cap;
     const unsigned used = count < cap ? count : cap;
     const unsigned tail = count - used;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned j = s_cc.hint[q];
+      if (j >= tail && j < count) {
+        const int slot = s_cc.hint_slot[q];
+        const int next = slot + 1 == (int) cap ? 0 : slot + 1;
+        const double tj = s_cc.tab_t[slot];
+        if (tj <= st && (j + 1 == count || !(s_cc.tab_t[next] <= st))) {
+          *idx = j;
+          *t_old = s_cc.sign * tj;
+          *h = s_cc.tab_h[slot];
+          return true; /* the same answer in every thread: no barrier needed */
+        }
+      }
+    }
     if (threadIdx.x == 0) {
       s_cc.b_ok = 0;
     }
@@ -120,13 +141,20 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
     }
     __syncthreads();
     const bool found = s_cc.b_ok != 0;
-    if (!found && threadIdx.x == 0) {
-      s_cc.error = 1;
-      s_cc.code = -6; /* ERR_YLAG_FAIL */
-    }
     *idx = s_cc.b_idx;
     *t_old = s_cc.b_told;
     *h = s_cc.b_h;
+    if (threadIdx.x == 0) { /* (everybody read the hints before the first barrier) */
+      if (found) {
+        s_cc.hint[s_cc.hint_next & 3u] = s_cc.b_idx;
+        s_cc.hint_slot[s_cc.hint_next & 3u] = (int) (s_cc.b_idx % cap);
+        s_cc.hint_next++;
+      } else {
+        s_cc.error = 1;
+        s_cc.code = -6; /* ERR_YLAG_FAIL */
+      }
+    }
+    __syncthreads();
     return found;
   }
   if (threadIdx.x == 0) {
@@ -465,6 +493,10 @@ __global__ void __launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 
       s_cc.error = 0;
       s_cc.code = 0;
       s_cc.c_valid = 0;
+      for (int q = 0; q < 4; ++q) {
+        s_cc.hint[q] = 0xffffffffu;
+      }
+      s_cc.hint_next = 0;
       /* the table of step times follows the model's scratch area */
       double *tab = (double *) ((char *) (s_coop_dyn + DDE_COOP_NVEC * (size_t) n) +
                                 DDE_COOP_SCRATCH_BYTES);
