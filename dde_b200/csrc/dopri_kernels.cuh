@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
   double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
   bool stop = false, last = false, reject = false;
   int times_idx = 1, tcrit_idx = 0;
-  double t_out = 0.0; /* times[times_idx], read once per output row, not once per step */
+  /* times[times_idx]: read once per output row, not once per step, and requested
+     before the previous row's interpolation so that a dense output grid does not
+     wait for it */
+  double t_out = 0.0;
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
 
@@ -717,6 +720,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
           if (!(last || sign * tq <= sign * t)) {
             break;
           }
+          const double t_next = times_idx + 1 < n_times ? a.times[times_idx + 1] : 0.0;
           const double theta = (tq - t_old) / h;
           const double theta1 = 1 - theta;
           double row[NMAX];
@@ -742,9 +746,7 @@ __global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N >
             }
           }
           ++times_idx;
-          if (times_idx < n_times) {
-            t_out = a.times[times_idx];
-          }
+          t_out = t_next;
         }
 
         /* ring_buffer_head_advance, src/dopri.c:460: the head entry goes to

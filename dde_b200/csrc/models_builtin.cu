@@ -26,12 +26,15 @@ DDE_EVENT_TABLE(growth_events, identity, double_variables, halve_variables, doub
 DDE_REGISTER_DOPRI_EVENTS(exponential,    exponential,    0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
 DDE_REGISTER_DOPRI_EVENTS(linear,         linear,         0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
 DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
+DDE_REGISTER_DOPRI(       delayed_growth_vec, delayed_growth_vec, 0, -1)
 
 /*                  name       target     n  n_parms n_out */
 DDE_REGISTER_DIFEQ(logistic,  logistic,  0, -1,     0)
 DDE_REGISTER_DIFEQ(additive,  additive,  0, -1,     -1)
 DDE_REGISTER_DIFEQ(fibonacci, fibonacci, 5, -1,     0)
 DDE_REGISTER_DIFEQ(fib_out,   fib_out,   1, -1,     1)
+DDE_REGISTER_DIFEQ(fib_all,   fib_all,   0, -1,     0)
+DDE_REGISTER_DIFEQ(fib_vec,   fib_vec,   0, -1,     0)
 DDE_REGISTER_DIFEQ(sir_delay, sir_delay, 3, 2,      0)
 
 #ifdef DDE_LAG_STATS

@@ -10,6 +10,9 @@
  *   fib_out    -- as fibonacci, n = 1 via yprev_1, with n_out = 1 output = the
  *                 lagged value (exercises the output-row pairing,
  *                 src/difeq.c:204-213,249-255)
+ *   fib_all    -- y' = y + y(step - 1) through yprev_all, n <= 16
+ *   fib_vec    -- y'_i = y_i + y_{n-1-i}(step - 1) through yprev_vec (size_t
+ *                 indices), n <= 16
  *   sir_delay  -- delayed SIR map, n = 3, parms = (beta, gamma), lag 14 steps
  *                 (BASELINE.json configs[3])
  */
@@ -53,6 +56,30 @@ DDE_MODEL_FN void fib_out(size_t n, size_t step, const double *y,
   const double prev = yprev_1((int) step - 1, 0);
   y_next[0] = y[0] + prev;
   output[0] = prev;
+}
+
+DDE_MODEL_FN void fib_all(size_t n, size_t step, const double *y,
+                          double *y_next, size_t n_out, double *output,
+                          const void *data) {
+  double prev[16];
+  yprev_all((int) step - 1, prev);
+  for (size_t i = 0; i < n; ++i) {
+    y_next[i] = y[i] + prev[i];
+  }
+}
+
+DDE_MODEL_FN void fib_vec(size_t n, size_t step, const double *y,
+                          double *y_next, size_t n_out, double *output,
+                          const void *data) {
+  size_t idx[16];
+  double prev[16];
+  for (size_t i = 0; i < n; ++i) {
+    idx[i] = n - 1 - i;
+  }
+  yprev_vec((int) step - 1, idx, n, prev);
+  for (size_t i = 0; i < n; ++i) {
+    y_next[i] = y[i] + prev[i];
+  }
 }
 
 DDE_MODEL_FN void sir_delay(size_t n, size_t step, const double *y,

@@ -30,6 +30,22 @@ DDE_MODEL_FN void delayed_growth(size_t n, double t, const double *y,
   }
 }
 
+/* as delayed_growth, each equation driven by the lagged value of its mirror
+   image, fetched with ylag_vec (size_t indices, src/dopri.c:802-814); n <= 16 */
+DDE_MODEL_FN void delayed_growth_vec(size_t n, double t, const double *y,
+                                     double *dydt, const void *data) {
+  const double *r = (const double *) data;
+  size_t idx[16];
+  double lagged[16];
+  for (size_t i = 0; i < n; ++i) {
+    idx[i] = n - 1 - i;
+  }
+  ylag_vec(t - 1.0, idx, n, lagged);
+  for (size_t i = 0; i < n; ++i) {
+    dydt[i] = r[i] * lagged[i];
+  }
+}
+
 /* The reference's event fixtures (/root/reference/tests/testthat/growth.c:20-49):
  * applied to the state -- or to the parameters -- at critical times. */
 DDE_MODEL_FN void identity(size_t n, double t, double *y, void *data) {

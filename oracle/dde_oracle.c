@@ -193,6 +193,7 @@ static const model_entry MODELS[] = {
     {"exponential", exponential, NULL, NULL, growth_event_table, 5},
     {"linear", linear, NULL, NULL, growth_event_table, 5},
     {"delayed_growth", delayed_growth, NULL, NULL},
+    {"delayed_growth_vec", delayed_growth_vec, NULL, NULL},
     {"exponential_wide", exponential_wide, NULL, NULL},
     {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
     {"seir_age", seir_age, NULL, NULL},
@@ -200,6 +201,8 @@ static const model_entry MODELS[] = {
     {"additive", NULL, NULL, additive},
     {"fibonacci", NULL, NULL, fibonacci},
     {"fib_out", NULL, NULL, fib_out},
+    {"fib_all", NULL, NULL, fib_all},
+    {"fib_vec", NULL, NULL, fib_vec},
     {"sir_delay", NULL, NULL, sir_delay},
 };
 

@@ -155,6 +155,35 @@ def test_oracle_matches_reference_on_fresh_inputs():
     a = pyoracle.difeq_batch("oracle", model, y0, steps, parms, **kw)
     b = pyoracle.difeq_batch("ref", model, y0, steps, parms, **kw)
     assert_bits_equal(a.y, b.y, "y")
+    # the lag functions no workload uses: ylag_vec, yprev_all, yprev_vec (size_t indices)
+    y0 = rng.uniform(0.5, 2.0, (5, 4))
+    r = rng.uniform(0.1, 1.0, (5, 4))
+    a = pyoracle.dopri_batch("oracle", "delayed_growth_vec", y0, np.linspace(0, 3, 13), r,
+                             n_history=200)
+    b = pyoracle.dopri_batch("ref", "delayed_growth_vec", y0, np.linspace(0, 3, 13), r,
+                             n_history=200)
+    np.testing.assert_array_equal(a.statistics, b.statistics)
+    assert_bits_equal(a.y, b.y, "y")
+    for model in ("fib_all", "fib_vec"):
+        a = pyoracle.difeq_batch("oracle", model, y0, np.arange(0, 30), None, n_history=3)
+        b = pyoracle.difeq_batch("ref", model, y0, np.arange(0, 30), None, n_history=3)
+        assert_bits_equal(a.y, b.y, model)
+    # grow_history == a large history (tests/testthat/test-ode.R:627-640, test-difeq.R:410-428)
+    model, y0, parms, times, kw = workloads.mackey_glass(4, first=40)
+    for backend in ("oracle", "ref"):
+        g = pyoracle.dopri_history(backend, model, y0[:1], times, parms[:1], grow_history=True,
+                                   max_entries=2000, **dict(kw, n_history=10))
+        big = pyoracle.dopri_history(backend, model, y0[:1], times, parms[:1], max_entries=2000,
+                                     **dict(kw, n_history=2000))
+        assert g.n_entries == big.n_entries == g.statistics[2]
+        assert_bits_equal(g.history, big.history, "grown history")
+        assert_bits_equal(g.y, big.y, "y")
+    a = pyoracle.difeq_history("oracle", "fib_vec", [[1.0, 2.0, 3.0]], np.arange(0, 25), None,
+                               n_history=4, grow_history=True, max_entries=64)
+    b = pyoracle.difeq_history("ref", "fib_vec", [[1.0, 2.0, 3.0]], np.arange(0, 25), None,
+                               n_history=4, grow_history=True, max_entries=64)
+    assert a.n_entries == b.n_entries == 25
+    assert_bits_equal(a.history, b.history, "difeq history")
 
 
 @needs_ref

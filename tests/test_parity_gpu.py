@@ -99,6 +99,9 @@ def test_growth_models_runtime_n(backend, method):
         check_dopri(backend, "linear", y0, np.linspace(0, 3, 13), r, method=method)
         check_dopri(backend, "delayed_growth", y0, np.linspace(0, 3, 13), r, method=method,
                     n_history=200)
+        # the same through ylag_vec (size_t indices), mirrored components
+        check_dopri(backend, "delayed_growth_vec", y0, np.linspace(0, 3, 13), r, method=method,
+                    n_history=200)
 
 
 def test_negative_time(backend):
@@ -242,6 +245,18 @@ def test_difeq_fibonacci(backend):
     y, out, _ = check_difeq(backend, "fib_out", [[1.0]], np.arange(11), None, n_out=1, n_history=2)
     assert y[0, :, 0].tolist() == [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144]
     assert out[0, :, 0].tolist() == [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89]
+
+
+@pytest.mark.parametrize("model", ["fib_all", "fib_vec"])
+@pytest.mark.parametrize("n_history", [2, 3, 40, 400])
+def test_difeq_yprev_all_and_vec(backend, model, n_history):
+    """yprev_all and yprev_vec (size_t indices): on-chip history, and (400 entries) the ring
+    in HBM"""
+    rng = np.random.default_rng(5)
+    for n in (1, 4, 7):
+        y0 = np.floor(rng.uniform(1, 9, (6, n)))
+        y, _, code = check_difeq(backend, model, y0, np.arange(0, 40), None, n_history=n_history)
+        assert (code == 1).all()
 
 
 def test_difeq_history_miss(backend):
