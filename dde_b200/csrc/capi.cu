@@ -114,6 +114,30 @@ __global__ void max_uint_kernel(const unsigned *x, long long n, unsigned *out) {
   }
 }
 
+/* grow_history on a restart: lay the surviving entries of every trajectory's ring out
+ * again in a ring of larger capacity (logical entry idx lives in slot idx % capacity) */
+__global__ void ring_regrow_kernel(const double *old_ring, double *new_ring,
+                                   const unsigned *count, long long n_traj, unsigned old_cap,
+                                   unsigned new_cap, int hl) {
+  const long long gid = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if (gid >= n_traj * old_cap) {
+    return;
+  }
+  const long long traj = gid / old_cap;
+  const unsigned e = (unsigned) (gid % old_cap);
+  const unsigned c = count[traj];
+  const unsigned used = c < old_cap ? c : old_cap;
+  if (e >= used) {
+    return;
+  }
+  const unsigned idx = c - used + e;
+  const double *src = old_ring + ((size_t) traj * old_cap + idx % old_cap) * (size_t) hl;
+  double *dst = new_ring + ((size_t) traj * new_cap + idx % new_cap) * (size_t) hl;
+  for (int i = 0; i < hl; ++i) {
+    dst[i] = src[i];
+  }
+}
+
 __global__ void fill_int_kernel(int *x, long long n, int value) {
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if (i < n) {
@@ -882,10 +906,6 @@ int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double
   if (!b->ran) {
     return fail("nothing has been run on this handle: there is nothing to continue");
   }
-  if (b->ctl.grow_history) {
-    return fail("a batch with grow_history cannot be continued (a run that outgrows its rings "
-                "is repeated from its start): pre-size n_history instead");
-  }
   if (times == nullptr || n_times < 2) {
     return fail("At least two times must be given"); /* src/r_dopri.c:211-213 */
   }
@@ -893,18 +913,117 @@ int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double
     return fail("Incorrect sign for the times"); /* src/r_dopri.c:218-220 */
   }
   DDE_CUDA(cudaSetDevice(b->device));
-  if (y != nullptr) { /* a new state: it is also the pre-history from now on, src/dopri.c:157 */
-    DDE_CUDA(cudaMemcpyAsync(b->d_y0, y, sizeof(double) * b->n * b->n_traj,
-                             cudaMemcpyHostToDevice, b->stream));
-  } else {
-    DDE_CUDA(cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * b->n * b->n_traj,
-                             cudaMemcpyDeviceToDevice, b->stream));
+  const size_t nt = b->n_traj, n = b->n;
+  const size_t hl = (size_t) b->order * n + 2;
+  const bool grow = b->ctl.grow_history && b->ctl.n_history > 0 && b->reset_code == 0;
+  /* grow_history: the continuation overwrites what it starts from, so keep a copy
+     to start again from if a ring wraps (blocking, like a growing first run) */
+  double *kept_ring = nullptr, *kept_t_last = nullptr, *kept_step = nullptr, *kept_y_final = nullptr;
+  int *kept_code = nullptr;
+  unsigned *kept_count = nullptr;
+  const size_t snap_cap = (size_t) b->ctl.n_history;
+  auto release = [&]() {
+    free_dev(kept_ring);
+    free_dev(kept_t_last);
+    free_dev(kept_step);
+    free_dev(kept_y_final);
+    free_dev(kept_code);
+    free_dev(kept_count);
+  };
+  if (grow) {
+    DDE_CUDA(cudaStreamSynchronize(b->stream));
+    bool ok = cudaMalloc(&kept_ring, sizeof(double) * hl * snap_cap * nt) == cudaSuccess &&
+              cudaMalloc(&kept_t_last, sizeof(double) * nt) == cudaSuccess &&
+              cudaMalloc(&kept_step, sizeof(double) * nt) == cudaSuccess &&
+              cudaMalloc(&kept_y_final, sizeof(double) * n * nt) == cudaSuccess &&
+              cudaMalloc(&kept_code, sizeof(int) * nt) == cudaSuccess &&
+              cudaMalloc(&kept_count, sizeof(unsigned) * nt) == cudaSuccess;
+    ok = ok && cudaMemcpy(kept_ring, b->d_ring, sizeof(double) * hl * snap_cap * nt,
+                          cudaMemcpyDeviceToDevice) == cudaSuccess &&
+         cudaMemcpy(kept_t_last, b->d_t_last, sizeof(double) * nt, cudaMemcpyDeviceToDevice) ==
+             cudaSuccess &&
+         cudaMemcpy(kept_step, b->d_step_size, sizeof(double) * nt, cudaMemcpyDeviceToDevice) ==
+             cudaSuccess &&
+         cudaMemcpy(kept_y_final, b->d_y_final, sizeof(double) * n * nt, cudaMemcpyDeviceToDevice) ==
+             cudaSuccess &&
+         cudaMemcpy(kept_code, b->d_code, sizeof(int) * nt, cudaMemcpyDeviceToDevice) == cudaSuccess &&
+         cudaMemcpy(kept_count, b->d_ring_count, sizeof(unsigned) * nt, cudaMemcpyDeviceToDevice) ==
+             cudaSuccess;
+    if (!ok) {
+      (void) cudaGetLastError();
+      release();
+      return fail("grow_history: cannot allocate the restart copy of the history rings "
+                  "(%.2f GB)", (double) (sizeof(double) * hl * snap_cap * nt) / 1e9);
+    }
   }
-  const int rc = dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
-  if (rc != 0) {
-    return rc;
+  for (;;) {
+    if (y != nullptr) { /* a new state: it is also the pre-history from now on, src/dopri.c:157 */
+      DDE_CUDA(cudaMemcpyAsync(b->d_y0, y, sizeof(double) * n * nt, cudaMemcpyHostToDevice,
+                               b->stream));
+    } else {
+      DDE_CUDA(cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * n * nt,
+                               cudaMemcpyDeviceToDevice, b->stream));
+    }
+    int rc = dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
+    rc = rc ? rc : dopri_run_impl(b, 1);
+    if (rc != 0 || !grow) {
+      release();
+      return rc;
+    }
+    const size_t cap = (size_t) b->ctl.n_history;
+    unsigned *d_max = reinterpret_cast<unsigned *>(b->d_next);
+    unsigned most = 0;
+    cudaError_t err = cudaMemsetAsync(d_max, 0, sizeof(unsigned), b->stream);
+    const int threads = 256;
+    max_uint_kernel<<<(unsigned) (((long long) nt + threads - 1) / threads), threads, 0,
+                      b->stream>>>(b->d_ring_count, (long long) nt, d_max);
+    err = err != cudaSuccess ? err : cudaGetLastError();
+    err = err != cudaSuccess ? err
+                             : cudaMemcpyAsync(&most, d_max, sizeof most, cudaMemcpyDeviceToHost,
+                                               b->stream);
+    err = err != cudaSuccess ? err : cudaStreamSynchronize(b->stream);
+    if (err != cudaSuccess) {
+      release();
+      return fail("CUDA error: %s", cudaGetErrorString(err));
+    }
+    if ((size_t) most <= cap) {
+      release();
+      return 0;
+    }
+    /* a ring wrapped: back to the state before the continuation, in larger rings */
+    const size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
+    free_dev(b->d_ring);
+    if (cudaMalloc(&b->d_ring, sizeof(double) * hl * bigger * nt) != cudaSuccess) {
+      (void) cudaGetLastError();
+      b->d_ring = nullptr;
+      b->ran = false;
+      release();
+      return fail("grow_history: cannot allocate %.2f GB of history rings (%zu entries per "
+                  "trajectory)", (double) (sizeof(double) * hl * bigger * nt) / 1e9, bigger);
+    }
+    const long long cells = (long long) nt * (long long) snap_cap;
+    ring_regrow_kernel<<<(unsigned) ((cells + threads - 1) / threads), threads, 0, b->stream>>>(
+        kept_ring, b->d_ring, kept_count, (long long) nt, (unsigned) snap_cap, (unsigned) bigger,
+        (int) hl);
+    err = cudaGetLastError();
+    err = err != cudaSuccess ? err : cudaMemcpyAsync(b->d_t_last, kept_t_last, sizeof(double) * nt,
+                                                     cudaMemcpyDeviceToDevice, b->stream);
+    err = err != cudaSuccess ? err : cudaMemcpyAsync(b->d_step_size, kept_step, sizeof(double) * nt,
+                                                     cudaMemcpyDeviceToDevice, b->stream);
+    err = err != cudaSuccess ? err : cudaMemcpyAsync(b->d_y_final, kept_y_final,
+                                                     sizeof(double) * n * nt,
+                                                     cudaMemcpyDeviceToDevice, b->stream);
+    err = err != cudaSuccess ? err : cudaMemcpyAsync(b->d_code, kept_code, sizeof(int) * nt,
+                                                     cudaMemcpyDeviceToDevice, b->stream);
+    err = err != cudaSuccess ? err : cudaMemcpyAsync(b->d_ring_count, kept_count,
+                                                     sizeof(unsigned) * nt,
+                                                     cudaMemcpyDeviceToDevice, b->stream);
+    if (err != cudaSuccess) {
+      release();
+      return fail("CUDA error: %s", cudaGetErrorString(err));
+    }
+    b->ctl.n_history = bigger;
   }
-  return dopri_run_impl(b, 1);
 }
 
 /* dopri_data_copy, src/dopri.c:92-134: an independent handle with the same

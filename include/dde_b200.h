@@ -182,7 +182,10 @@ int dde_dopri_batch_run(dde_dopri_batch_t *b);
  * y == NULL keeps the final states; a new y [n x n_traj] also becomes the
  * pre-history (src/dopri.c:157).  A trajectory that did not complete, or
  * stopped at another time, gets DDE_ERR_RESTART and keeps its state.
- * Asynchronous like dde_dopri_batch_run; results through _download. */
+ * Asynchronous like dde_dopri_batch_run; results through _download.  With
+ * ctl.grow_history the call blocks: it keeps a copy of the state it starts
+ * from and, if a ring wraps, repeats the continuation from that copy in
+ * larger rings. */
 int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y,
                              const double *times, size_t n_times,
                              const double *tcrit, size_t n_tcrit);

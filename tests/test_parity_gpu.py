@@ -673,8 +673,32 @@ def test_grow_history_dopri(backend):
         assert h.shape[0] == ref.n_entries == want.statistics[j, 2]
         assert_bits_equal(h, ref.history, "history %d" % j)
     assert b.n_history >= want.statistics[:, 2].max()
-    with pytest.raises(dde_b200.DdeError, match="grow_history"):
-        b.continue_(np.linspace(500, 600, 3))
+    b.close()
+    # restart with a growing ring (dopri_continue on a grow_history object): the rings are
+    # outgrown during the continuation, which is then repeated from a copy of its start
+    t1, t2 = np.linspace(0, 100, 3), np.linspace(100, 500, 5)
+    b = dde_b200.DopriBatch(model, 1, 48, n_parms=3, grow_history=True, **kw)
+    b.upload(y0, parms)
+    b.set_times(t1)
+    b.run()
+    cap1 = int(b._lib.dde_dopri_batch_n_history(b._h))
+    b.continue_(t2)
+    got2 = b.download()
+    assert int(b._lib.dde_dopri_batch_n_history(b._h)) > cap1
+    want2 = pyoracle.dopri_continue(backend, model, y0, t1, t2, parms, grow_history=True, **kw)
+    np.testing.assert_array_equal(got2.code, want2.code)
+    np.testing.assert_array_equal(got2.statistics, want2.statistics)
+    assert_bits_equal(got2.y, want2.y, "continued y")
+    # ... and equals the continuation of a run whose ring was large from the start
+    big = dde_b200.DopriBatch(model, 1, 48, n_parms=3, **dict(kw, n_history=2000))
+    big.upload(y0, parms)
+    big.set_times(t1)
+    big.run()
+    big.continue_(t2)
+    assert_bits_equal(got2.y, big.download().y, "grown vs large")
+    for j in (3, 40):
+        assert_bits_equal(b.history(j), big.history(j), "history %d" % j)
+    big.close()
     b.close()
     # the single-trajectory interface, history attribute included
     one = dde_b200.dopri(y0[5], times, model, parms[5], grow_history=True, return_history=True,
