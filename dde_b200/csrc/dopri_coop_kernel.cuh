@@ -420,7 +420,9 @@ __device__ __forceinline__ void coop_seqsum(int n, const double *red, double *re
 }
 
 template <class M, int METHOD, int TPT, int CMAX>
-__global__ void __launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 128 ? 4 : 8))) dopri_coop_kernel(const DopriArgs a) {
+__global__ void
+__launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 128 ? 4 : 8)))
+dopri_coop_kernel(const DopriArgs a) {
   constexpr int ORDER = METHOD == 0 ? 5 : 8;
   const int n = a.n;
   const int hl = ORDER * n + 2;

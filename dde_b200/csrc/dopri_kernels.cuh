@@ -88,7 +88,10 @@ __device__ __forceinline__ RingStart ring_start(const DopriArgs &a, long long tr
 }
 
 template <class M, int METHOD>
-__global__ void __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS : (M::N > 1 && M::N <= 4 ? DDE_MIN_BLOCKS_SMALL : 1))) dopri_tpt_kernel(const DopriArgs a) {
+__global__ void
+__launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS
+                                      : (M::N > 1 && M::N <= 4 ? DDE_MIN_BLOCKS_SMALL : 1)))
+dopri_tpt_kernel(const DopriArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);

@@ -150,7 +150,8 @@ __shared__ int s_dctx32[DDE_DI_COUNT32][DDE_TPB];
  * step attempt (lag_window_ensure), while all lanes of a warp are in step,
  * so that it covers [sign t + dq_lo, sign (t + h) + dq_hi], where dq_lo and
  * dq_hi bound the offsets (query time - evaluation time) seen so far (learnt
- * from misses; for a constant lag tau both are -tau after the first miss).  Newly committed entries are appended straight from registers when
+ * from misses; for a constant lag tau both are -tau after the first miss).
+ * Newly committed entries are appended straight from registers when
  * the window sits at the head of the ring.  A query outside the window takes
  * the slow path (lag_window_miss): the entry is found by bisection over the
  * step times stored in the ring, starting next to the window (the search
@@ -508,7 +509,9 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
   }
 #undef DDE_TIME
   s_hint[s] = lo;
-  DDE_LAG_TRACE("miss thr %d st %.6f tt %.6f att [%.6f %.6f] dq [%.3f %.3f] base %u wn %u wt0 %.6f wtop %.6f -> idx %u\n", s, st, s_tt[s], s_att_lo[s], s_att_hi[s], s_dq_lo[s], s_dq_hi[s], base, wn,
+  DDE_LAG_TRACE("miss thr %d st %.6f tt %.6f att [%.6f %.6f] dq [%.3f %.3f] base %u wn %u "
+                "wt0 %.6f wtop %.6f -> idx %u\n",
+                s, st, s_tt[s], s_att_lo[s], s_att_hi[s], s_dq_lo[s], s_dq_hi[s], base, wn,
                 s_wt[base % DDE_WIN][s], s_wtop[s], lo);
   *from_ring = false;
   if (wn == 0) {
