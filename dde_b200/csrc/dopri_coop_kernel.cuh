@@ -62,7 +62,8 @@ struct CoopCtx {
   int error, code;         /* obj->error, obj->code */
   /* start time (sign-adjusted) and step of every ring slot, in shared memory
      when the ring is short enough: a look-up is then a block-wide scan */
-  double *tab_t, *tab_h;
+  int tab_off; /* offset of the table in s_coop_dyn (doubles), -1: no table.  An offset, not a
+                  pointer, so that the accesses compile to shared-memory loads */
   /* the entries the last few look-ups ended at (logical indices): a step's
      evaluations query each lag within an entry or two, so most look-ups are
      answered by testing these, identically in every thread, without a scan */
@@ -83,6 +84,8 @@ struct CoopCtx {
 
 __shared__ CoopCtx s_cc;
 extern __shared__ double s_coop_dyn[]; /* 16 solver vectors of n doubles, then model scratch */
+#define DDE_COOP_TAB_T (s_coop_dyn + s_cc.tab_off)
+#define DDE_COOP_TAB_H (s_coop_dyn + s_cc.tab_off + s_cc.cap)
 
 __device__ __forceinline__ double coop_na_real() {
   return __longlong_as_double(0x7FF00000000007A2LL);
@@ -95,14 +98,16 @@ __device__ __forceinline__ double coop_inf() {
 __device__ __forceinline__ const double *coop_entry(unsigned idx) {
   int slot = s_cc.head - (int) (s_cc.count - idx);
   slot = slot < 0 ? slot + s_cc.cap : slot;
-  return s_cc.ring + (size_t) slot * (size_t) s_cc.hl;
+  const double *ring = s_cc.ring;
+  __builtin_assume(__isGlobal(ring)); /* global, not generic, loads */
+  return ring + (size_t) slot * (size_t) s_cc.hl;
 }
 
 /* Block-wide: the last committed entry whose time is <= t (>= t backwards),
  * src/dopri.c:742-769.  Thread 0 searches, everybody gets the answer.  On
  * failure ERR_YLAG_FAIL is recorded and false returned. */
 __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_old, double *h) {
-  if (s_cc.tab_t != nullptr) {
+  if (s_cc.tab_off >= 0) {
     /* every thread tests the entries it owns: the wanted one starts at or
        before t while its successor (if any) starts after t */
     const double st = s_cc.sign * t;
@@ -116,11 +121,11 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
       if (j >= tail && j < count) {
         const int slot = s_cc.hint_slot[q];
         const int next = slot + 1 == (int) cap ? 0 : slot + 1;
-        const double tj = s_cc.tab_t[slot];
-        if (tj <= st && (j + 1 == count || !(s_cc.tab_t[next] <= st))) {
+        const double tj = DDE_COOP_TAB_T[slot];
+        if (tj <= st && (j + 1 == count || !(DDE_COOP_TAB_T[next] <= st))) {
           *idx = j;
           *t_old = s_cc.sign * tj;
-          *h = s_cc.tab_h[slot];
+          *h = DDE_COOP_TAB_H[slot];
           return true; /* the same answer in every thread: no barrier needed */
         }
       }
@@ -131,12 +136,12 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
     __syncthreads();
     for (unsigned k = threadIdx.x; k < used; k += blockDim.x) {
       const unsigned j = tail + k; /* logical index; slot j % cap */
-      const double tj = s_cc.tab_t[j % cap];
-      if (tj <= st && (j + 1 == count || !(s_cc.tab_t[(j + 1) % cap] <= st))) {
+      const double tj = DDE_COOP_TAB_T[j % cap];
+      if (tj <= st && (j + 1 == count || !(DDE_COOP_TAB_T[(j + 1) % cap] <= st))) {
         s_cc.b_ok = 1;
         s_cc.b_idx = j;
         s_cc.b_told = s_cc.sign * tj;
-        s_cc.b_h = s_cc.tab_h[j % cap];
+        s_cc.b_h = DDE_COOP_TAB_H[j % cap];
       }
     }
     __syncthreads();
@@ -503,19 +508,18 @@ dopri_coop_kernel(const DopriArgs a) {
       double *tab = (double *) ((char *) (s_coop_dyn + DDE_COOP_NVEC * (size_t) n) +
                                 DDE_COOP_SCRATCH_BYTES);
       const bool have_tab = a.n_history > 0 && a.n_history <= DDE_COOP_MAX_TABLE;
-      s_cc.tab_t = have_tab ? tab : nullptr;
-      s_cc.tab_h = have_tab ? tab + a.n_history : nullptr;
+      s_cc.tab_off = have_tab ? (int) (tab - s_coop_dyn) : -1;
     }
     DDE_EACH(i) { Y[i] = y0[i]; }
     __syncthreads();
-    if (s_cc.tab_t != nullptr && s_cc.count > 0) { /* restart: the times of the surviving entries */
+    if (s_cc.tab_off >= 0 && s_cc.count > 0) { /* restart: the times of the surviving entries */
       const unsigned cap = (unsigned) a.n_history;
       const unsigned used = s_cc.count < cap ? s_cc.count : cap;
       for (unsigned k = tid; k < used; k += TPT) {
         const unsigned slot = (s_cc.count - used + k) % cap;
         const double *e = ring + (size_t) slot * (size_t) hl;
-        s_cc.tab_t[slot] = sign * e[hl - 2];
-        s_cc.tab_h[slot] = e[hl - 1];
+        DDE_COOP_TAB_T[slot] = sign * e[hl - 2];
+        DDE_COOP_TAB_H[slot] = e[hl - 1];
       }
       __syncthreads();
     }
@@ -852,9 +856,9 @@ dopri_coop_kernel(const DopriArgs a) {
       if (a.n_history > 0 && tid == 0) {
         dst[ORDER * n] = t_old;
         dst[ORDER * n + 1] = h;
-        if (s_cc.tab_t != nullptr) {
-          s_cc.tab_t[s_cc.head] = sign * t_old;
-          s_cc.tab_h[s_cc.head] = h;
+        if (s_cc.tab_off >= 0) {
+          DDE_COOP_TAB_T[s_cc.head] = sign * t_old;
+          DDE_COOP_TAB_H[s_cc.head] = h;
         }
         const unsigned newest = s_cc.count;
         s_cc.head = s_cc.head + 1 == a.n_history ? 0 : s_cc.head + 1;
