@@ -336,13 +336,68 @@ DDE_HD_NOINLINE double dde_pow_slow(double x, double y) {
   return dde_pow_main(ix, y, sign_bias);
 }
 
-DDE_HD double dde_pow(double x, double y) {
+/* The common path of dde_pow_main without a branch: the value when x is
+ * positive normal and the exponent of the final exp() is ordinary, something
+ * harmless (never a trap, never an out-of-range table index) otherwise;
+ * *exp_rare tells which. */
+DDE_HD double dde_pow_common(uint64_t ix, double y, int *exp_rare) {
+  double lo;
+  const double hi = dde_pow_log_inline(ix, &lo);
+  const double ehi = y * hi;
+  const double elo = DDE_FMA(y, lo, DDE_FMA(hi, y, -ehi));
+  const uint32_t abstop = dde_top12(ehi) & 0x7ff;
+  *exp_rare = abstop - 0x3c9u >= 0x3fu;
+  /* dde_exp_inline(ehi, elo, 0, 1), its common path */
+  double kd = DDE_FMA(ehi, DDE_EXP_INVLN2N, DDE_EXP_SHIFT);
+  const uint64_t ki = dde_asuint64(kd);
+  kd = kd - DDE_EXP_SHIFT;
+  double r = DDE_FMA(kd, DDE_EXP_NEGLN2HIN, ehi);
+  r = DDE_FMA(kd, DDE_EXP_NEGLN2LON, r);
+  r = elo + r;
+  const uint64_t top = ki << 45;
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 entry = __ldg(&dde_exp_tab_d[ki % 128]);
+  const double tail = dde_asdouble((uint64_t) entry.x);
+  const uint64_t sbits = (uint64_t) entry.y + top;
+#else
+  const uint64_t idx = 2 * (ki % 128);
+  const double tail = dde_asdouble(DDE_EXP_TAB(idx));
+  const uint64_t sbits = DDE_EXP_TAB(idx + 1) + top;
+#endif
+  const double r2 = r * r;
+  const double p23 = DDE_FMA(r, DDE_EXP_C3, DDE_EXP_C2);
+  const double p45 = DDE_FMA(r, DDE_EXP_C5, DDE_EXP_C4);
+  double tmp = DDE_FMA(p23, r2, r + tail);
+  tmp = DDE_FMA(r2 * r2, p45, tmp);
+  const double scale = dde_asdouble(sbits);
+  return DDE_FMA(scale, tmp, scale);
+}
+
+/* Everything dde_pow_common does not cover.  `common` is not used: taking it
+ * keeps the common path's arithmetic ahead of the (one) branch in dde_pow, so
+ * that path is a single basic block a scheduler can interleave with whatever
+ * else the caller has in flight. */
+DDE_HD_NOINLINE double dde_pow_rare(double x, double y, double common) {
+  (void) common;
   const uint32_t topx = dde_top12(x);
   const uint32_t topy = dde_top12(y);
   if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu) {
     return dde_pow_slow(x, y);
   }
   return dde_pow_main(dde_asuint64(x), y, 0);
+}
+
+DDE_HD double dde_pow(double x, double y) {
+  const uint32_t topx = dde_top12(x);
+  const uint32_t topy = dde_top12(y);
+  const int rare =
+      (topx - 0x001u >= 0x7ffu - 0x001u) | ((topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  int exp_rare;
+  const double common = dde_pow_common(dde_asuint64(x), y, &exp_rare);
+  if (rare | exp_rare) {
+    return dde_pow_rare(x, y, common);
+  }
+  return common;
 }
 
 #endif /* DDE_MATH_H */

@@ -59,6 +59,14 @@ namespace dde {
 #endif
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+/* the step-size controller's pow (once per attempt) is out of line, so that the hot
+   loop holds one copy of pow, the model's (measured: +1.2 %) */
+#ifndef DDE_CTRL_POW_INLINE
+static __device__ __noinline__ double dde_pow_ctrl(double x, double y) { return dde_pow(x, y); }
+#else
+#define dde_pow_ctrl dde_pow
+#endif
+
 /* Ring state a trajectory starts from: empty, or -- on a restart -- what the
  * previous run left, in which case t0 is the oldest surviving entry's time
  * (dopri_data_reset, src/dopri.c:185-191). */
@@ -607,9 +615,9 @@ dopri_tpt_kernel(const DopriArgs a) {
           err = sign * err * sqrt(1.0 / ((double) n * deno));
         }
         /* dopri_h_new, src/dopri.c:516-525 */
-        const double fac11 = dde_pow(err, step_constant);
+        const double fac11 = dde_pow_ctrl(err, step_constant);
         /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
-        const double facb = METHOD == 0 ? dde_pow(fac_old, step_beta) : 1.0;
+        const double facb = METHOD == 0 ? dde_pow_ctrl(fac_old, step_beta) : 1.0;
         double fac = fac11 / facb;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
         h_new = h / fac;

@@ -67,11 +67,8 @@ enum {
   DDE_F_RING = 0, /* double *: this trajectory's ring base */
   DDE_F_Y0,       /* const double *: pre-history state (src/dopri.c:777-778) */
   DDE_F_T0,       /* sign * start time (src/dopri.c:186) */
-  DDE_F_SIGN,     /* per-thread copy of the batch-uniform sign: the hot path reads
-                     it at base + offset like everything else */
   DDE_F_WTOP,     /* the staged lag window, see below */
   DDE_F_ATT_LO,
-  DDE_F_ATT_HI,
   DDE_F_TT,
   DDE_F_DQ_LO,
   DDE_F_DQ_HI,
@@ -87,7 +84,6 @@ enum {
   DDE_FI_ERROR,     /* obj->error */
   DDE_FI_WBASE,
   DDE_FI_WN,
-  DDE_FI_HINT,
   DDE_FI_CFG,       /* per-thread copy of n | order << 16 | staged << 24 */
   DDE_FI_COUNT32
 };
@@ -108,7 +104,6 @@ static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s
    to chase while other lanes of the warp wait) */
 #define s_y0_value (s_ctx64[::dde::DDE_F_Y0])
 #define s_t0 (s_ctx64[::dde::DDE_F_T0])
-#define s_sign (s_ctx64[::dde::DDE_F_SIGN])
 #define s_cfg (s_ctx32[::dde::DDE_FI_CFG])
 #define s_count ((unsigned *) s_ctx32[::dde::DDE_FI_COUNT])
 #define s_head (s_ctx32[::dde::DDE_FI_HEAD])
@@ -165,8 +160,6 @@ __shared__ int s_dctx32[DDE_DI_COUNT32][DDE_TPB];
 #define s_wbase ((unsigned *) s_ctx32[::dde::DDE_FI_WBASE])
 #define s_wn ((unsigned *) s_ctx32[::dde::DDE_FI_WN])
 #define s_att_lo (s_ctx64[::dde::DDE_F_ATT_LO]) /* sign * t of the attempt in progress */
-#define s_att_hi (s_ctx64[::dde::DDE_F_ATT_HI]) /* sign * (t + h) of the attempt in progress */
-#define s_hint ((unsigned *) s_ctx32[::dde::DDE_FI_HINT]) /* entry the last search ended at */
 #define s_tt (s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
 #define s_dq_lo (s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
 #define s_dq_hi (s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
@@ -219,7 +212,6 @@ __device__ __forceinline__ const double *ring_entry(int s, unsigned idx) {
 }
 
 __device__ __forceinline__ void lag_window_reset(int s) {
-  s_sign[s] = s_lag_u.sign;
   s_cfg[s] = s_lag_u.n | (s_lag_u.order << 16) | (s_lag_u.staged << 24);
 #pragma unroll
   for (int k = 0; k < DDE_WIN; ++k) {
@@ -228,9 +220,7 @@ __device__ __forceinline__ void lag_window_reset(int s) {
   s_wtop[s] = pos_inf();
   s_wbase[s] = 0;
   s_wn[s] = 0;
-  s_hint[s] = 0;
   s_att_lo[s] = 0.0;
-  s_att_hi[s] = 0.0;
   s_tt[s] = 0.0;
   s_dq_lo[s] = pos_inf();
   s_dq_hi[s] = -pos_inf();
@@ -299,7 +289,6 @@ __device__ __forceinline__ void lag_window_evict(int s, unsigned &base, unsigned
 template <int NCOEF_MAX, bool EXACT>
 __device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double att_hi) {
   s_att_lo[s] = att_lo;
-  s_att_hi[s] = att_hi;
   const double need_hi = att_hi + s_dq_hi[s];
   const double need_lo = att_lo + s_dq_lo[s];
   unsigned wn = s_wn[s];
@@ -474,9 +463,8 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
     lo_known = false;
     hi = lo; /* empty bracket: fails below */
   } else {
-    /* try next to where the last search ended: two independent loads */
-    unsigned g = s_hint[s];
-    g = g < lo ? lo : (g >= hi ? hi - 1 : g);
+    /* try next to the window: two independent loads */
+    const unsigned g = above ? lo : hi - 1;
     const double tg = DDE_TIME(g);
     const double tg1 = g + 1 < hi ? DDE_TIME(g + 1) : pos_inf();
     if (tg <= st) {
@@ -508,10 +496,9 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
     }
   }
 #undef DDE_TIME
-  s_hint[s] = lo;
   DDE_LAG_TRACE("miss thr %d st %.6f tt %.6f att [%.6f %.6f] dq [%.3f %.3f] base %u wn %u "
                 "wt0 %.6f wtop %.6f -> idx %u\n",
-                s, st, s_tt[s], s_att_lo[s], s_att_hi[s], s_dq_lo[s], s_dq_hi[s], base, wn,
+                s, st, s_tt[s], s_att_lo[s], s_att_lo[s], s_dq_lo[s], s_dq_hi[s], base, wn,
                 s_wt[base % DDE_WIN][s], s_wtop[s], lo);
   *from_ring = false;
   if (wn == 0) {
@@ -550,12 +537,12 @@ static __device__ __noinline__ unsigned lag_window_miss(int s, double st, bool *
 /* The entry a lag query at time t reads, src/dopri.c:742-769.  On failure
  * obj->error / ERR_YLAG_FAIL are set and ok is false. */
 __device__ __forceinline__ LagHit find_time(int s, double t) {
-  const double sign = s_sign[s];
+  const double sign = s_lag_u.sign;
   const double st = sign * t; /* entries are ordered by sign * time */
   LagHit hit;
   hit.ok = true;
   hit.cfg = s_cfg[s];
-  hit.from_ring = (hit.cfg >> 24) == 0;
+  hit.from_ring = ((hit.cfg >> 24) & 1) == 0;
   /* Entries in the window are consecutive and unused slots hold +inf, so the
      number of slots (in any order) that start at or before st locates the
      entry: no search, no slot arithmetic. */
@@ -654,7 +641,7 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
-  if (s_sign[s] * t <= s_t0[s]) {
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
     return (s_cfg[s] & 0xffff) == 1 ? s_y0_value[s] : s_y0[s][i];
   }
   const dde::LagHit hit = dde::find_time(s, t);
@@ -669,7 +656,7 @@ static __device__ __forceinline__ double ylag_1(double t, size_t i) {
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
   const int s = threadIdx.x;
   const int n = dde::s_lag_u.n;
-  if (s_sign[s] * t <= s_t0[s]) {
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
     if (n == 1) {
       y[0] = s_y0_value[s];
       return;
@@ -689,7 +676,7 @@ template <class Index>
 static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *idx,
                                                         size_t nidx, double *y) {
   const int s = threadIdx.x;
-  if (s_sign[s] * t <= s_t0[s]) {
+  if (dde::s_lag_u.sign * t <= s_t0[s]) {
     if ((s_cfg[s] & 0xffff) == 1) {
       for (size_t i = 0; i < nidx; ++i) {
         y[i] = s_y0_value[s];

@@ -6,3 +6,4 @@ for lib in "$@"; do
   echo "== $lib" >> gpurun_out/variants_$tag.log
   DDE_B200_LIB=$PWD/$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline >> gpurun_out/variants_$tag.log 2>&1
 done
+grep -o '"value": [0-9.]*\|"e2e": {"value": [0-9.]*\|^== .*' gpurun_out/variants_$tag.log
