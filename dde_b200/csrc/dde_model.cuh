@@ -89,7 +89,13 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
     return err;
   }
   /* the stepping kernel: one resident wave of persistent threads */
-  auto kernel = dopri_tpt_kernel<M, METHOD>;
+  /* a small model without history: the unrolled stage loop (dopri_kernels.cuh) */
+  constexpr bool CAN_UNROLL = M::N >= 1 && M::N <= 4;
+  auto kernel = dopri_tpt_kernel<M, METHOD, false>;
+  if (CAN_UNROLL && args.n_history == 0) {
+    kernel = dopri_tpt_kernel<M, METHOD, CAN_UNROLL>;
+    dyn = DDE_CTX_BYTES + sizeof(double) * (DDE_STAGE_ROW_DOUBLES + 1) * DDE_TPB; /* staged rows */
+  }
   err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
   if (err != cudaSuccess) {
     return err;

@@ -57,6 +57,18 @@ namespace dde {
 #ifndef DDE_MIN_BLOCKS_SMALL
 #define DDE_MIN_BLOCKS_SMALL 2 /* the same for compile-time n = 2 .. 4 */
 #endif
+#ifndef DDE_MIN_BLOCKS_UNROLLED
+/* ... and for the unrolled dopri5 kernel of a model with n = 2 .. 4 (no history: its shared
+   memory is the context and the staged output rows); 3 blocks: 168 registers, a
+   48-byte spill (measured on the Lorenz sweep: 1000 rows 54.3 -> 49.7 ms per 1 M
+   trajectories, 10 rows 37.2 -> 25.1 ms) */
+#define DDE_MIN_BLOCKS_UNROLLED 3
+#endif
+#ifndef DDE_STAGE_ROW_DOUBLES
+/* doubles of output rows a thread of the unrolled kernel stages before its warp
+   writes them out (48: 16 rows of a three-equation system; pitch 49) */
+#define DDE_STAGE_ROW_DOUBLES 48
+#endif
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 /* the step-size controller's pow (once per attempt) is out of line, so that the hot
@@ -95,10 +107,20 @@ __device__ __forceinline__ RingStart ring_start(const DopriArgs &a, long long tr
   return r;
 }
 
-template <class M, int METHOD>
+/* UNROLLED: the stage loop fully unrolled -- one inlined copy of the model per
+ * evaluation, no stage switch, tableau entries as instruction operands.  For a
+ * small right-hand side without history (Lorenz: 9 flops) the loop + switch
+ * around the one shared copy cost several times the model itself; for a
+ * right-hand side with pow and a lag look-up the copies overflow the
+ * instruction cache (profiles/r1a).  Chosen at launch: fixed n <= 4 and no
+ * history ring. */
+template <class M, int METHOD, bool UNROLLED = false>
 __global__ void
 __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS
-                                      : (M::N > 1 && M::N <= 4 ? DDE_MIN_BLOCKS_SMALL : 1)))
+                            : M::N > 4 || M::N < 1
+                                ? 1
+                                : (UNROLLED && METHOD == 0 ? DDE_MIN_BLOCKS_UNROLLED
+                                                           : DDE_MIN_BLOCKS_SMALL)))
 dopri_tpt_kernel(const DopriArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
@@ -157,7 +179,45 @@ dopri_tpt_kernel(const DopriArgs a) {
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
 
+  /* Output rows of the unrolled kernel are staged: a thread's rows go to its own
+     buffer in shared memory (where a model with history keeps its lag window) and
+     the warp writes a buffer out together, as one contiguous run of the
+     trajectory's result block -- a few full-line stores instead of one 8-byte
+     transaction per component, row and lane (the dense grids of a parameter sweep
+     are bound by exactly those transactions).  Rows that do not fit (one step
+     crossing more than the buffer holds) and a retiring trajectory's remainder are
+     written directly. */
+  constexpr bool STAGE_OUT = UNROLLED && NC > 0;
+  constexpr int STAGE_DOUBLES = STAGE_OUT ? DDE_STAGE_ROW_DOUBLES / NMAX * NMAX : 1;
+  double *const stage = s_wc + (size_t) s * (DDE_STAGE_ROW_DOUBLES + 1); /* odd pitch */
+  int st_count = 0;          /* doubles pending */
+  double *st_dst = nullptr;  /* where the first of them goes */
+
   for (;;) {
+    if (STAGE_OUT) {
+      const unsigned am = __activemask();
+      unsigned want = __ballot_sync(am, st_count >= STAGE_DOUBLES / 2);
+      if (want) {
+        const unsigned lane = threadIdx.x & 31u;
+        const int rank = __popc(am & ((1u << lane) - 1u)), nact = __popc(am);
+        do {
+          const int src_lane = __ffs(want) - 1;
+          want &= want - 1;
+          const int cnt = __shfl_sync(am, st_count, src_lane);
+          double *const dst =
+              (double *) __shfl_sync(am, (unsigned long long) st_dst, src_lane);
+          const double *const src =
+              s_wc + (size_t) ((threadIdx.x & ~31u) + src_lane) * (DDE_STAGE_ROW_DOUBLES + 1);
+          for (int k = rank; k < cnt; k += nact) {
+            dst[k] = src[k];
+          }
+          if ((int) lane == src_lane) {
+            st_count = 0;
+          }
+        } while (want);
+        __syncwarp(am); /* orders the rows before their owner's retirement fence */
+      }
+    }
     if (!active) {
       /* persistent threads: take the next trajectory, or leave */
       traj = (long long) atomicAdd(a.next_traj, 1ULL);
@@ -290,7 +350,8 @@ dopri_tpt_kernel(const DopriArgs a) {
     /* how many evaluations this lane takes part in: none, the attempt's, or --
        once accepted -- the accept-only ones too */
     int my_stages = run ? NST_STEP : 0;
-#pragma unroll 1
+    constexpr int STAGE_UNROLL = UNROLLED ? NST : 1;
+#pragma unroll STAGE_UNROLL
     for (int st = 0; st < NST; ++st) {
       if (st >= my_stages) {
         continue;
@@ -743,7 +804,21 @@ dopri_tpt_kernel(const DopriArgs a) {
           for (int i = 0; i < n; ++i) {
             row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
                                  : interp853(n, theta, theta1, hd + i);
-            yo[i] = row[i];
+          }
+          if (STAGE_OUT && st_count + n <= STAGE_DOUBLES) {
+            if (st_count == 0) {
+              st_dst = yo;
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              stage[st_count + i] = row[i];
+            }
+            st_count += n;
+          } else {
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              yo[i] = row[i];
+            }
           }
           if (n_out > 0) {
             double o[OMAX];
@@ -807,6 +882,12 @@ dopri_tpt_kernel(const DopriArgs a) {
     }
 
     if (done) {
+      if (STAGE_OUT) { /* the rows still staged */
+        for (int k = 0; k < st_count; ++k) {
+          st_dst[k] = stage[k];
+        }
+        st_count = 0;
+      }
       /* retire: statistics as r_dopri_cleanup reads them, src/r_dopri.c:412-428 */
       a.stats[4 * traj + 0] = n_eval;
       a.stats[4 * traj + 1] = n_step;
