@@ -107,21 +107,43 @@ __device__ __forceinline__ RingStart ring_start(const DopriArgs &a, long long tr
   return r;
 }
 
-/* UNROLLED: the stage loop fully unrolled -- one inlined copy of the model per
- * evaluation, no stage switch, tableau entries as instruction operands.  For a
- * small right-hand side without history (Lorenz: 9 flops) the loop + switch
- * around the one shared copy cost several times the model itself; for a
- * right-hand side with pow and a lag look-up the copies overflow the
- * instruction cache (profiles/r1a).  Chosen at launch: fixed n <= 4 and no
- * history ring. */
-template <class M, int METHOD, bool UNROLLED = false>
+/* MODE, chosen at launch (dde_model.cuh):
+ *   0  the stage loop as a loop: a warp-uniform stage counter, one inlined copy of
+ *      the model, one switch that files its result and forms the next input;
+ *   1  the stage loop fully unrolled -- one inlined copy of the model per
+ *      evaluation, no switch, output rows staged in shared memory.  For a small
+ *      right-hand side without history (Lorenz: 9 flops) the loop + switch cost
+ *      several times the model itself (fixed n <= 4, no history ring);
+ *   2  unrolled too, but around ONE out-of-line copy of the model (arguments and
+ *      result by value, in registers): for a right-hand side with pow and a lag
+ *      look-up, whose sixteen inlined copies would overflow the instruction
+ *      cache (profiles/r1a) while the loop + switch still cost ~10 % (n = 1). */
+template <int N>
+struct DdeVec {
+  double v[N];
+};
+
+/* the model, out of line (MODE 2): arguments and result by value, in registers */
+template <class M, int NMAX, int PMAX, int CFG>
+static __device__ __noinline__ DdeVec<NMAX> dde_deriv_call(double tt, DdeVec<NMAX> yin,
+                                                           DdeVec<PMAX> p) {
+  const int s = threadIdx.x;
+  s_tt[s] = tt;
+  __builtin_assume(s_cfg[s] == CFG);
+  DdeVec<NMAX> kt;
+  M::deriv((size_t) NMAX, tt, yin.v, kt.v, p.v);
+  return kt;
+}
+
+template <class M, int METHOD, int MODE = 0>
 __global__ void
 __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS
                             : M::N > 4 || M::N < 1
                                 ? 1
-                                : (UNROLLED && METHOD == 0 ? DDE_MIN_BLOCKS_UNROLLED
+                                : (MODE == 1 && METHOD == 0 ? DDE_MIN_BLOCKS_UNROLLED
                                                            : DDE_MIN_BLOCKS_SMALL)))
 dopri_tpt_kernel(const DopriArgs a) {
+  constexpr bool UNROLLED = MODE != 0;
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
@@ -187,7 +209,7 @@ dopri_tpt_kernel(const DopriArgs a) {
      are bound by exactly those transactions).  Rows that do not fit (one step
      crossing more than the buffer holds) and a retiring trajectory's remainder are
      written directly. */
-  constexpr bool STAGE_OUT = UNROLLED && NC > 0;
+  constexpr bool STAGE_OUT = MODE == 1 && NC > 0;
   constexpr int STAGE_DOUBLES = STAGE_OUT ? DDE_STAGE_ROW_DOUBLES / NMAX * NMAX : 1;
   double *const stage = s_wc + (size_t) s * (DDE_STAGE_ROW_DOUBLES + 1); /* odd pitch */
   int st_count = 0;          /* doubles pending */
@@ -359,13 +381,27 @@ dopri_tpt_kernel(const DopriArgs a) {
       /* -- 1. dopri_eval, src/dopri.c:831-835: the one hot copy of the model, on
             the stage input `yin` at time `tt` that the previous trip through the
             switch below (or the attempt's prologue) prepared -- */
-      s_tt[s] = tt; /* lag look-ups learn their offset from it */
-      if (NC > 0) {
-        /* the lag functions read the method / width / staging flags from the
-           thread's context: tell the optimiser what they will find */
-        __builtin_assume(s_cfg[s] == (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24)));
+      if (MODE == 2) {
+        DdeVec<NMAX> vin;
+        DdeVec<PMAX> vp;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) vin.v[i] = yin[i];
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) vp.v[i] = p[i];
+        const DdeVec<NMAX> vk =
+            dde_deriv_call<M, NMAX, PMAX, (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24))>(tt, vin,
+                                                                                         vp);
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) kt[i] = vk.v[i];
+      } else {
+        s_tt[s] = tt; /* lag look-ups learn their offset from it */
+        if (NC > 0) {
+          /* the lag functions read the method / width / staging flags from the
+             thread's context: tell the optimiser what they will find */
+          __builtin_assume(s_cfg[s] == (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24)));
+        }
+        M::deriv((size_t) n, tt, yin, kt, p);
       }
-      M::deriv((size_t) n, tt, yin, kt, p);
       ++n_eval;
 
       /* -- 2. file the result and form the input of the next evaluation (one
