@@ -136,7 +136,10 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
       a.staged = 1;
     }
   }
-  auto kernel = (a.restart || a.restartable) ? difeq_tpt_kernel<M, true> : difeq_tpt_kernel<M, false>;
+  const bool keep = a.restart || a.restartable;
+  auto kernel = a.staged ? (keep ? difeq_tpt_kernel<M, true, true> : difeq_tpt_kernel<M, false, true>)
+                         : (keep ? difeq_tpt_kernel<M, true, false>
+                                 : difeq_tpt_kernel<M, false, false>);
   cudaError_t err =
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
   if (err != cudaSuccess) {

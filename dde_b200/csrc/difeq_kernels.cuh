@@ -59,7 +59,9 @@ struct DifeqArgs {
 
 /* RESTART: compiled with the difeq_continue paths (start from / leave a history
  * in HBM); the plain instantiation is ~10 % faster on C4 without them. */
-template <class M, bool RESTART>
+/* STAGED: the history lives in shared memory (a.staged, decided at launch); a
+ * template argument so that yprev_* see it in the per-thread cfg word at compile time. */
+template <class M, bool RESTART, bool STAGED>
 __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
@@ -78,10 +80,17 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     s_lag_u.n = n;
     s_lag_u.hl = hl;
     s_lag_u.order = 0;
-    s_lag_u.staged = a.staged;
+    s_lag_u.staged = STAGED ? 1 : 0;
   }
   __syncthreads();
-  const int cfg = n | (a.staged << 24);
+  /* what yprev_* read: n, "history on chip" and, then, its capacity (< 128: it fits
+     the shared-memory budget) */
+  const int cfg = n | ((STAGED ? 1 : 0) << 24) | (STAGED ? (int) ((unsigned) cap << 25) : 0);
+  /* this thread's column of the on-chip history as a shared-window address; opaque
+     to the optimiser so that it is formed once, not from the special registers in
+     every step */
+  unsigned hist_col = (unsigned) __cvta_generic_to_shared(sd_hist + s);
+  asm volatile("" : "+r"(hist_col));
 
   const int n_steps = a.n_steps;
   const int nt = a.return_initial ? n_steps : n_steps - 1;
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       if (count > 0) {
         sd_step0[s] = (long long) (a.step_origin + (count - used));
       }
-      if (a.staged) { /* back on chip */
+      if (STAGED) { /* back on chip */
         for (unsigned k = 0; k < used; ++k) {
           const double *src = ring + (size_t) k * (size_t) hl + 1;
           double *dst = sd_hist + (size_t) k * n * DDE_TPB + s;
@@ -152,11 +161,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
 #define DDE_DIFEQ_COMMIT(yy)                                  \
   do {                                                        \
     if (cap > 0) {                                            \
-      if (a.staged) {                                         \
+      if (STAGED) {                                           \
         /* on-chip history: only y is ever read back */       \
-        double *dst = sd_hist + (size_t) head * n * DDE_TPB + s; \
+        const unsigned dst = hist_col + (unsigned) (head * n * DDE_TPB * 8); \
         _Pragma("unroll") for (int i = 0; i < n; ++i) {       \
-          dst[(size_t) i * DDE_TPB] = (yy)[i];                \
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + (unsigned) (i * DDE_TPB * 8)), \
+                       "d"((yy)[i]) : "memory");              \
         }                                                     \
       } else {                                                \
         double *dst = ring + (size_t) head * (size_t) hl;     \
@@ -195,6 +205,8 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     }
 
     bool failed = false;
+    /* the next step a row is wanted at: read when the row index moves, not per step */
+    unsigned long long step_out = steps_idx < n_steps ? a.steps[steps_idx] : ~0ULL;
     for (;;) {
       sd_step[s] = (long long) step;
       if (NC > 0) { /* what yprev_* will read: lets the optimiser drop the other path */
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         wo += n_out;
         store_next_output = false;
       }
-      if (steps_idx < n_steps && step == a.steps[steps_idx]) {
+      if (step == step_out) {
 #pragma unroll
         for (int i = 0; i < n; ++i) {
           wy[i] = y[i];
@@ -229,6 +241,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         wy += n;
         store_next_output = true;
         ++steps_idx;
+        step_out = steps_idx < n_steps ? a.steps[steps_idx] : ~0ULL;
       }
       DDE_DIFEQ_COMMIT(y);
       if (step == step_last) {
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       /* what a later difeq_continue needs: the count, and an on-chip history
          written back to the replicate's ring (slot order is the same) */
       a.ring_count[rep] = count;
-      if (a.staged) {
+      if (STAGED) {
         const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
         for (unsigned k = 0; k < used; ++k) {
           double *dst = ring + (size_t) k * (size_t) hl + 1;

@@ -720,10 +720,12 @@ static __device__ __forceinline__ PrevHit dde_find_step(int s, int step) {
   PrevHit hit;
   const int cfg = sd_cfg[s];
   const int offset = (int) sd_step[s] - step;
-  const int cap = dde::s_lag_u.cap;
+  /* an on-chip history is short: its capacity travels in the per-thread cfg word
+     (bits 25-31), next to everything else the look-up reads */
+  const int cap = (cfg >> 24) & 1 ? (int) ((unsigned) cfg >> 25) : dde::s_lag_u.cap;
   const unsigned count = sd_count[s];
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
-  hit.staged = (cfg >> 24) != 0;
+  hit.staged = ((cfg >> 24) & 1) != 0;
   hit.ok = !(cap == 0 || offset < 0 || (unsigned) offset >= used);
   hit.e = nullptr;
   hit.stride = 1;
