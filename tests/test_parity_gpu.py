@@ -630,6 +630,33 @@ def test_streamed_download_equals_run_then_download(backend, n_traj):
         assert_bits_equal(got.y, ref.y, "one-shot y vs reference")
 
 
+@pytest.mark.parametrize("model_fn,n_times", [("lorenz_sweep", 41), ("rossler_sweep", 1001),
+                                              ("lorenz_sweep", 6001)])
+def test_staged_rows_of_the_unrolled_kernel(backend, model_fn, n_times):
+    """Small models without history run the unrolled kernel, whose output rows are staged
+    in shared memory and written out by the warp (dopri_kernels.cuh, MODE 1): same bits as
+    the reference for sparse grids, dense grids, and grids so dense that one step crosses
+    more rows than a thread stages (written directly); the streamed download (several
+    completion blocks, a ragged last one) sees every row before its block is flagged."""
+    n_traj = 70001 if n_times == 41 else 300
+    model, y0, parms, times, kw = getattr(workloads, model_fn)(n_traj, first=17, n_times=n_times)
+    got = dde_b200.dopri_batch(y0, times, model, parms, **kw)  # the streamed path
+    b = dde_b200.DopriBatch(model, 3, n_traj, n_parms=3, **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    held = b.download()
+    b.close()
+    assert_bits_equal(got.y, held.y, "streamed vs run + download")
+    np.testing.assert_array_equal(got.statistics, held.statistics)
+    k = 64  # the reference on both ends of the batch
+    for sl in (slice(0, k), slice(n_traj - k, n_traj)):
+        want = pyoracle.dopri_batch(backend, model, y0[sl], times, parms[sl], **kw)
+        np.testing.assert_array_equal(got.code[sl], want.code)
+        np.testing.assert_array_equal(got.statistics[sl], want.statistics)
+        assert_bits_equal(got.y[sl], want.y, "y vs reference")
+
+
 def test_streamed_download_large_model(backend):
     """the block-per-trajectory kernel raises the same completion flags"""
     model, y0, parms, times, kw = workloads.seir_age(8)
