@@ -71,6 +71,16 @@ namespace dde {
 #endif
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+/* shared memory by shared-window address */
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 /* the step-size controller's pow (once per attempt) is out of line, so that the hot
    loop holds one copy of pow, the model's (measured: +1.2 %) */
 #ifndef DDE_CTRL_POW_INLINE
@@ -211,7 +221,12 @@ dopri_tpt_kernel(const DopriArgs a) {
      written directly. */
   constexpr bool STAGE_OUT = MODE == 1 && NC > 0;
   constexpr int STAGE_DOUBLES = STAGE_OUT ? DDE_STAGE_ROW_DOUBLES / NMAX * NMAX : 1;
-  double *const stage = s_wc + (size_t) s * (DDE_STAGE_ROW_DOUBLES + 1); /* odd pitch */
+  /* the thread's buffer as a shared-window address (odd pitch), opaque to the
+     optimiser: it would otherwise re-derive it from the special registers per row */
+  unsigned stage =
+      (unsigned) __cvta_generic_to_shared(s_wc + (size_t) s * (DDE_STAGE_ROW_DOUBLES + 1));
+  asm volatile("" : "+r"(stage));
+  double *yo_next = nullptr; /* where the trajectory's next output row goes */
   int st_count = 0;          /* doubles pending */
   double *st_dst = nullptr;  /* where the first of them goes */
 
@@ -228,10 +243,9 @@ dopri_tpt_kernel(const DopriArgs a) {
           const int cnt = __shfl_sync(am, st_count, src_lane);
           double *const dst =
               (double *) __shfl_sync(am, (unsigned long long) st_dst, src_lane);
-          const double *const src =
-              s_wc + (size_t) ((threadIdx.x & ~31u) + src_lane) * (DDE_STAGE_ROW_DOUBLES + 1);
+          const unsigned src = __shfl_sync(am, stage, src_lane);
           for (int k = rank; k < cnt; k += nact) {
-            dst[k] = src[k];
+            dst[k] = lds_f64(src + 8u * (unsigned) k);
           }
           if ((int) lane == src_lane) {
             st_count = 0;
@@ -263,6 +277,7 @@ dopri_tpt_kernel(const DopriArgs a) {
          the host: times are shared by all trajectories) */
       t = a.times[0];
       times_idx = 1;
+      yo_next = a.y_out + ((size_t) traj * (size_t) nt + (a.return_initial ? 1u : 0u)) * (size_t) n;
       t_out = n_times > 1 ? a.times[1] : 0.0;
       tcrit_idx = a.tcrit_idx0;
       n_eval = n_step = n_accept = n_reject = 0;
@@ -345,7 +360,7 @@ dopri_tpt_kernel(const DopriArgs a) {
         last = true;
       }
       ++n_step;
-      if (a.n_history > 0) {
+      if (MODE != 1 && a.n_history > 0) { /* MODE 1 is launched without a ring */
         /* top up the staged lag window while the warp is in step */
         lag_window_ensure<ORDER * NMAX, (NC > 0)>(s, sign * t, sign * (t + h));
       }
@@ -832,10 +847,10 @@ dopri_tpt_kernel(const DopriArgs a) {
           const double theta = (tq - t_old) / h;
           const double theta1 = 1 - theta;
           double row[NMAX];
-          /* row of this time: times_idx, shifted by one without the initial row */
-          const size_t r = (size_t) traj * (size_t) nt +
-                           (size_t) (times_idx - (a.return_initial ? 0 : 1));
-          double *yo = a.y_out + r * (size_t) n;
+          /* row of this time: times_idx, shifted by one without the initial row; rows
+             are emitted in order, so where they go is a running pointer */
+          double *yo = yo_next;
+          yo_next += n;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
@@ -847,7 +862,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             }
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              stage[st_count + i] = row[i];
+              sts_f64(stage + 8u * (unsigned) (st_count + i), row[i]);
             }
             st_count += n;
           } else {
@@ -858,6 +873,8 @@ dopri_tpt_kernel(const DopriArgs a) {
           }
           if (n_out > 0) {
             double o[OMAX];
+            const size_t r = (size_t) traj * (size_t) nt +
+                             (size_t) (times_idx - (a.return_initial ? 0 : 1));
             double *oo = a.out + r * (size_t) n_out;
             M::output((size_t) n, tq, row, (size_t) n_out, o, p);
 #pragma unroll
@@ -873,7 +890,7 @@ dopri_tpt_kernel(const DopriArgs a) {
 
         /* ring_buffer_head_advance, src/dopri.c:460: the head entry goes to
            its slot in HBM and becomes visible to lag queries */
-        if (a.n_history > 0) {
+        if (MODE != 1 && a.n_history > 0) {
           double *dst = s_ring[s] + (size_t) s_head[s] * (size_t) hl;
 #pragma unroll
           for (int i = 0; i < ORDER * n; ++i) {
@@ -920,7 +937,7 @@ dopri_tpt_kernel(const DopriArgs a) {
     if (done) {
       if (STAGE_OUT) { /* the rows still staged */
         for (int k = 0; k < st_count; ++k) {
-          st_dst[k] = stage[k];
+          st_dst[k] = lds_f64(stage + 8u * (unsigned) k);
         }
         st_count = 0;
       }
