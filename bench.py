@@ -335,11 +335,16 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum of the stepping kernel from the
         # committed ncu --set full capture of this command (profiles/), if it matches
         traffic = None
+        ncu_pipe = None
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
             tj = json.loads(tpath.read_text())
             if tj.get("n_traj_per_gpu") == n_traj:
                 traffic = tj.get("dram_bytes_per_launch")
+                # the same capture's pipe counters: the flop convention counts a division
+                # or a pow as written, the pipe executes their expansions
+                ncu_pipe = {k: tj[k] for k in ("fp64_pipe_pct_of_peak", "issue_active_pct",
+                                               "threads_per_warp_instruction") if k in tj}
         fp64 = measure_fp64_peaks(torch)
         achieved_tflops = flops / (ms_kernel * 1e-3) / 1e12
         line = {
@@ -364,7 +369,8 @@ def main():
                          "peak_nofma_tflops": fp64["nofma"], "peak_fma_tflops": fp64["fma"],
                          "frac_of_nofma": achieved_tflops / fp64["nofma"] if fp64["nofma"] else None,
                          "flops_convention": "SURVEY.md 8d: one + - * / fmax as written = 1 flop; "
-                                             "F_pow = %d" % F_POW}},
+                                             "F_pow = %d" % F_POW,
+                         "ncu": ncu_pipe}},
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
