@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
   const int n_steps = a.n_steps;
   const int nt = a.return_initial ? n_steps : n_steps - 1;
   const unsigned long long step_first = a.steps[0];
-  const unsigned long long step_last = a.steps[n_steps - 1];
   const bool has_output = n_out > 0;
 
   for (;;) {
@@ -233,6 +232,7 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         wo += n_out;
         store_next_output = false;
       }
+      bool at_end = false; /* the last requested step is the last row (one test per step) */
       if (step == step_out) {
 #pragma unroll
         for (int i = 0; i < n; ++i) {
@@ -241,10 +241,11 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         wy += n;
         store_next_output = true;
         ++steps_idx;
-        step_out = steps_idx < n_steps ? a.steps[steps_idx] : ~0ULL;
+        at_end = steps_idx >= n_steps;
+        step_out = at_end ? ~0ULL : a.steps[steps_idx];
       }
       DDE_DIFEQ_COMMIT(y);
-      if (step == step_last) {
+      if (at_end) {
         if (a.y_final != nullptr) {
 #pragma unroll
           for (int i = 0; i < n; ++i) {
