@@ -31,6 +31,7 @@
 #include "difeq_kernels.cuh"
 #include "dopri_kernels.cuh"
 #include "registry.h"
+#include "dde_model_def.h"
 
 /* Model sources call libm by name; give them the bit-reproducible versions
    (see dde_math.h). */
@@ -153,59 +154,8 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
 
 } /* namespace dde */
 
-#define DDE_DYN_OR(v, dyn) ((v) > 0 ? 0 : (dyn))
-
-/* Event functions (src/dopri.h:53: void event(size_t n, double t, double *y,
- * void *data), applied at critical times, src/dopri.c:476-482): list a model's
- * events once,
- *     DDE_EVENT_TABLE(growth_events, identity, double_variables, halve_variables)
- * and register the model with DDE_REGISTER_DOPRI_EVENTS(..., growth_events, 3);
- * dde_dopri_batch_set_events() then names them by position.  Up to 8. */
-#define DDE_EVENT_CASE_(k, f) \
-  case k:                     \
-    f(n, t, y, data);         \
-    break;
-#define DDE_EVENT_CASES_1(a) DDE_EVENT_CASE_(0, a)
-#define DDE_EVENT_CASES_2(a, b) DDE_EVENT_CASES_1(a) DDE_EVENT_CASE_(1, b)
-#define DDE_EVENT_CASES_3(a, b, c) DDE_EVENT_CASES_2(a, b) DDE_EVENT_CASE_(2, c)
-#define DDE_EVENT_CASES_4(a, b, c, d) DDE_EVENT_CASES_3(a, b, c) DDE_EVENT_CASE_(3, d)
-#define DDE_EVENT_CASES_5(a, b, c, d, e) DDE_EVENT_CASES_4(a, b, c, d) DDE_EVENT_CASE_(4, e)
-#define DDE_EVENT_CASES_6(a, b, c, d, e, f) DDE_EVENT_CASES_5(a, b, c, d, e) DDE_EVENT_CASE_(5, f)
-#define DDE_EVENT_CASES_7(a, b, c, d, e, f, g) \
-  DDE_EVENT_CASES_6(a, b, c, d, e, f) DDE_EVENT_CASE_(6, g)
-#define DDE_EVENT_CASES_8(a, b, c, d, e, f, g, h) \
-  DDE_EVENT_CASES_7(a, b, c, d, e, f, g) DDE_EVENT_CASE_(7, h)
-#define DDE_EVENT_PICK_(_1, _2, _3, _4, _5, _6, _7, _8, NAME, ...) NAME
-#define DDE_EVENT_TABLE(TABLE, ...)                                                            \
-  static __device__ __forceinline__ void TABLE(int which, size_t n, double t, double *y,       \
-                                               void *data) {                                   \
-    switch (which) {                                                                           \
-      DDE_EVENT_PICK_(__VA_ARGS__, DDE_EVENT_CASES_8, DDE_EVENT_CASES_7, DDE_EVENT_CASES_6,    \
-                      DDE_EVENT_CASES_5, DDE_EVENT_CASES_4, DDE_EVENT_CASES_3,                 \
-                      DDE_EVENT_CASES_2, DDE_EVENT_CASES_1)(__VA_ARGS__)                       \
-      default:                                                                                 \
-        break;                                                                                 \
-    }                                                                                          \
-  }
-#define DDE_NO_EVENTS(which, n, t, y, data) ((void) 0)
-
 #define DDE_REGISTER_DOPRI_EVENTS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)     \
-  struct dde_dopri_model_##NAME {                                                              \
-    static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT), N_EVENTS = (NEVENTS);       \
-    static __device__ __forceinline__ void deriv(size_t n, double t, const double *y,          \
-                                                 double *dydt, const void *data) {             \
-      DERIV(n, t, y, dydt, data);                                                              \
-    }                                                                                          \
-    static __device__ __forceinline__ void output(size_t n, double t, const double *y,         \
-                                                  size_t n_out, double *out,                   \
-                                                  const void *data) {                          \
-      OUTPUT(n, t, y, n_out, out, data);                                                       \
-    }                                                                                          \
-    static __device__ __forceinline__ void event(int which, size_t n, double t, double *y,     \
-                                                 void *data) {                                 \
-      EVENTS(which, n, t, y, data);                                                            \
-    }                                                                                          \
-  };                                                                                           \
+  DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)                 \
   static dde::ModelDesc dde_dopri_desc_##NAME = {#NAME,                                        \
                                                  1,                                            \
                                                  (NEQ),                                        \
@@ -222,8 +172,6 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
 
 #define DDE_REGISTER_DOPRI_OUTPUT(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT) \
   DDE_REGISTER_DOPRI_EVENTS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, DDE_NO_EVENTS, 0)
-
-#define DDE_NO_OUTPUT(n, t, y, n_out, out, data) ((void) 0)
 
 #define DDE_REGISTER_DOPRI(NAME, DERIV, NEQ, NPARMS) \
   DDE_REGISTER_DOPRI_OUTPUT(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0)

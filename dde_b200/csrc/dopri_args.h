@@ -62,7 +62,7 @@ struct DopriArgs {
   int chunk_shift;
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(DDE_HOST_EMU)
 /* called by the one thread that has written a trajectory's last result */
 __device__ __forceinline__ void chunk_retire(const DopriArgs &a, long long traj) {
   if (a.chunk_done == nullptr) {

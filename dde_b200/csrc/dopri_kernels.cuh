@@ -78,6 +78,13 @@ namespace dde {
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 /* shared memory by shared-window address */
+#ifdef DDE_HOST_EMU /* tests/emu: an "address" is a byte offset into dde_smem */
+static inline size_t __cvta_generic_to_shared(const void *p) {
+  return (size_t) ((const char *) p - (const char *) dde_smem);
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) { return dde_smem[addr / 8]; }
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { dde_smem[addr / 8] = v; }
+#else
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
@@ -86,6 +93,7 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+#endif
 
 /* the step-size controller's pow (once per attempt) is out of line, so that the hot
    loop holds one copy of pow, the model's (measured: +1.2 %) */

@@ -92,7 +92,11 @@ enum {
  * whole per-thread state hangs off ONE thread-dependent base address; every
  * launch of a kernel that includes this file passes at least DDE_CTX_BYTES of
  * dynamic shared memory. */
+#ifdef DDE_HOST_EMU /* tests/emu: the device code compiled by g++, one lane at a time */
+static double dde_smem[24 * 1024];
+#else
 extern __shared__ double dde_smem[];
+#endif
 #define DDE_CTX_BYTES \
   (sizeof(double) * ::dde::DDE_F_COUNT64 * DDE_TPB + sizeof(int) * ::dde::DDE_FI_COUNT32 * DDE_TPB)
 static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s_wc alignment");

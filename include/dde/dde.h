@@ -67,7 +67,7 @@ static __device__ char *dde_coop_scratch(void);
 #define DDE_SCRATCH(type, name, len) type name[len]
 #endif
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(DDE_HOST_EMU) /* DDE_HOST_EMU: tests/emu, the device code compiled by g++ */
 
 #define DDE_MODEL_FN static __device__ __forceinline__
 

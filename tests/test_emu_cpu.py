@@ -1,0 +1,64 @@
+"""The device code, compiled by g++ and run one lane at a time (tests/emu), against
+the oracle: control flow and arithmetic of the stepping kernels checked bit for bit
+where there is no GPU.  Nothing warp-wide is exercised here (a warp of one lane);
+the GPU parity tests are the gate for that."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+from dde_b200 import workloads
+from oracle import pyoracle
+
+pyemu = pytest.importorskip("emu.pyemu")
+
+needs_oracle = pytest.mark.skipif(not pyoracle.available("oracle"),
+                                  reason="oracle/liboracle.so not built (make -C oracle oracle)")
+
+
+def compare(got, want):
+    np.testing.assert_array_equal(got.code, want.code)
+    np.testing.assert_array_equal(got.statistics, want.statistics)
+    assert_bits_equal(got.t_last, want.t_last, "t_last")
+    assert_bits_equal(got.step_size, want.step_size, "step_size")
+    assert_bits_equal(got.y, want.y, "y")
+
+
+@needs_oracle
+@pytest.mark.parametrize("mode", [0, 2])
+def test_mackey_glass(mode):
+    model, y0, parms, times, kw = workloads.mackey_glass(192)
+    got = pyemu.dopri_batch(model, y0, times, parms, mode=mode, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
+    assert (want.code != 1).any(), "the sample should include failing trajectories"
+    compare(got, want)
+
+
+@needs_oracle
+@pytest.mark.parametrize("n_history", [3, 8])
+def test_mackey_glass_small_ring(n_history):
+    """ring overwrite / underflow: ERR_YLAG_FAIL where the reference reports it"""
+    model, y0, parms, times, kw = workloads.mackey_glass(64)
+    kw = dict(kw, n_history=n_history)
+    got = pyemu.dopri_batch(model, y0, times, parms, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
+    compare(got, want)
+
+
+@needs_oracle
+def test_mackey_glass_dopri5_and_tcrit():
+    model, y0, parms, times, kw = workloads.mackey_glass(48)
+    kw = dict(kw, method="dopri5")
+    tcrit = np.array([17.0, 34.0, 51.0])
+    got = pyemu.dopri_batch(model, y0, times, parms, tcrit=tcrit, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, tcrit=tcrit, **kw)
+    compare(got, want)
+
+
+@needs_oracle
+@pytest.mark.parametrize("mode", [0, 1])
+def test_lorenz_sweep(mode):
+    model, y0, parms, times, kw = workloads.lorenz_sweep(32, n_times=101, t_end=2.0)
+    got = pyemu.dopri_batch(model, y0, times, parms, n_out=2, mode=mode, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, n_out=2, **kw)
+    compare(got, want)
+    assert_bits_equal(got.output, want.output, "output")
