@@ -26,10 +26,13 @@
 #include <math.h>
 #include <stddef.h>
 
+#include <type_traits>
+
 #include <dde/dde.h>
 
 #include "difeq_kernels.cuh"
 #include "dopri_kernels.cuh"
+#include "dopri_lag1_kernel.cuh"
 #include "registry.h"
 #include "dde_model_def.h"
 
@@ -61,6 +64,20 @@ inline int persistent_grid(Kernel kernel, long long n_items, int device_sms, siz
   const long long grid = wanted < resident ? wanted : resident;
   return (int) (grid < 1 ? 1 : grid);
 }
+
+/* stands in for a model dopri_lag1_kernel cannot take, so that the template is only
+   instantiated for models it can (the branch that would launch it is never taken) */
+struct Lag1Placeholder {
+  static constexpr int N = 1, NP = 0, N_OUT = 0, N_EVENTS = 0, N_LAGS = 1;
+  static __device__ __forceinline__ void lags(double t, const void *, double *tlag) { tlag[0] = t; }
+  static __device__ __forceinline__ void deriv(size_t, double, const double *, double *dydt,
+                                               const void *) {
+    dydt[0] = 0.0;
+  }
+  static __device__ __forceinline__ void output(size_t, double, const double *, size_t, double *,
+                                                const void *) {}
+  static __device__ __forceinline__ void event(int, size_t, double, double *, void *) {}
+};
 
 template <class M, int METHOD>
 cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaStream_t stream) {
@@ -104,6 +121,23 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
   constexpr bool CAN_CALL = M::N == 1 && M::NP >= 0 && M::NP <= 8;
   if (CAN_CALL && args.n_history > 0) {
     kernel = dopri_tpt_kernel<M, METHOD, CAN_CALL ? 2 : 0>;
+  }
+#ifdef DDE_LAGS_AHEAD /* measured slower (13.0 M against 16.6 M trajectories/s): off */
+  /* ... and the model declares its lag (M::lags): the look-ups of a step attempt are
+     answered together, ahead of the evaluations (dopri_kernels.cuh, MODE 3) */
+  constexpr bool CAN_AHEAD = CAN_CALL && M::N_LAGS == 1;
+  if (CAN_AHEAD && args.n_history > 0 && args.win_staged) {
+    kernel = dopri_tpt_kernel<M, METHOD, CAN_AHEAD ? 3 : 0>;
+  }
+#endif
+#endif
+#ifdef DDE_LAG1_KERNEL /* measured slower (12.1 M): off */
+  /* dop853 of one delay equation with a declared lag: the data-driven stage loop with
+     its stage values in shared memory (dopri_lag1_kernel.cuh) */
+  constexpr bool CAN_LAG1 = M::N == 1 && M::NP >= 0 && M::NP <= 8 && M::N_LAGS == 1 && METHOD == 1;
+  if (CAN_LAG1 && args.n_history > 0 && args.win_staged) {
+    kernel = dopri_lag1_kernel<typename std::conditional<CAN_LAG1, M, Lag1Placeholder>::type>;
+    dyn += DDE_L1_SMEM_BYTES;
   }
 #endif
   err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
@@ -154,8 +188,21 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
 
 } /* namespace dde */
 
-#define DDE_REGISTER_DOPRI_EVENTS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)     \
-  DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)                 \
+#define DDE_REGISTER_DOPRI_EVENTS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS) \
+  DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, DDE_NO_LAGS, 0)
+
+/* ... with the model's lags declared (dde_model_def.h: M::lags), e.g.
+ *     DDE_MODEL_FN void mackey_glass_lags(double t, const void *data, double *tlag) {
+ *       tlag[0] = t - 17.0;
+ *     }
+ *     DDE_REGISTER_DOPRI_LAGS(mackey_glass, mackey_glass, 1, 3, mackey_glass_lags, 1) */
+#define DDE_REGISTER_DOPRI_LAGS(NAME, DERIV, NEQ, NPARMS, LAGS, NLAGS)                        \
+  DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0, LAGS, NLAGS)
+
+#define DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, LAGS, \
+                                NLAGS)                                                         \
+  DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, LAGS,   \
+                              NLAGS)                                                           \
   static dde::ModelDesc dde_dopri_desc_##NAME = {#NAME,                                        \
                                                  1,                                            \
                                                  (NEQ),                                        \

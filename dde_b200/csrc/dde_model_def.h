@@ -7,6 +7,15 @@
  *   M::N, M::NP, M::N_OUT, M::N_EVENTS   compile-time shape (0 / -1: run time)
  *   M::deriv, M::output, M::event        the reference's model ABI, inlined
  *                                        (/root/reference/src/dopri.h:49-53)
+ *   M::N_LAGS, M::lags                   optional (an extension): the times at which
+ *                                        deriv(t, ...) reads the history,
+ *                                            void lags(double t, const void *data, double *tlag)
+ *                                        (the `lags` argument of dde23-style solvers).  The
+ *                                        kernel then answers the look-ups of a whole step
+ *                                        attempt up front, next to each other, and ylag_1 uses
+ *                                        an answer only when the model asks for exactly that
+ *                                        time: a wrong or missing declaration costs speed,
+ *                                        never correctness.
  */
 #ifndef DDE_MODEL_DEF_H
 #define DDE_MODEL_DEF_H
@@ -47,9 +56,19 @@
   }
 #define DDE_NO_EVENTS(which, n, t, y, data) ((void) 0)
 
-#define DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)        \
+#define DDE_NO_LAGS(t, data, tlag) ((void) 0)
+
+#define DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS) \
+  DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, DDE_NO_LAGS, 0)
+
+#define DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS,   \
+                                    LAGS, NLAGS)                                               \
   struct dde_dopri_model_##NAME {                                                              \
     static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT), N_EVENTS = (NEVENTS);       \
+    static constexpr int N_LAGS = (NLAGS);                                                     \
+    static __device__ __forceinline__ void lags(double t, const void *data, double *tlag) {    \
+      LAGS(t, data, tlag);                                                                     \
+    }                                                                                          \
     static __device__ __forceinline__ void deriv(size_t n, double t, const double *y,          \
                                                  double *dydt, const void *data) {             \
       DERIV(n, t, y, dydt, data);                                                              \

@@ -40,11 +40,13 @@
 #define DDE_TPB 128 /* threads per block of the thread-per-trajectory kernels */
 #endif
 #ifndef DDE_WIN
-#define DDE_WIN 6 /* entries in a thread's staged lag window */
+/* entries in a thread's staged lag window (queries that miss it, tests/emu on 2048
+   Mackey-Glass trajectories: 1.8 per trajectory with 6, 4.6 with 5, 10.5 with 4) */
+#define DDE_WIN 6
 #endif
 /* shared memory a block may spend on staged coefficients; above this the
    window keeps only step times and sizes and coefficients are read from HBM */
-#define DDE_WIN_COEF_BUDGET (72 * 1024)
+#define DDE_WIN_COEF_BUDGET (72 * 1024 * (DDE_TPB / 128))
 
 namespace dde {
 
@@ -72,6 +74,8 @@ enum {
   DDE_F_TT,
   DDE_F_DQ_LO,
   DDE_F_DQ_HI,
+  DDE_F_MEMO_T,   /* a lag query answered ahead of the evaluation that makes it ... */
+  DDE_F_MEMO_V,   /* ... and its value (lag_prefetch_value) */
   DDE_F_WT,       /* DDE_WIN rows */
   DDE_F_WH = DDE_F_WT + DDE_WIN,
   DDE_F_COUNT64 = DDE_F_WH + DDE_WIN,
@@ -167,15 +171,25 @@ __shared__ int s_dctx32[DDE_DI_COUNT32][DDE_TPB];
 #define s_tt (s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
 #define s_dq_lo (s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
 #define s_dq_hi (s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
+/* A model that declares its lags (M::lags, dde_model_def.h) has the queries of a whole
+ * step attempt answered up front, next to each other (lag_prefetch_value); the
+ * integrator hands the evaluation the predicted query time and its value, and ylag_1
+ * returns the value when the model asks for exactly that time -- bit for bit -- and
+ * component.  Anything else takes the ordinary path.  NaN: nothing predicted. */
+#define s_memo_t (s_ctx64[::dde::DDE_F_MEMO_T])
+#define s_memo_v (s_ctx64[::dde::DDE_F_MEMO_V])
+/* bit 25 of the per-thread cfg word: the kernel fills the memo */
+#define DDE_CFG_MEMO (1 << 25)
 /* [DDE_WIN][order * n][DDE_TPB] when staged (difeq: the on-chip history) */
 #define s_wc (::dde::dde_smem + DDE_CTX_BYTES / sizeof(double))
 
 #ifdef DDE_LAG_STATS
 /* debug build only: [0] misses above, [1] misses below, [2] misses on an empty
    window, [3] entries appended by lag_window_ensure, [4] failures, [5] ring
-   probes of the search, [6] queries answered from the ring directly */
+   probes of the search, [6] queries answered from the ring directly, [7] queries
+   answered ahead (the memo), [8] queries of a memo kernel that were not */
 static __device__ unsigned long long dde_lag_stats[16];
-#define DDE_LAG_COUNT(i) atomicAdd(&dde_lag_stats[i], 1ULL)
+#define DDE_LAG_COUNT(i) atomicAdd(&::dde::dde_lag_stats[i], 1ULL)
 #ifdef DDE_LAG_TRACE_PRINT
 #include <stdio.h>
 #define DDE_LAG_TRACE(...) printf(__VA_ARGS__)
@@ -184,7 +198,7 @@ static __device__ unsigned long long dde_lag_stats[16];
 #endif
 /* the same build checks every ring / window index it forms (compute-sanitizer
    is not available on the GPU pool): violations are counted in slot [15] */
-#define DDE_CHECK(cond) ((cond) ? (void) 0 : (void) atomicAdd(&dde_lag_stats[15], 1ULL))
+#define DDE_CHECK(cond) ((cond) ? (void) 0 : (void) atomicAdd(&::dde::dde_lag_stats[15], 1ULL))
 #else
 #define DDE_CHECK(cond) ((void) 0)
 #define DDE_LAG_TRACE(...) ((void) 0)
@@ -291,10 +305,7 @@ __device__ __forceinline__ void lag_window_evict(int s, unsigned &base, unsigned
  * highest one (or is full).  Purely a prefetch: any query it fails to
  * anticipate still finds its entry through the slow path. */
 template <int NCOEF_MAX, bool EXACT>
-__device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double att_hi) {
-  s_att_lo[s] = att_lo;
-  const double need_hi = att_hi + s_dq_hi[s];
-  const double need_lo = att_lo + s_dq_lo[s];
+__device__ __forceinline__ void lag_window_ensure_range(int s, double need_lo, double need_hi) {
   unsigned wn = s_wn[s];
   const bool live = need_lo <= need_hi && wn > 0; /* else: nothing learnt yet */
   unsigned base = s_wbase[s];
@@ -361,6 +372,14 @@ __device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double a
     s_wn[s] = wn;
     s_wtop[s] = wtop;
   }
+}
+
+/* ... where the range comes from the offsets (query time - evaluation time) the
+ * queries seen so far had: learnt from misses, -tau for a constant lag. */
+template <int NCOEF_MAX, bool EXACT>
+__device__ __forceinline__ void lag_window_ensure(int s, double att_lo, double att_hi) {
+  s_att_lo[s] = att_lo;
+  lag_window_ensure_range<NCOEF_MAX, EXACT>(s, att_lo + s_dq_lo[s], att_hi + s_dq_hi[s]);
 }
 
 /* Bookkeeping after the integrating thread has written the head entry to
@@ -615,6 +634,163 @@ __device__ __forceinline__ double interp_entry(const double *c, int order, int s
   return order == 5 ? interp5(stride, theta, theta1, c) : interp853(stride, theta, theta1, c);
 }
 
+/* a / b exactly as the compiler's double-precision division computes it on its fast
+ * path -- the same instruction sequence (reciprocal seed with the low word set to 1,
+ * two Newton steps, quotient, one correction; compare the SASS of any `/`) -- but
+ * without its branch: *ok tells whether the compiler's code would have stayed on that
+ * path (the numerator not tiny, the quotient normal and finite).  The caller does
+ * something else, with the ordinary `/`, when it is false.  Branch-free, so that
+ * several independent look-ups schedule next to each other. */
+__device__ __forceinline__ double dde_div_fast(double a, double b, bool *ok) {
+#ifdef DDE_HOST_EMU
+  const double res = a / b;
+#else
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(b));
+  y0 = __hiloint2double(__double2hiint(y0), 1);
+  double e = fma(y0, -b, 1.0);
+  e = fma(e, e, e);
+  const double y1 = fma(y0, e, y0);
+  const double e2 = fma(y1, -b, 1.0);
+  const double y2 = fma(y1, e2, y1);
+  const double q = a * y2;
+  const double r = fma(q, -b, a);
+  const double res = fma(y2, r, q);
+#endif
+  const float ah = __int_as_float(__double2hiint(a));
+  const float chk = fmaf(0.0f, __int_as_float(__double2hiint(b)), __int_as_float(__double2hiint(res)));
+  *ok = (fabsf(ah) >= 6.5827683646048100446e-37f) && (fabsf(chk) > 1.469367938527859385e-39f);
+  return res;
+}
+
+/* What the look-ups of one step attempt share: the window's start times, its end, the
+ * pre-history, in registers. */
+struct LagWin {
+  double wt[DDE_WIN];
+  double wtop, t0s, y0v, sign;
+  unsigned wbase;
+};
+
+__device__ __forceinline__ void lag_win_read(int s, LagWin &w) {
+#pragma unroll
+  for (int k = 0; k < DDE_WIN; ++k) {
+    w.wt[k] = s_wt[k][s];
+  }
+  w.wtop = s_wtop[s];
+  w.t0s = s_t0[s];
+  w.y0v = s_y0_value[s];
+  w.sign = s_lag_u.sign;
+  w.wbase = s_wbase[s];
+}
+
+/* The values ylag_1(tq[q], 0), q = 0 .. G-1, of a one-equation system would return,
+ * from the staged window, without a branch and without side effects; bit q of the
+ * result tells whether z[q] is that value -- or is not to be had that way (the entry
+ * is not in the window, there is no entry, an irregular division): the evaluation then
+ * asks in the ordinary way.  The arithmetic is that of find_time + lag_eval above,
+ * operation for operation (src/dopri.c:582-598,776-788); it is written one operation
+ * at a time ACROSS the G queries, so that the instruction stream holds G independent
+ * dependency chains next to each other (the look-up of a single query is one chain of
+ * ~30 dependent operations at ~9 cycles each, profiles/r2a_fp64_lat.txt). */
+template <int ORDER, int G>
+__device__ __forceinline__ unsigned lag_prefetch_group(int s, const LagWin &w, const double (&tq)[G],
+                                                       double (&z)[G]) {
+  double st[G];
+  unsigned below[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    st[q] = w.sign * tq[q];
+    below[q] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < DDE_WIN; ++k) {
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      below[q] += st[q] >= w.wt[k] ? 1u : 0u;
+    }
+  }
+  const double *c[G];
+  double num[G], hh[G];
+  unsigned good = 0, pre = 0;
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    /* entry wbase + below - 1, in slot (that) % DDE_WIN: in range whatever `below` is */
+    const unsigned slot = (w.wbase + below[q] - 1u) % DDE_WIN;
+    pre |= st[q] <= w.t0s ? 1u << q : 0u; /* src/dopri.c:777-778 */
+    good |= (below[q] > 0) & (st[q] < w.wtop) ? 1u << q : 0u;
+    c[q] = s_wc + (size_t) slot * ORDER * DDE_TPB + s;
+    num[q] = s_wt[slot][s];
+    hh[q] = s_wh[slot][s];
+  }
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    num[q] = tq[q] - w.sign * num[q];
+  }
+  /* theta = num / hh: dde_div_fast, step by step across the queries */
+  double theta[G], theta1[G];
+#ifdef DDE_HOST_EMU
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    theta[q] = num[q] / hh[q];
+  }
+#else
+  {
+    double y0[G], e[G], y1[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[q]) : "d"(hh[q]));
+      y0[q] = __hiloint2double(__double2hiint(y0[q]), 1);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) e[q] = fma(y0[q], -hh[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < G; ++q) e[q] = fma(e[q], e[q], e[q]);
+#pragma unroll
+    for (int q = 0; q < G; ++q) y1[q] = fma(y0[q], e[q], y0[q]);
+#pragma unroll
+    for (int q = 0; q < G; ++q) e[q] = fma(y1[q], -hh[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < G; ++q) y1[q] = fma(y1[q], e[q], y1[q]);
+#pragma unroll
+    for (int q = 0; q < G; ++q) theta[q] = num[q] * y1[q];
+#pragma unroll
+    for (int q = 0; q < G; ++q) e[q] = fma(theta[q], -hh[q], num[q]);
+#pragma unroll
+    for (int q = 0; q < G; ++q) theta[q] = fma(y1[q], e[q], theta[q]);
+  }
+#endif
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    /* would the compiler's division have stayed on its fast path? (dde_div_fast) */
+    const float ah = __int_as_float(__double2hiint(num[q]));
+    const float chk = fmaf(0.0f, __int_as_float(__double2hiint(hh[q])),
+                           __int_as_float(__double2hiint(theta[q])));
+    const bool dok =
+        (fabsf(ah) >= 6.5827683646048100446e-37f) && (fabsf(chk) > 1.469367938527859385e-39f);
+    good &= dok ? ~0u : ~(1u << q);
+    theta1[q] = 1 - theta[q];
+  }
+  /* the dense-output polynomial (src/dopri_5.c:120-127, src/dopri_853.c:369-380), innermost
+     coefficient first: c[k] + (k even ? theta : theta1) * (...) */
+  double acc[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    acc[q] = c[q][(size_t) (ORDER - 1) * DDE_TPB];
+  }
+#pragma unroll
+  for (int k = ORDER - 2; k >= 0; --k) {
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      acc[q] = c[q][(size_t) k * DDE_TPB] + (k % 2 == 0 ? theta[q] : theta1[q]) * acc[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    z[q] = (pre >> q) & 1u ? w.y0v : acc[q];
+  }
+  return pre | good;
+}
+
 /* Components idx[0..nidx) (NULL: 0..nidx-1) of the dense output of the entry
  * `hit` at time t, src/dopri.c:582-666.  Two copies so that the staged
  * window is read with shared-memory loads and the ring with global ones. */
@@ -643,7 +819,27 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 
 /* ---- the model-facing functions (declared in <dde/dde.h>) -------------- */
 
+static __device__ __forceinline__ double dde_ylag_1_lookup(double t, size_t i);
+/* the ordinary look-up, out of line: what an evaluation falls back to when the query it
+   makes is not the one answered ahead of it */
+static __device__ __noinline__ double dde_ylag_1_unpredicted(double t, size_t i) {
+  return dde_ylag_1_lookup(t, i);
+}
+
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
+  const int s = threadIdx.x;
+  if (s_cfg[s] & DDE_CFG_MEMO) { /* a one-equation system whose kernel answers ahead */
+    if (t == s_memo_t[s]) {
+      DDE_LAG_COUNT(7);
+      return s_memo_v[s];
+    }
+    DDE_LAG_COUNT(8);
+    return dde_ylag_1_unpredicted(t, i);
+  }
+  return dde_ylag_1_lookup(t, i);
+}
+
+static __device__ __forceinline__ double dde_ylag_1_lookup(double t, size_t i) {
   const int s = threadIdx.x;
   if (dde::s_lag_u.sign * t <= s_t0[s]) {
     return (s_cfg[s] & 0xffff) == 1 ? s_y0_value[s] : s_y0[s][i];

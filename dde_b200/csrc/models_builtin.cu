@@ -17,7 +17,7 @@
 /*                         name            deriv           n  n_parms  output        n_out */
 DDE_REGISTER_DOPRI_OUTPUT(lorenz,         lorenz,         3, 3,       lorenz_output, 2)
 DDE_REGISTER_DOPRI(       rossler,        rossler,        3, 3)
-DDE_REGISTER_DOPRI(       mackey_glass,   mackey_glass,   1, 3)
+DDE_REGISTER_DOPRI_LAGS(  mackey_glass,   mackey_glass,   1, 3,       mackey_glass_lags, 1)
 DDE_REGISTER_DOPRI_OUTPUT(seir,           seir,           4, -1,      seir_output,   1)
 DDE_REGISTER_DOPRI_OUTPUT(seir_int,       seir_int,       4, -1,      seir_output,   1)
 /* the reference's growth fixtures come with five event functions */

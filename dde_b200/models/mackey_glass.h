@@ -11,3 +11,9 @@ DDE_MODEL_FN void mackey_glass(size_t n, double t, const double *y,
   const double ylag = ylag_1(t - 17.0, 0);
   dydt[0] = beta * ylag / (1.0 + pow(ylag, expo)) - gamma * y[0];
 }
+
+/* The one time at which mackey_glass(t, ...) reads the history (optional: lets the
+ * solver answer a step attempt's look-ups ahead of its evaluations, dde_model_def.h). */
+DDE_MODEL_FN void mackey_glass_lags(double t, const void *data, double *tlag) {
+  tlag[0] = t - 17.0;
+}

@@ -6,5 +6,5 @@ cd "$(dirname "$0")"
 g++ -O2 -g -std=c++17 -fPIC -mfma -ffp-contract=off -Wall -Wno-unused-function \
     -Wno-unused-variable -Wno-unused-but-set-variable -Wno-unknown-pragmas -Wno-sign-compare \
     ${DDE_EMU_EXTRA:-} -I. -I../../include -I../../dde_b200/csrc \
-    -shared -o ${DDE_EMU_OUT:-libdde_emu.so} emu_driver.cpp -lm
+    -fvisibility=hidden -Wl,-Bsymbolic -shared -o ${DDE_EMU_OUT:-libdde_emu.so} emu_driver.cpp -lm
 echo "built tests/emu/${DDE_EMU_OUT:-libdde_emu.so}"

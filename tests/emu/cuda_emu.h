@@ -45,6 +45,8 @@ static emu_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1
 #define __builtin_assume(x) ((void) 0)
 
 static inline void __syncthreads() {}
+static inline int __syncthreads_and(int p) { return p; }
+static inline int __syncthreads_or(int p) { return p; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
@@ -83,6 +85,9 @@ static inline long long __double_as_longlong(double d) {
   return v;
 }
 static inline int __double2hiint(double d) { return (int) (__double_as_longlong(d) >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+  return __longlong_as_double((long long) (((unsigned long long) (unsigned) hi << 32) | (unsigned) lo));
+}
 static inline float __int_as_float(int v) {
   float f;
   memcpy(&f, &v, sizeof f);

@@ -21,6 +21,7 @@
 #include <dde/dde.h>
 
 #include "dopri_kernels.cuh"
+#include "dopri_lag1_kernel.cuh"
 #include "dde_model_def.h"
 
 #define pow(x, y) dde_pow((x), (y))
@@ -33,12 +34,8 @@
 
 DDE_DEFINE_DOPRI_MODEL(lorenz, lorenz, 3, 3, lorenz_output, 2, DDE_NO_EVENTS, 0)
 DDE_DEFINE_DOPRI_MODEL(rossler, rossler, 3, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0)
-#ifdef DDE_EMU_MG_LAGS
 DDE_DEFINE_DOPRI_MODEL_LAGS(mackey_glass, mackey_glass, 1, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0,
                             mackey_glass_lags, 1)
-#else
-DDE_DEFINE_DOPRI_MODEL(mackey_glass, mackey_glass, 1, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0)
-#endif
 DDE_DEFINE_DOPRI_MODEL(seir, seir, 4, -1, seir_output, 1, DDE_NO_EVENTS, 0)
 
 namespace {
@@ -77,10 +74,21 @@ void run_model(dde::DopriArgs a) {
 
 } /* namespace */
 
+/* the library is built with hidden visibility and -Bsymbolic so that its instantiations of
+   the kernel templates cannot be interposed by the product library's launch stubs of the
+   same names when both are loaded into one process */
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *emu_last_message(void) { return g_message.c_str(); }
 double emu_last_seconds(void) { return 0.0; }
+
+#ifdef DDE_LAG_STATS
+void emu_lag_stats(unsigned long long *out) {
+  memcpy(out, dde::dde_lag_stats, sizeof dde::dde_lag_stats);
+  memset(dde::dde_lag_stats, 0, sizeof dde::dde_lag_stats);
+}
+#endif
 
 /* mode: the stepping kernel's MODE template argument (dopri_kernels.cuh) */
 static int g_mode = -1;
@@ -160,13 +168,20 @@ int emu_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, s
     }                                      \
   } while (0)
   if (name == "mackey_glass") {
-    const int mode = g_mode >= 0 ? g_mode : (hist ? 2 : 1);
+    const int mode = g_mode >= 0 ? g_mode : (hist ? 4 : 1);
     if (mode == 0) {
       EMU_RUN(dde_dopri_model_mackey_glass, 0);
     } else if (mode == 1) {
       EMU_RUN(dde_dopri_model_mackey_glass, 1);
-    } else {
+    } else if (mode == 2) {
       EMU_RUN(dde_dopri_model_mackey_glass, 2);
+    } else if (mode == 3 || method == 0) {
+      EMU_RUN(dde_dopri_model_mackey_glass, 3);
+    } else { /* 4: dopri_lag1_kernel (dop853 only) */
+      a.win_staged = 1;
+      const unsigned init_grid = (unsigned) ((a.n_traj + DDE_TPB - 1) / DDE_TPB);
+      run_grid(dde::dopri_init_kernel<dde_dopri_model_mackey_glass, 1>, a, init_grid, DDE_TPB);
+      run_grid(dde::dopri_lag1_kernel<dde_dopri_model_mackey_glass>, a, 1, 1);
     }
   } else if (name == "lorenz") {
     const int mode = g_mode >= 0 ? g_mode : (hist ? 0 : 1);
@@ -192,3 +207,4 @@ int emu_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, s
 }
 
 } /* extern "C" */
+#pragma GCC visibility pop

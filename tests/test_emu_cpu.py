@@ -24,7 +24,7 @@ def compare(got, want):
 
 
 @needs_oracle
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4])
 def test_mackey_glass(mode):
     model, y0, parms, times, kw = workloads.mackey_glass(192)
     got = pyemu.dopri_batch(model, y0, times, parms, mode=mode, **kw)
@@ -62,3 +62,36 @@ def test_lorenz_sweep(mode):
     want = pyoracle.dopri_batch("oracle", model, y0, times, parms, n_out=2, **kw)
     compare(got, want)
     assert_bits_equal(got.output, want.output, "output")
+
+
+@needs_oracle
+@pytest.mark.parametrize("kwargs", [
+    dict(tcrit=np.array([17.0, 34.0, 51.0, 400.0])),
+    dict(stiff_check=1),
+    dict(step_size_max=0.5, step_max_n=400),
+    dict(step_size_min=0.05, step_size_min_allow=True),
+    dict(step_size_min=0.05),
+    dict(step_size_initial=0.01),
+    dict(rtol=1e-9, atol=1e-9, n_history=200),
+    dict(return_initial=False),
+])
+def test_mackey_glass_lag1_kernel_options(kwargs):
+    """dopri_lag1_kernel (dop853, declared lag) under the controls that steer its branches"""
+    model, y0, parms, times, kw = workloads.mackey_glass(40)
+    kwargs = dict(kwargs)
+    tcrit = kwargs.pop("tcrit", None)
+    kw = dict(kw, **kwargs)
+    got = pyemu.dopri_batch(model, y0, times, parms, tcrit=tcrit, mode=4, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, tcrit=tcrit, **kw)
+    compare(got, want)
+
+
+@needs_oracle
+def test_mackey_glass_lag1_kernel_backward_time():
+    """integrating backwards: the reference's dop853 error norm goes negative there
+    (SURVEY.md A.1#1) and the run ends in ERR_STEP_SIZE_TOO_SMALL / VANISHED -- same here"""
+    model, y0, parms, times, kw = workloads.mackey_glass(16)
+    times = -times
+    got = pyemu.dopri_batch(model, y0, times, parms, mode=4, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
+    compare(got, want)
