@@ -32,7 +32,7 @@
 
 #include "difeq_kernels.cuh"
 #include "dopri_kernels.cuh"
-#include "dopri_lag1_kernel.cuh"
+#include "dopri_dde1_kernel.cuh"
 #include "registry.h"
 #include "dde_model_def.h"
 
@@ -65,9 +65,9 @@ inline int persistent_grid(Kernel kernel, long long n_items, int device_sms, siz
   return (int) (grid < 1 ? 1 : grid);
 }
 
-/* stands in for a model dopri_lag1_kernel cannot take, so that the template is only
+/* stands in for a model dopri_dde1_kernel cannot take, so that the template is only
    instantiated for models it can (the branch that would launch it is never taken) */
-struct Lag1Placeholder {
+struct Dde1Placeholder {
   static constexpr int N = 1, NP = 0, N_OUT = 0, N_EVENTS = 0, N_LAGS = 1;
   static __device__ __forceinline__ void lags(double t, const void *, double *tlag) { tlag[0] = t; }
   static __device__ __forceinline__ void deriv(size_t, double, const double *, double *dydt,
@@ -122,22 +122,16 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
   if (CAN_CALL && args.n_history > 0) {
     kernel = dopri_tpt_kernel<M, METHOD, CAN_CALL ? 2 : 0>;
   }
-#ifdef DDE_LAGS_AHEAD /* measured slower (13.0 M against 16.6 M trajectories/s): off */
-  /* ... and the model declares its lag (M::lags): the look-ups of a step attempt are
-     answered together, ahead of the evaluations (dopri_kernels.cuh, MODE 3) */
-  constexpr bool CAN_AHEAD = CAN_CALL && M::N_LAGS == 1;
-  if (CAN_AHEAD && args.n_history > 0 && args.win_staged) {
-    kernel = dopri_tpt_kernel<M, METHOD, CAN_AHEAD ? 3 : 0>;
-  }
 #endif
-#endif
-#ifdef DDE_LAG1_KERNEL /* measured slower (12.1 M): off */
-  /* dop853 of one delay equation with a declared lag: the data-driven stage loop with
-     its stage values in shared memory (dopri_lag1_kernel.cuh) */
-  constexpr bool CAN_LAG1 = M::N == 1 && M::NP >= 0 && M::NP <= 8 && M::N_LAGS == 1 && METHOD == 1;
-  if (CAN_LAG1 && args.n_history > 0 && args.win_staged) {
-    kernel = dopri_lag1_kernel<typename std::conditional<CAN_LAG1, M, Lag1Placeholder>::type>;
-    dyn += DDE_L1_SMEM_BYTES;
+#ifndef DDE_NO_DDE1_KERNEL
+  /* dop853 of one delay equation with a declared lag, the plain case (forward, fresh
+     start, no critical times, output function or stiffness test): dopri_dde1_kernel.cuh */
+  constexpr bool CAN_DDE1 =
+      M::N == 1 && M::NP >= 0 && M::NP <= 8 && M::N_LAGS == 1 && METHOD == 1;
+  if (CAN_DDE1 && args.n_history > 0 && args.sign > 0 && !args.restart && args.n_tcrit == 0 &&
+      args.n_out == 0 && args.stiff_check == 0) {
+    kernel = dopri_dde1_kernel<typename std::conditional<CAN_DDE1, M, Dde1Placeholder>::type>;
+    dyn = DDE1_SMEM_BYTES;
   }
 #endif
   err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);

@@ -159,63 +159,6 @@ static __device__ __noinline__ DdeVec<NMAX> dde_deriv_call(double tt, DdeVec<NMA
   return kt;
 }
 
-/* ... with one lag query answered ahead (MODE 3): ylag_1 finds the predicted query time
-   and its value in the thread's memo (lag_ctx.cuh); the compiler forwards both from the
-   stores below, so a predicted query costs one comparison */
-template <class M, int NMAX, int PMAX, int CFG>
-static __device__ __noinline__ DdeVec<NMAX> dde_deriv_call_memo(double tt, DdeVec<NMAX> yin,
-                                                                DdeVec<PMAX> p, double tq,
-                                                                double zq) {
-  const int s = threadIdx.x;
-  s_tt[s] = tt;
-  s_memo_t[s] = tq;
-  s_memo_v[s] = zq;
-  __builtin_assume(s_cfg[s] == CFG);
-  DdeVec<NMAX> kt;
-  M::deriv((size_t) NMAX, tt, yin.v, kt.v, p.v);
-  return kt;
-}
-
-/* Time of right-hand-side evaluation j of a step (attempt: 0 .. 5 dopri5, 0 .. 10 dop853;
- * accepted dop853 steps go on with 11 .. 15): src/dopri_5.c:54-80, src/dopri_853.c:178-240,
- * src/dopri.c:400-403, src/dopri_853.c:304,330-347.  The one place these are written, so
- * that a look-up made ahead of an evaluation sees the evaluation's time bit for bit. */
-template <int METHOD>
-__device__ __forceinline__ double stage_time(int j, double t, double h) {
-  if (METHOD == 0) {
-    switch (j) {
-      case 0: return t + DP5_C2 * h;
-      case 1: return t + DP5_C3 * h;
-      case 2: return t + DP5_C4 * h;
-      case 3: return t + DP5_C5 * h;
-      default: return t + h;
-    }
-  }
-  switch (j) {
-    case 0: return t + DP8_C2 * h;
-    case 1: return t + DP8_C3 * h;
-    case 2: return t + DP8_C4 * h;
-    case 3: return t + DP8_C5 * h;
-    case 4: return t + DP8_C6 * h;
-    case 5: return t + DP8_C7 * h;
-    case 6: return t + DP8_C8 * h;
-    case 7: return t + DP8_C9 * h;
-    case 8: return t + DP8_C10 * h;
-    case 9: return t + DP8_C11 * h;
-    case 11: return t;
-    case 13: return t + DP8_C14 * h;
-    case 14: return t + DP8_C15 * h;
-    case 15: return t + DP8_C16 * h;
-    default: return t + h; /* 10, 12 */
-  }
-}
-
-/* evaluation j asks the history at the same time as evaluation stage_alias(j) < j did */
-template <int METHOD>
-__device__ __forceinline__ constexpr int stage_alias(int j) {
-  return METHOD == 0 ? (j == 5 ? 4 : j) : (j == 12 ? 10 : j);
-}
-
 template <class M, int METHOD, int MODE = 0>
 __global__ void
 __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS
@@ -225,10 +168,6 @@ __launch_bounds__(DDE_TPB, (M::N == 1 ? DDE_MIN_BLOCKS
                                                            : DDE_MIN_BLOCKS_SMALL)))
 dopri_tpt_kernel(const DopriArgs a) {
   constexpr bool UNROLLED = MODE != 0;
-  /* MODE 3: MODE 2 for a model that declares its lags (M::lags): the look-ups of a
-     whole step attempt are answered up front, next to each other (independent chains
-     the FP64 pipe overlaps), and each evaluation finds its answer in the memo */
-  constexpr bool AHEAD = MODE == 3;
   constexpr int NC = M::N;
   constexpr int NMAX = NC > 0 ? NC : DDE_DYN_MAXN;
   constexpr int PMAX = M::NP > 0 ? M::NP : (M::NP == 0 ? 1 : DDE_DYN_MAXP);
@@ -242,9 +181,6 @@ dopri_tpt_kernel(const DopriArgs a) {
   /* window coefficients staged in shared memory (decided by the shape alone) */
   constexpr bool STAGED =
       NC > 0 && sizeof(double) * DDE_WIN * ORDER * NC * DDE_TPB <= DDE_WIN_COEF_BUDGET;
-  static_assert(!AHEAD || (NC == 1 && M::N_LAGS == 1 && STAGED),
-                "answering ahead: one equation, one declared lag, window in shared memory");
-  constexpr int CFG = NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24) | (AHEAD ? DDE_CFG_MEMO : 0);
   const int n = NC > 0 ? NC : a.n;
   const int n_parms = M::NP >= 0 ? M::NP : a.n_parms;
   const int n_out = M::N_OUT == 0 ? 0 : a.n_out; /* 0 = output function not requested */
@@ -371,10 +307,6 @@ dopri_tpt_kernel(const DopriArgs a) {
       s_count[s] = rs.count;
       s_head[s] = rs.head;
       lag_window_reset(s);
-      if (AHEAD) {
-        s_cfg[s] = CFG;
-        s_memo_t[s] = na_real();
-      }
       s_code[s] = 0; /* NOT_SET */
       s_error[s] = 0;
 
@@ -442,47 +374,9 @@ dopri_tpt_kernel(const DopriArgs a) {
         last = true;
       }
       ++n_step;
-      if (AHEAD) {
-        /* the window follows the declared lag: [lags(t), lags(t + h)] */
-        double la[1], lb[1];
-        M::lags(t, p, la);
-        M::lags(t + h, p, lb);
-        s_att_lo[s] = sign * t;
-        lag_window_ensure_range<ORDER * NMAX, true>(s, fmin(sign * la[0], sign * lb[0]),
-                                                    fmax(sign * la[0], sign * lb[0]));
-      } else if (MODE != 1 && a.n_history > 0) { /* MODE 1 is launched without a ring */
+      if (MODE != 1 && a.n_history > 0) { /* MODE 1 is launched without a ring */
         /* top up the staged lag window while the warp is in step */
         lag_window_ensure<ORDER * NMAX, (NC > 0)>(s, sign * t, sign * (t + h));
-      }
-    }
-    /* MODE 3: the attempt's look-ups, all at once: zq[j] answers evaluation j's query,
-       bit j of zok tells whether it could be answered from the window */
-    double zq[AHEAD ? NST : 1];
-    unsigned zok = 0;
-    if (AHEAD && run) {
-      LagWin w;
-      lag_win_read(s, w);
-      /* evaluations 0 .. NST_STEP - 1 less the last of dopri5 (which asks what its
-         fifth asked): groups of four */
-      constexpr int NQ = METHOD == 0 ? 5 : 11;
-#pragma unroll
-      for (int j0 = 0; j0 < NQ; j0 += 4) {
-        if (j0 + 4 <= NQ) {
-          double tl[4], zz[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) M::lags(stage_time<METHOD>(j0 + q, t, h), p, &tl[q]);
-          zok |= lag_prefetch_group<ORDER, 4>(s, w, tl, zz) << j0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) zq[AHEAD ? j0 + q : 0] = zz[q];
-        } else {
-          constexpr int R = NQ % 4 == 0 ? 4 : NQ % 4;
-          double tl[R], zz[R];
-#pragma unroll
-          for (int q = 0; q < R; ++q) M::lags(stage_time<METHOD>(j0 + q, t, h), p, &tl[q]);
-          zok |= lag_prefetch_group<ORDER, R>(s, w, tl, zz) << j0;
-#pragma unroll
-          for (int q = 0; q < R; ++q) zq[AHEAD ? j0 + q : 0] = zz[q];
-        }
       }
     }
 
@@ -501,7 +395,7 @@ dopri_tpt_kernel(const DopriArgs a) {
       for (int i = 0; i < n; ++i) {
         yin[i] = y[i] + h * (METHOD == 0 ? DP5_A21 : DP8_A21) * k1[i];
       }
-      tt = stage_time<METHOD>(0, t, h);
+      tt = t + (METHOD == 0 ? DP5_C2 : DP8_C2) * h;
     }
 
     /* how many evaluations this lane takes part in: none, the attempt's, or --
@@ -516,23 +410,16 @@ dopri_tpt_kernel(const DopriArgs a) {
       /* -- 1. dopri_eval, src/dopri.c:831-835: the one hot copy of the model, on
             the stage input `yin` at time `tt` that the previous trip through the
             switch below (or the attempt's prologue) prepared -- */
-      if (MODE == 2 || MODE == 3) {
+      if (MODE == 2) {
         DdeVec<NMAX> vin;
         DdeVec<PMAX> vp;
 #pragma unroll
         for (int i = 0; i < NMAX; ++i) vin.v[i] = yin[i];
 #pragma unroll
         for (int i = 0; i < PMAX; ++i) vp.v[i] = p[i];
-        DdeVec<NMAX> vk;
-        if (AHEAD) {
-          const int zi = stage_alias<METHOD>(st);
-          double tl[1];
-          M::lags(tt, p, tl);
-          vk = dde_deriv_call_memo<M, NMAX, PMAX, CFG>(
-              tt, vin, vp, (zok >> zi) & 1u ? tl[0] : na_real(), zq[AHEAD ? zi : 0]);
-        } else {
-          vk = dde_deriv_call<M, NMAX, PMAX, CFG>(tt, vin, vp);
-        }
+        const DdeVec<NMAX> vk =
+            dde_deriv_call<M, NMAX, PMAX, (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24))>(tt, vin,
+                                                                                         vp);
 #pragma unroll
         for (int i = 0; i < NMAX; ++i) kt[i] = vk.v[i];
       } else {
@@ -540,7 +427,7 @@ dopri_tpt_kernel(const DopriArgs a) {
         if (NC > 0) {
           /* the lag functions read the method / width / staging flags from the
              thread's context: tell the optimiser what they will find */
-          __builtin_assume(s_cfg[s] == CFG);
+          __builtin_assume(s_cfg[s] == (NC | (ORDER << 16) | ((STAGED ? 1 : 0) << 24)));
         }
         M::deriv((size_t) n, tt, yin, kt, p);
       }
@@ -561,7 +448,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP5_A31 * k1[i] + DP5_A32 * k2[i]);
             }
-            tt = stage_time<0>(1, t, h);
+            tt = t + DP5_C3 * h;
             break;
           case 1:
 #pragma unroll
@@ -571,7 +458,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP5_A41 * k1[i] + DP5_A42 * k2[i] + DP5_A43 * k3[i]);
             }
-            tt = stage_time<0>(2, t, h);
+            tt = t + DP5_C4 * h;
             break;
           case 2:
 #pragma unroll
@@ -582,7 +469,7 @@ dopri_tpt_kernel(const DopriArgs a) {
               yin[i] = y[i] + h * (DP5_A51 * k1[i] + DP5_A52 * k2[i] + DP5_A53 * k3[i] +
                                    DP5_A54 * k4[i]);
             }
-            tt = stage_time<0>(3, t, h);
+            tt = t + DP5_C5 * h;
             break;
           case 3:
 #pragma unroll
@@ -623,7 +510,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A31 * k1[i] + DP8_A32 * k2[i]);
             }
-            tt = stage_time<1>(1, t, h);
+            tt = t + DP8_C3 * h;
             break;
           case 1:
 #pragma unroll
@@ -633,7 +520,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A41 * k1[i] + DP8_A43 * k3[i]);
             }
-            tt = stage_time<1>(2, t, h);
+            tt = t + DP8_C4 * h;
             break;
           case 2:
 #pragma unroll
@@ -643,7 +530,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A51 * k1[i] + DP8_A53 * k3[i] + DP8_A54 * k4[i]);
             }
-            tt = stage_time<1>(3, t, h);
+            tt = t + DP8_C5 * h;
             break;
           case 3:
 #pragma unroll
@@ -653,7 +540,7 @@ dopri_tpt_kernel(const DopriArgs a) {
             for (int i = 0; i < n; ++i) {
               yin[i] = y[i] + h * (DP8_A61 * k1[i] + DP8_A64 * k4[i] + DP8_A65 * k5[i]);
             }
-            tt = stage_time<1>(4, t, h);
+            tt = t + DP8_C6 * h;
             break;
           case 4:
 #pragma unroll
@@ -664,7 +551,7 @@ dopri_tpt_kernel(const DopriArgs a) {
               yin[i] = y[i] + h * (DP8_A71 * k1[i] + DP8_A74 * k4[i] + DP8_A75 * k5[i] +
                                    DP8_A76 * k6[i]);
             }
-            tt = stage_time<1>(5, t, h);
+            tt = t + DP8_C7 * h;
             break;
           case 5:
 #pragma unroll
@@ -675,7 +562,7 @@ dopri_tpt_kernel(const DopriArgs a) {
               yin[i] = y[i] + h * (DP8_A81 * k1[i] + DP8_A84 * k4[i] + DP8_A85 * k5[i] +
                                    DP8_A86 * k6[i] + DP8_A87 * k7[i]);
             }
-            tt = stage_time<1>(6, t, h);
+            tt = t + DP8_C8 * h;
             break;
           case 6:
 #pragma unroll
@@ -686,7 +573,7 @@ dopri_tpt_kernel(const DopriArgs a) {
               yin[i] = y[i] + h * (DP8_A91 * k1[i] + DP8_A94 * k4[i] + DP8_A95 * k5[i] +
                                    DP8_A96 * k6[i] + DP8_A97 * k7[i] + DP8_A98 * k8[i]);
             }
-            tt = stage_time<1>(7, t, h);
+            tt = t + DP8_C9 * h;
             break;
           case 7:
 #pragma unroll
@@ -698,7 +585,7 @@ dopri_tpt_kernel(const DopriArgs a) {
                                    DP8_A106 * k6[i] + DP8_A107 * k7[i] + DP8_A108 * k8[i] +
                                    DP8_A109 * k9[i]);
             }
-            tt = stage_time<1>(8, t, h);
+            tt = t + DP8_C10 * h;
             break;
           case 8:
 #pragma unroll
@@ -710,7 +597,7 @@ dopri_tpt_kernel(const DopriArgs a) {
                                    DP8_A116 * k6[i] + DP8_A117 * k7[i] + DP8_A118 * k8[i] +
                                    DP8_A119 * k9[i] + DP8_A1110 * k10[i]);
             }
-            tt = stage_time<1>(9, t, h);
+            tt = t + DP8_C11 * h;
             break;
           case 9:
 #pragma unroll
@@ -755,7 +642,7 @@ dopri_tpt_kernel(const DopriArgs a) {
                                    DP8_A149 * k9[i] + DP8_A1410 * k10[i] + DP8_A1411 * k2[i] +
                                    DP8_A1412 * k3[i] + DP8_A1413 * k4[i]);
             }
-            tt = stage_time<1>(13, t, h);
+            tt = t + DP8_C14 * h;
             break;
           case 13:
 #pragma unroll
@@ -767,7 +654,7 @@ dopri_tpt_kernel(const DopriArgs a) {
                                    DP8_A158 * k8[i] + DP8_A1511 * k2[i] + DP8_A1512 * k3[i] +
                                    DP8_A1513 * k4[i] + DP8_A1514 * k14[i]);
             }
-            tt = stage_time<1>(14, t, h);
+            tt = t + DP8_C15 * h;
             break;
           case 14:
 #pragma unroll
@@ -779,7 +666,7 @@ dopri_tpt_kernel(const DopriArgs a) {
                                    DP8_A168 * k8[i] + DP8_A169 * k9[i] + DP8_A1613 * k4[i] +
                                    DP8_A1614 * k14[i] + DP8_A1615 * k15[i]);
             }
-            tt = stage_time<1>(15, t, h);
+            tt = t + DP8_C16 * h;
             break;
           default: /* 15, src/dopri_853.c:306-327,350-366 */
 #pragma unroll
@@ -876,23 +763,6 @@ dopri_tpt_kernel(const DopriArgs a) {
               yin[i] = k5[i];
             }
             tt = t;
-            if (AHEAD) {
-              /* the look-ups of the accept-only evaluations (12 asks what 10 asked); the
-                 window may have moved since the attempt began: read it again */
-              LagWin w;
-              lag_win_read(s, w);
-              double tl[4], zz[4];
-              M::lags(stage_time<METHOD>(11, t, h), p, &tl[0]);
-              M::lags(stage_time<METHOD>(13, t, h), p, &tl[1]);
-              M::lags(stage_time<METHOD>(14, t, h), p, &tl[2]);
-              M::lags(stage_time<METHOD>(15, t, h), p, &tl[3]);
-              const unsigned okb = lag_prefetch_group<ORDER, 4>(s, w, tl, zz);
-              zq[AHEAD ? 11 : 0] = zz[0];
-              zq[AHEAD ? 13 : 0] = zz[1];
-              zq[AHEAD ? 14 : 0] = zz[2];
-              zq[AHEAD ? 15 : 0] = zz[3];
-              zok |= (okb & 1u) << 11 | (okb >> 1) << 13;
-            }
           }
         } else {
           /* rejected, src/dopri.c:495-509 */

@@ -64,59 +64,76 @@ __shared__ LagUniform s_lag_u;
 
 /* The per-thread part: ONE structure-of-arrays block, [field][thread], so that
  * every access is one thread-dependent base register plus an immediate offset
- * (conflict-free LDS/STS, no per-array address arithmetic).  64-bit fields: */
+ * (conflict-free LDS/STS, no per-array address arithmetic).  It starts with what the
+ * model-facing functions of EVERY dopri kernel read -- the error flag, the return code,
+ * the configuration word and the memo of a query answered ahead -- so that a kernel
+ * with a leaner context of its own (dopri_dde1_kernel.cuh) shares that head and
+ * nothing else.  First 32-bit block: */
 enum {
-  DDE_F_RING = 0, /* double *: this trajectory's ring base */
-  DDE_F_Y0,       /* const double *: pre-history state (src/dopri.c:777-778) */
-  DDE_F_T0,       /* sign * start time (src/dopri.c:186) */
-  DDE_F_WTOP,     /* the staged lag window, see below */
+  DDE_FI_ERROR = 0, /* obj->error */
+  DDE_FI_CODE,      /* obj->code */
+  DDE_FI_CFG,       /* per-thread copy of n | order << 16 | staged << 24 | flags */
+  DDE_FI_HEAD,      /* slot the next commit goes to */
+  DDE_FI_COUNT32A
+};
+/* 64-bit fields: */
+enum {
+  DDE_F_MEMO_T = 0, /* a lag query answered ahead of the evaluation that makes it ... */
+  DDE_F_MEMO_V,     /* ... and its value */
+  DDE_F_RING,       /* double *: this trajectory's ring base */
+  DDE_F_Y0,         /* const double *: pre-history state (src/dopri.c:777-778) */
+  DDE_F_T0,         /* sign * start time (src/dopri.c:186) */
+  DDE_F_WTOP,       /* the staged lag window, see below */
   DDE_F_ATT_LO,
   DDE_F_TT,
   DDE_F_DQ_LO,
   DDE_F_DQ_HI,
-  DDE_F_MEMO_T,   /* a lag query answered ahead of the evaluation that makes it ... */
-  DDE_F_MEMO_V,   /* ... and its value (lag_prefetch_value) */
-  DDE_F_WT,       /* DDE_WIN rows */
+  DDE_F_WT,         /* DDE_WIN rows */
   DDE_F_WH = DDE_F_WT + DDE_WIN,
   DDE_F_COUNT64 = DDE_F_WH + DDE_WIN,
 };
-/* 32-bit fields: */
+/* second 32-bit block: */
 enum {
-  DDE_FI_COUNT = 0, /* entries committed so far */
-  DDE_FI_HEAD,      /* slot the next commit goes to */
-  DDE_FI_CODE,      /* obj->code */
-  DDE_FI_ERROR,     /* obj->error */
-  DDE_FI_WBASE,
-  DDE_FI_WN,
-  DDE_FI_CFG,       /* per-thread copy of n | order << 16 | staged << 24 */
-  DDE_FI_COUNT32
+  DDE_FJ_COUNT = 0, /* entries committed so far */
+  DDE_FJ_WBASE,
+  DDE_FJ_WN,
+  DDE_FJ_SPARE,
+  DDE_FJ_COUNT32B
 };
-/* The block lives at the start of the kernel's dynamic shared memory, followed
- * by the 32-bit fields and then the staged coefficients (s_wc), so that the
- * whole per-thread state hangs off ONE thread-dependent base address; every
- * launch of a kernel that includes this file passes at least DDE_CTX_BYTES of
+/* The block lives at the start of the kernel's dynamic shared memory, followed by the
+ * staged coefficients (s_wc), so that the whole per-thread state hangs off ONE
+ * thread-dependent base address; every launch of a kernel that includes this file
+ * passes at least DDE_CTX_HEAD_BYTES (the shared head) or DDE_CTX_BYTES (all of it) of
  * dynamic shared memory. */
 #ifdef DDE_HOST_EMU /* tests/emu: the device code compiled by g++, one lane at a time */
-static double dde_smem[24 * 1024];
+alignas(16) static double dde_smem[24 * 1024];
 #else
-extern __shared__ double dde_smem[];
+extern __shared__ __align__(16) double dde_smem[];
 #endif
-#define DDE_CTX_BYTES \
-  (sizeof(double) * ::dde::DDE_F_COUNT64 * DDE_TPB + sizeof(int) * ::dde::DDE_FI_COUNT32 * DDE_TPB)
-static_assert((sizeof(int) * DDE_FI_COUNT32 * DDE_TPB) % sizeof(double) == 0, "s_wc alignment");
-#define s_ctx64 ((double (*)[DDE_TPB]) ::dde::dde_smem)
-#define s_ctx32 ((int (*)[DDE_TPB]) (::dde::dde_smem + ::dde::DDE_F_COUNT64 * DDE_TPB))
+#define DDE_CTX_HEAD_BYTES \
+  (sizeof(int) * ::dde::DDE_FI_COUNT32A * DDE_TPB + sizeof(double) * 2 * DDE_TPB)
+#define DDE_CTX_BYTES                                                                      \
+  (sizeof(int) * ::dde::DDE_FI_COUNT32A * DDE_TPB + sizeof(double) * ::dde::DDE_F_COUNT64 * DDE_TPB + \
+   sizeof(int) * ::dde::DDE_FJ_COUNT32B * DDE_TPB)
+static_assert((sizeof(int) * DDE_FI_COUNT32A * DDE_TPB) % 16 == 0, "s_ctx64 alignment");
+static_assert((sizeof(int) * DDE_FJ_COUNT32B * DDE_TPB) % 16 == 0, "s_wc alignment");
+#define s_ctx32a ((int (*)[DDE_TPB]) ::dde::dde_smem)
+#define s_ctx64 \
+  ((double (*)[DDE_TPB]) (::dde::dde_smem + ::dde::DDE_FI_COUNT32A * DDE_TPB / 2))
+#define s_ctx32b                                                                            \
+  ((int (*)[DDE_TPB]) (::dde::dde_smem + ::dde::DDE_FI_COUNT32A * DDE_TPB / 2 + \
+                       ::dde::DDE_F_COUNT64 * DDE_TPB))
 #define s_ring ((double **) s_ctx64[::dde::DDE_F_RING])
 #define s_y0 ((const double **) s_ctx64[::dde::DDE_F_Y0])
 /* dopri, n = 1: the pre-history VALUE itself sits in the Y0 field (no pointer
    to chase while other lanes of the warp wait) */
 #define s_y0_value (s_ctx64[::dde::DDE_F_Y0])
 #define s_t0 (s_ctx64[::dde::DDE_F_T0])
-#define s_cfg (s_ctx32[::dde::DDE_FI_CFG])
-#define s_count ((unsigned *) s_ctx32[::dde::DDE_FI_COUNT])
-#define s_head (s_ctx32[::dde::DDE_FI_HEAD])
-#define s_code (s_ctx32[::dde::DDE_FI_CODE])
-#define s_error (s_ctx32[::dde::DDE_FI_ERROR])
+#define s_cfg (s_ctx32a[::dde::DDE_FI_CFG])
+#define s_count ((unsigned *) s_ctx32b[::dde::DDE_FJ_COUNT])
+#define s_head (s_ctx32a[::dde::DDE_FI_HEAD])
+#define s_code (s_ctx32a[::dde::DDE_FI_CODE])
+#define s_error (s_ctx32a[::dde::DDE_FI_ERROR])
 
 /* A difference equation needs far less -- no lag window, no times -- and its
  * on-chip history is written every step: its context is a block of its own in
@@ -165,17 +182,17 @@ __shared__ int s_dctx32[DDE_DI_COUNT32][DDE_TPB];
 #define s_wt (&s_ctx64[::dde::DDE_F_WT])      /* [DDE_WIN][thread] sign-adjusted start times */
 #define s_wh (&s_ctx64[::dde::DDE_F_WH])      /* [DDE_WIN][thread] step sizes */
 #define s_wtop (s_ctx64[::dde::DDE_F_WTOP])
-#define s_wbase ((unsigned *) s_ctx32[::dde::DDE_FI_WBASE])
-#define s_wn ((unsigned *) s_ctx32[::dde::DDE_FI_WN])
+#define s_wbase ((unsigned *) s_ctx32b[::dde::DDE_FJ_WBASE])
+#define s_wn ((unsigned *) s_ctx32b[::dde::DDE_FJ_WN])
 #define s_att_lo (s_ctx64[::dde::DDE_F_ATT_LO]) /* sign * t of the attempt in progress */
 #define s_tt (s_ctx64[::dde::DDE_F_TT])       /* time of the RHS evaluation in progress */
 #define s_dq_lo (s_ctx64[::dde::DDE_F_DQ_LO]) /* lowest / highest query seen, relative to the time of */
 #define s_dq_hi (s_ctx64[::dde::DDE_F_DQ_HI]) /* the evaluation that made it (+inf / -inf: none yet) */
-/* A model that declares its lags (M::lags, dde_model_def.h) has the queries of a whole
- * step attempt answered up front, next to each other (lag_prefetch_value); the
- * integrator hands the evaluation the predicted query time and its value, and ylag_1
- * returns the value when the model asks for exactly that time -- bit for bit -- and
- * component.  Anything else takes the ordinary path.  NaN: nothing predicted. */
+/* A one-equation model that declares its lag (M::lags, dde_model_def.h) can run on a
+ * kernel that answers each evaluation's query itself, one evaluation ahead
+ * (dopri_dde1_kernel.cuh): the integrator hands the evaluation the declared query time
+ * and its value, and ylag_1 returns the value when the model asks for exactly that
+ * time, bit for bit. */
 #define s_memo_t (s_ctx64[::dde::DDE_F_MEMO_T])
 #define s_memo_v (s_ctx64[::dde::DDE_F_MEMO_V])
 /* bit 25 of the per-thread cfg word: the kernel fills the memo */
@@ -663,134 +680,6 @@ __device__ __forceinline__ double dde_div_fast(double a, double b, bool *ok) {
   return res;
 }
 
-/* What the look-ups of one step attempt share: the window's start times, its end, the
- * pre-history, in registers. */
-struct LagWin {
-  double wt[DDE_WIN];
-  double wtop, t0s, y0v, sign;
-  unsigned wbase;
-};
-
-__device__ __forceinline__ void lag_win_read(int s, LagWin &w) {
-#pragma unroll
-  for (int k = 0; k < DDE_WIN; ++k) {
-    w.wt[k] = s_wt[k][s];
-  }
-  w.wtop = s_wtop[s];
-  w.t0s = s_t0[s];
-  w.y0v = s_y0_value[s];
-  w.sign = s_lag_u.sign;
-  w.wbase = s_wbase[s];
-}
-
-/* The values ylag_1(tq[q], 0), q = 0 .. G-1, of a one-equation system would return,
- * from the staged window, without a branch and without side effects; bit q of the
- * result tells whether z[q] is that value -- or is not to be had that way (the entry
- * is not in the window, there is no entry, an irregular division): the evaluation then
- * asks in the ordinary way.  The arithmetic is that of find_time + lag_eval above,
- * operation for operation (src/dopri.c:582-598,776-788); it is written one operation
- * at a time ACROSS the G queries, so that the instruction stream holds G independent
- * dependency chains next to each other (the look-up of a single query is one chain of
- * ~30 dependent operations at ~9 cycles each, profiles/r2a_fp64_lat.txt). */
-template <int ORDER, int G>
-__device__ __forceinline__ unsigned lag_prefetch_group(int s, const LagWin &w, const double (&tq)[G],
-                                                       double (&z)[G]) {
-  double st[G];
-  unsigned below[G];
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    st[q] = w.sign * tq[q];
-    below[q] = 0;
-  }
-#pragma unroll
-  for (int k = 0; k < DDE_WIN; ++k) {
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      below[q] += st[q] >= w.wt[k] ? 1u : 0u;
-    }
-  }
-  const double *c[G];
-  double num[G], hh[G];
-  unsigned good = 0, pre = 0;
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    /* entry wbase + below - 1, in slot (that) % DDE_WIN: in range whatever `below` is */
-    const unsigned slot = (w.wbase + below[q] - 1u) % DDE_WIN;
-    pre |= st[q] <= w.t0s ? 1u << q : 0u; /* src/dopri.c:777-778 */
-    good |= (below[q] > 0) & (st[q] < w.wtop) ? 1u << q : 0u;
-    c[q] = s_wc + (size_t) slot * ORDER * DDE_TPB + s;
-    num[q] = s_wt[slot][s];
-    hh[q] = s_wh[slot][s];
-  }
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    num[q] = tq[q] - w.sign * num[q];
-  }
-  /* theta = num / hh: dde_div_fast, step by step across the queries */
-  double theta[G], theta1[G];
-#ifdef DDE_HOST_EMU
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    theta[q] = num[q] / hh[q];
-  }
-#else
-  {
-    double y0[G], e[G], y1[G];
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[q]) : "d"(hh[q]));
-      y0[q] = __hiloint2double(__double2hiint(y0[q]), 1);
-    }
-#pragma unroll
-    for (int q = 0; q < G; ++q) e[q] = fma(y0[q], -hh[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < G; ++q) e[q] = fma(e[q], e[q], e[q]);
-#pragma unroll
-    for (int q = 0; q < G; ++q) y1[q] = fma(y0[q], e[q], y0[q]);
-#pragma unroll
-    for (int q = 0; q < G; ++q) e[q] = fma(y1[q], -hh[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < G; ++q) y1[q] = fma(y1[q], e[q], y1[q]);
-#pragma unroll
-    for (int q = 0; q < G; ++q) theta[q] = num[q] * y1[q];
-#pragma unroll
-    for (int q = 0; q < G; ++q) e[q] = fma(theta[q], -hh[q], num[q]);
-#pragma unroll
-    for (int q = 0; q < G; ++q) theta[q] = fma(y1[q], e[q], theta[q]);
-  }
-#endif
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    /* would the compiler's division have stayed on its fast path? (dde_div_fast) */
-    const float ah = __int_as_float(__double2hiint(num[q]));
-    const float chk = fmaf(0.0f, __int_as_float(__double2hiint(hh[q])),
-                           __int_as_float(__double2hiint(theta[q])));
-    const bool dok =
-        (fabsf(ah) >= 6.5827683646048100446e-37f) && (fabsf(chk) > 1.469367938527859385e-39f);
-    good &= dok ? ~0u : ~(1u << q);
-    theta1[q] = 1 - theta[q];
-  }
-  /* the dense-output polynomial (src/dopri_5.c:120-127, src/dopri_853.c:369-380), innermost
-     coefficient first: c[k] + (k even ? theta : theta1) * (...) */
-  double acc[G];
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    acc[q] = c[q][(size_t) (ORDER - 1) * DDE_TPB];
-  }
-#pragma unroll
-  for (int k = ORDER - 2; k >= 0; --k) {
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      acc[q] = c[q][(size_t) k * DDE_TPB] + (k % 2 == 0 ? theta[q] : theta1[q]) * acc[q];
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < G; ++q) {
-    z[q] = (pre >> q) & 1u ? w.y0v : acc[q];
-  }
-  return pre | good;
-}
-
 /* Components idx[0..nidx) (NULL: 0..nidx-1) of the dense output of the entry
  * `hit` at time t, src/dopri.c:582-666.  Two copies so that the staged
  * window is read with shared-memory loads and the ring with global ones. */
@@ -820,21 +709,26 @@ __device__ __forceinline__ void lag_eval(int s, const LagHit &hit, double t, con
 /* ---- the model-facing functions (declared in <dde/dde.h>) -------------- */
 
 static __device__ __forceinline__ double dde_ylag_1_lookup(double t, size_t i);
-/* the ordinary look-up, out of line: what an evaluation falls back to when the query it
-   makes is not the one answered ahead of it */
-static __device__ __noinline__ double dde_ylag_1_unpredicted(double t, size_t i) {
-  return dde_ylag_1_lookup(t, i);
+
+/* A kernel that answers the model's declared lag queries itself (dopri_dde1_kernel.cuh)
+ * has no general look-up behind ylag_*: a query the model did not declare (M::lags,
+ * dde_model_def.h) ends the trajectory with DDE_ERR_LAG_UNDECLARED (-11), loudly, the
+ * way a failed look-up does (src/dopri.c:387-389).  Out of line: never taken by a model
+ * that keeps its declaration. */
+static __device__ __noinline__ double dde_ylag_undeclared() {
+  const int s = threadIdx.x;
+  s_error[s] = 1;
+  s_code[s] = -11;
+  return dde::na_real();
 }
 
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
   if (s_cfg[s] & DDE_CFG_MEMO) { /* a one-equation system whose kernel answers ahead */
     if (t == s_memo_t[s]) {
-      DDE_LAG_COUNT(7);
       return s_memo_v[s];
     }
-    DDE_LAG_COUNT(8);
-    return dde_ylag_1_unpredicted(t, i);
+    return dde_ylag_undeclared();
   }
   return dde_ylag_1_lookup(t, i);
 }
@@ -855,6 +749,10 @@ static __device__ __forceinline__ double dde_ylag_1_lookup(double t, size_t i) {
 
 static __device__ __forceinline__ void ylag_all(double t, double *y) {
   const int s = threadIdx.x;
+  if (s_cfg[s] & DDE_CFG_MEMO) {
+    y[0] = ylag_1(t, 0);
+    return;
+  }
   const int n = dde::s_lag_u.n;
   if (dde::s_lag_u.sign * t <= s_t0[s]) {
     if (n == 1) {
@@ -876,6 +774,12 @@ template <class Index>
 static __device__ __forceinline__ void dde_ylag_indexed(double t, const Index *idx,
                                                         size_t nidx, double *y) {
   const int s = threadIdx.x;
+  if (s_cfg[s] & DDE_CFG_MEMO) {
+    for (size_t i = 0; i < nidx; ++i) {
+      y[i] = ylag_1(t, 0);
+    }
+    return;
+  }
   if (dde::s_lag_u.sign * t <= s_t0[s]) {
     if ((s_cfg[s] & 0xffff) == 1) {
       for (size_t i = 0; i < nidx; ++i) {

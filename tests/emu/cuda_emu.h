@@ -93,6 +93,13 @@ static inline float __int_as_float(int v) {
   memcpy(&f, &v, sizeof f);
   return f;
 }
+struct double2 {
+  double x, y;
+};
+static inline double2 make_double2(double x, double y) {
+  double2 v = {x, y};
+  return v;
+}
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __fma_rn(double a, double b, double c) { return __builtin_fma(a, b, c); }

@@ -21,7 +21,7 @@
 #include <dde/dde.h>
 
 #include "dopri_kernels.cuh"
-#include "dopri_lag1_kernel.cuh"
+#include "dopri_dde1_kernel.cuh"
 #include "dde_model_def.h"
 
 #define pow(x, y) dde_pow((x), (y))
@@ -168,20 +168,25 @@ int emu_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, s
     }                                      \
   } while (0)
   if (name == "mackey_glass") {
-    const int mode = g_mode >= 0 ? g_mode : (hist ? 4 : 1);
+    /* what the product launches (dde_model.cuh): dopri_dde1_kernel when it can take the run */
+    const bool dde1 = method == 1 && hist && a.sign > 0 && n_tcrit == 0 && n_out == 0 &&
+                      ctl->stiff_check == 0;
+    const int mode = g_mode >= 0 ? g_mode : (dde1 ? 4 : (hist ? 2 : 1));
     if (mode == 0) {
       EMU_RUN(dde_dopri_model_mackey_glass, 0);
     } else if (mode == 1) {
       EMU_RUN(dde_dopri_model_mackey_glass, 1);
     } else if (mode == 2) {
       EMU_RUN(dde_dopri_model_mackey_glass, 2);
-    } else if (mode == 3 || method == 0) {
-      EMU_RUN(dde_dopri_model_mackey_glass, 3);
-    } else { /* 4: dopri_lag1_kernel (dop853 only) */
+    } else { /* 4: dopri_dde1_kernel */
+      if (!dde1) {
+        g_message = "emu: dopri_dde1_kernel does not take this run";
+        return 1;
+      }
       a.win_staged = 1;
       const unsigned init_grid = (unsigned) ((a.n_traj + DDE_TPB - 1) / DDE_TPB);
       run_grid(dde::dopri_init_kernel<dde_dopri_model_mackey_glass, 1>, a, init_grid, DDE_TPB);
-      run_grid(dde::dopri_lag1_kernel<dde_dopri_model_mackey_glass>, a, 1, 1);
+      run_grid(dde::dopri_dde1_kernel<dde_dopri_model_mackey_glass>, a, 1, 1);
     }
   } else if (name == "lorenz") {
     const int mode = g_mode >= 0 ? g_mode : (hist ? 0 : 1);

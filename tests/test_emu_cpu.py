@@ -24,7 +24,7 @@ def compare(got, want):
 
 
 @needs_oracle
-@pytest.mark.parametrize("mode", [0, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 2, 4])
 def test_mackey_glass(mode):
     model, y0, parms, times, kw = workloads.mackey_glass(192)
     got = pyemu.dopri_batch(model, y0, times, parms, mode=mode, **kw)
@@ -66,32 +66,55 @@ def test_lorenz_sweep(mode):
 
 @needs_oracle
 @pytest.mark.parametrize("kwargs", [
-    dict(tcrit=np.array([17.0, 34.0, 51.0, 400.0])),
-    dict(stiff_check=1),
     dict(step_size_max=0.5, step_max_n=400),
     dict(step_size_min=0.05, step_size_min_allow=True),
     dict(step_size_min=0.05),
     dict(step_size_initial=0.01),
     dict(rtol=1e-9, atol=1e-9, n_history=200),
+    dict(rtol=1e-3, atol=1e-3),
     dict(return_initial=False),
+    dict(n_history=3),
+    dict(n_history=8),
+    dict(n_history=1),
 ])
-def test_mackey_glass_lag1_kernel_options(kwargs):
-    """dopri_lag1_kernel (dop853, declared lag) under the controls that steer its branches"""
+def test_mackey_glass_dde1_kernel_options(kwargs):
+    """dopri_dde1_kernel (dop853, declared lag) under the controls that steer its branches,
+    and with rings small enough to wrap below the lag (ERR_YLAG_FAIL where the reference
+    reports it, the redundant evaluation's look-up included)"""
     model, y0, parms, times, kw = workloads.mackey_glass(40)
-    kwargs = dict(kwargs)
-    tcrit = kwargs.pop("tcrit", None)
     kw = dict(kw, **kwargs)
-    got = pyemu.dopri_batch(model, y0, times, parms, tcrit=tcrit, mode=4, **kw)
-    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, tcrit=tcrit, **kw)
+    got = pyemu.dopri_batch(model, y0, times, parms, mode=4, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
     compare(got, want)
 
 
 @needs_oracle
-def test_mackey_glass_lag1_kernel_backward_time():
-    """integrating backwards: the reference's dop853 error norm goes negative there
-    (SURVEY.md A.1#1) and the run ends in ERR_STEP_SIZE_TOO_SMALL / VANISHED -- same here"""
-    model, y0, parms, times, kw = workloads.mackey_glass(16)
-    times = -times
+def test_mackey_glass_dde1_kernel_dense_times():
+    """many output rows per step, and a start time that is not zero"""
+    model, y0, parms, times, kw = workloads.mackey_glass(24)
+    times = np.linspace(3.0, 203.0, 801)
     got = pyemu.dopri_batch(model, y0, times, parms, mode=4, **kw)
     want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
     compare(got, want)
+
+
+@needs_oracle
+@pytest.mark.parametrize("kwargs", [
+    dict(tcrit=np.array([17.0, 34.0, 51.0, 400.0])),
+    dict(stiff_check=1),
+    dict(backward=True),
+])
+def test_mackey_glass_runs_the_dde1_kernel_does_not_take(kwargs):
+    """critical times, the stiffness test and backward time (where the reference's dop853
+    error norm goes negative, SURVEY.md A.1#1) stay on the general kernel"""
+    model, y0, parms, times, kw = workloads.mackey_glass(16)
+    kwargs = dict(kwargs)
+    tcrit = kwargs.pop("tcrit", None)
+    if kwargs.pop("backward", False):
+        times = -times
+    kw = dict(kw, **kwargs)
+    got = pyemu.dopri_batch(model, y0, times, parms, tcrit=tcrit, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, tcrit=tcrit, **kw)
+    compare(got, want)
+    with pytest.raises(RuntimeError, match="does not take"):
+        pyemu.dopri_batch(model, y0, times, parms, tcrit=tcrit, mode=4, **kw)
