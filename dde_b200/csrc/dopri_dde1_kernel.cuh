@@ -425,13 +425,17 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       }
       run = !done;
     }
-    /* ---- the evaluations of the step, in lock-step across the warp ---- */
-    double yin = 0.0, tt = t;
+    /* ---- the evaluations of the step, in lock-step across the warp ----
+       Position q of the loop is evaluation q for q <= 10 and evaluation q + 1 after that
+       (evaluation 11, the redundant one, is counted, not computed: see the head).  `tt` is
+       the time of the evaluation in hand, `tn` that of the one after it: its look-up is
+       made now, next to this evaluation's pow. */
+    double yin = 0.0, tt = t, tn = t;
     double k2 = 0.0, k3 = 0.0, k4 = 0.0, k5 = 0.0, k6 = 0.0, k7 = 0.0, k8 = 0.0, k9 = 0.0,
            k10 = 0.0, k14 = 0.0, k15 = 0.0;
     double h_new = 0.0;
-    double zq0 = 0.0, zq1 = 0.0, zkeep = 0.0; /* answers pending: evaluation st's in zq[st & 1] */
-    bool zok0 = false, zok1 = false;
+    double zn = 0.0;  /* the answer to the next evaluation's look-up ... */
+    bool okn = false; /* ... if it is one */
     bool lo_ok = true; /* the look-up of the redundant evaluation would succeed */
     double lo = 0.0;
     if (run) {
@@ -455,43 +459,29 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       /* input of evaluation 0, src/dopri_853.c:178-181, and its look-up */
       yin = y + h * DP8_A21 * k1;
       tt = dp8_stage_time(0, t, h);
+      tn = dp8_stage_time(1, t, h);
       double tq;
       M::lags(tt, p, &tq);
-      zq0 = dde1_lookup(w, t0, y0v, tq, &zok0);
+      zn = dde1_lookup(w, t0, y0v, tq, &okn);
     }
     int my_stages = run ? NST_STEP : 0;
 #pragma unroll 1
-    for (int st = 0; st < NST; ++st) {
-      if (st == 11) { /* the redundant evaluation: counted, not computed (see the head) */
-        continue;
-      }
+    for (int st = 0; st < NST - 1; ++st) {
       if (st >= my_stages) {
         continue;
       }
-      /* this evaluation's look-up was made one evaluation ago (12 asks what 10 asked) */
+      /* this evaluation's look-up was made one evaluation ago */
       double tq;
       M::lags(tt, p, &tq);
-      double z = st == 12 ? zkeep : (st & 1 ? zq1 : zq0);
-      const bool zgood = st == 12 ? true : (st & 1 ? zok1 : zok0);
-      if (!zgood) {
+      double z = zn;
+      if (!okn) {
         z = dde1_lookup_ring(ring, count, cap, t0, y0v, tq);
       }
-      zkeep = st == 10 ? z : zkeep;
       {
-        /* the next evaluation's: 0..9 -> st + 1, 10 -> 13, 12 -> 14, 13 -> 15; 14 and 15
-           have nothing to ask (their answers go nowhere) */
-        const int nx = st < 10 ? st + 1 : (st == 10 ? 13 : (st == 12 ? 14 : 15));
-        double tn;
-        M::lags(dp8_stage_time(nx, t, h), p, &tn);
-        bool okn;
-        const double zn = dde1_lookup(w, t0, y0v, tn, &okn);
-        if (nx & 1) {
-          zq1 = zn;
-          zok1 = okn;
-        } else {
-          zq0 = zn;
-          zok0 = okn;
-        }
+        /* the next evaluation's (the last one's goes nowhere) */
+        double tqn;
+        M::lags(tn, p, &tqn);
+        zn = dde1_lookup(w, t0, y0v, tqn, &okn);
       }
 
       /* -- dopri_eval, src/dopri.c:831-835: the one copy of the model -- */
@@ -508,57 +498,67 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
         case 0:
           k2 = kt;
           yin = y + h * (DP8_A31 * k1 + DP8_A32 * kt);
-          tt = dp8_stage_time(1, t, h);
+          tt = tn;
+          tn = dp8_stage_time(2, t, h);
           break;
         case 1:
           k3 = kt;
           yin = y + h * (DP8_A41 * k1 + DP8_A43 * kt);
-          tt = dp8_stage_time(2, t, h);
+          tt = tn;
+          tn = dp8_stage_time(3, t, h);
           break;
         case 2:
           k4 = kt;
           yin = y + h * (DP8_A51 * k1 + DP8_A53 * k3 + DP8_A54 * kt);
-          tt = dp8_stage_time(3, t, h);
+          tt = tn;
+          tn = dp8_stage_time(4, t, h);
           break;
         case 3:
           k5 = kt;
           yin = y + h * (DP8_A61 * k1 + DP8_A64 * k4 + DP8_A65 * kt);
-          tt = dp8_stage_time(4, t, h);
+          tt = tn;
+          tn = dp8_stage_time(5, t, h);
           break;
         case 4:
           k6 = kt;
           yin = y + h * (DP8_A71 * k1 + DP8_A74 * k4 + DP8_A75 * k5 + DP8_A76 * kt);
-          tt = dp8_stage_time(5, t, h);
+          tt = tn;
+          tn = dp8_stage_time(6, t, h);
           break;
         case 5:
           k7 = kt;
           yin = y + h * (DP8_A81 * k1 + DP8_A84 * k4 + DP8_A85 * k5 + DP8_A86 * k6 + DP8_A87 * kt);
-          tt = dp8_stage_time(6, t, h);
+          tt = tn;
+          tn = dp8_stage_time(7, t, h);
           break;
         case 6:
           k8 = kt;
           yin = y + h * (DP8_A91 * k1 + DP8_A94 * k4 + DP8_A95 * k5 + DP8_A96 * k6 + DP8_A97 * k7 +
                          DP8_A98 * kt);
-          tt = dp8_stage_time(7, t, h);
+          tt = tn;
+          tn = dp8_stage_time(8, t, h);
           break;
         case 7:
           k9 = kt;
           yin = y + h * (DP8_A101 * k1 + DP8_A104 * k4 + DP8_A105 * k5 + DP8_A106 * k6 +
                          DP8_A107 * k7 + DP8_A108 * k8 + DP8_A109 * kt);
-          tt = dp8_stage_time(8, t, h);
+          tt = tn;
+          tn = dp8_stage_time(9, t, h);
           break;
         case 8:
           k10 = kt;
           yin = y + h * (DP8_A111 * k1 + DP8_A114 * k4 + DP8_A115 * k5 + DP8_A116 * k6 +
                          DP8_A117 * k7 + DP8_A118 * k8 + DP8_A119 * k9 + DP8_A1110 * kt);
-          tt = dp8_stage_time(9, t, h);
+          tt = tn;
+          tn = dp8_stage_time(10, t, h);
           break;
         case 9: /* k2 is free again: stage 11's value goes there */
           k2 = kt;
           yin = y + h * (DP8_A121 * k1 + DP8_A124 * k4 + DP8_A125 * k5 + DP8_A126 * k6 +
                          DP8_A127 * k7 + DP8_A128 * k8 + DP8_A129 * k9 + DP8_A1210 * k10 +
                          DP8_A1211 * kt);
-          tt = dp8_stage_time(10, t, h);
+          tt = tn;
+          tn = dp8_stage_time(12, t, h); /* the same time: evaluation 12 asks what 10 asked */
           break;
         case 10: /* src/dopri_853.c:242-246 */
           k3 = kt;
@@ -567,25 +567,27 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           k5 = y + h * k4;
           attempt_done = true;
           break;
-        case 12: /* k4 = f(t + h, k5), src/dopri_853.c:304 */
+        case 11: /* evaluation 12: k4 = f(t + h, k5), src/dopri_853.c:304 */
           k4 = kt;
           yin = y + h * (DP8_A141 * k1 + DP8_A147 * k7 + DP8_A148 * k8 + DP8_A149 * k9 +
                          DP8_A1410 * k10 + DP8_A1411 * k2 + DP8_A1412 * k3 + DP8_A1413 * kt);
-          tt = dp8_stage_time(13, t, h);
+          tt = tn;
+          tn = dp8_stage_time(14, t, h);
           break;
-        case 13:
+        case 12: /* evaluation 13 */
           k14 = kt;
           yin = y + h * (DP8_A151 * k1 + DP8_A156 * k6 + DP8_A157 * k7 + DP8_A158 * k8 +
                          DP8_A1511 * k2 + DP8_A1512 * k3 + DP8_A1513 * k4 + DP8_A1514 * kt);
-          tt = dp8_stage_time(14, t, h);
+          tt = tn;
+          tn = dp8_stage_time(15, t, h);
           break;
-        case 14:
+        case 13: /* evaluation 14 */
           k15 = kt;
           yin = y + h * (DP8_A161 * k1 + DP8_A166 * k6 + DP8_A167 * k7 + DP8_A168 * k8 +
                          DP8_A169 * k9 + DP8_A1613 * k4 + DP8_A1614 * k14 + DP8_A1615 * kt);
-          tt = dp8_stage_time(15, t, h);
+          tt = tn;
           break;
-        default: /* 15: k16 = kt */
+        default: /* 14: evaluation 15, k16 = kt */
           step_done = true;
           break;
       }
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
         h_new = h / fac;
         if ((err <= 1) || force_this_step) {
-          my_stages = NST;
+          my_stages = NST - 1;
           fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
           ++n_accept;
           /* the redundant evaluation at the OLD time, src/dopri.c:400-403 (SURVEY.md
@@ -623,7 +625,8 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           }
           /* input of evaluation 12, src/dopri_853.c:304 */
           yin = k5;
-          tt = dp8_stage_time(12, t, h);
+          tt = tn;
+          tn = dp8_stage_time(13, t, h);
         } else {
           /* rejected, src/dopri.c:495-509 */
           h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);

@@ -713,22 +713,18 @@ static __device__ __forceinline__ double dde_ylag_1_lookup(double t, size_t i);
 /* A kernel that answers the model's declared lag queries itself (dopri_dde1_kernel.cuh)
  * has no general look-up behind ylag_*: a query the model did not declare (M::lags,
  * dde_model_def.h) ends the trajectory with DDE_ERR_LAG_UNDECLARED (-11), loudly, the
- * way a failed look-up does (src/dopri.c:387-389).  Out of line: never taken by a model
- * that keeps its declaration. */
-static __device__ __noinline__ double dde_ylag_undeclared() {
-  const int s = threadIdx.x;
-  s_error[s] = 1;
-  s_code[s] = -11;
-  return dde::na_real();
-}
-
+ * way a failed look-up does (src/dopri.c:387-389).  No branch: a select and two
+ * predicated stores, so that the model's arithmetic stays in the basic block of the
+ * look-up the kernel makes next to it. */
 static __device__ __forceinline__ double ylag_1(double t, size_t i) {
   const int s = threadIdx.x;
   if (s_cfg[s] & DDE_CFG_MEMO) { /* a one-equation system whose kernel answers ahead */
-    if (t == s_memo_t[s]) {
-      return s_memo_v[s];
+    const bool declared = t == s_memo_t[s];
+    if (!declared) {
+      s_error[s] = 1;
+      s_code[s] = -11;
     }
-    return dde_ylag_undeclared();
+    return declared ? s_memo_v[s] : dde::na_real();
   }
   return dde_ylag_1_lookup(t, i);
 }
