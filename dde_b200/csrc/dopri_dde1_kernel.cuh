@@ -195,27 +195,45 @@ __device__ __forceinline__ double dde1_lookup(const Dde1Win &w, double t0, doubl
 /* The same value from the trajectory's ring in HBM, for a query the window could not
  * answer: the last committed entry whose time is <= tq (src/dopri.c:742-769: only the
  * result of the search is defined), or ERR_YLAG_FAIL.  A fresh forward run: logical entry
- * idx sits in slot idx % cap.  Out of line and by value. */
+ * idx sits in slot idx % cap.  `top` is the first entry above the window (wbase + wn) and
+ * `wtop` its start time (+inf: there is none): a query at or above it -- a step attempt
+ * that spans more old entries than the window holds -- is found by walking up from there,
+ * two probes per round trip; anything else by bisection.  Out of line and by value. */
 static __device__ __noinline__ double dde1_lookup_ring(const double *ring, unsigned count, int cap,
-                                                       double t0, double y0v, double tq) {
+                                                       double t0, double y0v, double tq,
+                                                       unsigned top, double wtop) {
   if (tq <= t0) {
     return y0v;
   }
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   unsigned lo = count - used, hi = count;
 #define DDE1_TIME(j) (ring[(size_t) ((j) % (unsigned) cap) * 10u + 8u])
-  if (used == 0 || !(DDE1_TIME(lo) <= tq)) {
-    const int s = threadIdx.x;
-    s_error[s] = 1;
-    s_code[s] = -6; /* ERR_YLAG_FAIL */
-    return na_real();
-  }
-  while (hi - lo > 1) {
-    const unsigned mid = lo + (hi - lo) / 2;
-    if (DDE1_TIME(mid) <= tq) {
-      lo = mid;
-    } else {
-      hi = mid;
+  if (tq >= wtop) { /* entry `top` exists and starts at wtop */
+    lo = top;
+    for (;;) {
+      const double t1 = lo + 1 < count ? DDE1_TIME(lo + 1) : pos_inf();
+      const double t2 = lo + 2 < count ? DDE1_TIME(lo + 2) : pos_inf();
+      if (t2 <= tq) {
+        lo += 2;
+      } else {
+        lo += t1 <= tq ? 1u : 0u;
+        break;
+      }
+    }
+  } else {
+    if (used == 0 || !(DDE1_TIME(lo) <= tq)) {
+      const int s = threadIdx.x;
+      s_error[s] = 1;
+      s_code[s] = -6; /* ERR_YLAG_FAIL */
+      return na_real();
+    }
+    while (hi - lo > 1) {
+      const unsigned mid = lo + (hi - lo) / 2;
+      if (DDE1_TIME(mid) <= tq) {
+        lo = mid;
+      } else {
+        hi = mid;
+      }
     }
   }
 #undef DDE1_TIME
@@ -475,7 +493,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       M::lags(tt, p, &tq);
       double z = zn;
       if (!okn) {
-        z = dde1_lookup_ring(ring, count, cap, t0, y0v, tq);
+        z = dde1_lookup_ring(ring, count, cap, t0, y0v, tq, w.wbase + w.wn, w.wtop);
       }
       {
         /* the next evaluation's (the last one's goes nowhere) */
@@ -621,7 +639,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           /* the redundant evaluation at the OLD time, src/dopri.c:400-403 (SURVEY.md
              A.1#2): it counts (n_eval below), and its look-up can fail */
           if (!lo_ok) {
-            (void) dde1_lookup_ring(ring, count, cap, t0, y0v, lo);
+            (void) dde1_lookup_ring(ring, count, cap, t0, y0v, lo, w.wbase + w.wn, w.wtop);
           }
           /* input of evaluation 12, src/dopri_853.c:304 */
           yin = k5;
