@@ -186,25 +186,23 @@ DDE_HD double dde_exp(double x) {
   return dde_exp_inline(x, 0.0, 0, 0);
 }
 
-/* log(x) for the normalised bit pattern ix as hi + *tail. */
-DDE_HD double dde_pow_log_inline(uint64_t ix, double *tail) {
-  /* x = 2^k z, z in [OFF, 2 OFF); the range is cut into 128 subintervals */
+/* log(x) for the normalised bit pattern ix as hi + *tail, in two parts around the table
+ * read so that the caller chooses where the table is (global memory, .rodata, or a
+ * kernel's copy in shared memory): x = 2^k z, z in [OFF, 2 OFF); the range is cut into
+ * 128 subintervals, and this is the subinterval's index. */
+DDE_HD int dde_pow_log_index(uint64_t ix) {
   const uint64_t tmp = ix - 0x3fe6955500000000ULL;
-  const int i = (int) ((tmp >> 45) % 128);
+  return (int) ((tmp >> 45) % 128);
+}
+
+/* ... and this the rest, given entry i = {invc, logc, logctail}. */
+DDE_HD double dde_pow_log_finish(uint64_t ix, double invc, double logc, double logctail,
+                                 double *tail) {
+  const uint64_t tmp = ix - 0x3fe6955500000000ULL;
   const int k = (int) ((int64_t) tmp >> 52);
   const uint64_t iz = ix - (tmp & 0xfffULL << 52);
   const double z = dde_asdouble(iz);
   const double kd = (double) k;
-
-#if defined(__CUDA_ARCH__)
-  const double2 invc_logc = __ldg(&dde_pow_log_tab_d[i].invc_logc);
-  const double invc = invc_logc.x, logc = invc_logc.y;
-  const double logctail = __ldg(&dde_pow_log_tab_d[i].logctail);
-#else
-  const double invc = DDE_POW_LOG_TAB(3 * i);
-  const double logc = DDE_POW_LOG_TAB(3 * i + 1);
-  const double logctail = DDE_POW_LOG_TAB(3 * i + 2);
-#endif
 
   /* r = z/c - 1 is exactly representable */
   const double r = DDE_FMA(z, invc, -1.0);
@@ -233,6 +231,26 @@ DDE_HD double dde_pow_log_inline(uint64_t ix, double *tail) {
   const double y = hi + lo;
   *tail = (hi - y) + lo;
   return y;
+}
+
+/* the default table */
+DDE_HD void dde_pow_log_entry(int i, double *invc, double *logc, double *logctail) {
+#if defined(__CUDA_ARCH__)
+  const double2 invc_logc = __ldg(&dde_pow_log_tab_d[i].invc_logc);
+  *invc = invc_logc.x;
+  *logc = invc_logc.y;
+  *logctail = __ldg(&dde_pow_log_tab_d[i].logctail);
+#else
+  *invc = DDE_POW_LOG_TAB(3 * i);
+  *logc = DDE_POW_LOG_TAB(3 * i + 1);
+  *logctail = DDE_POW_LOG_TAB(3 * i + 2);
+#endif
+}
+
+DDE_HD double dde_pow_log_inline(uint64_t ix, double *tail) {
+  double invc, logc, logctail;
+  dde_pow_log_entry(dde_pow_log_index(ix), &invc, &logc, &logctail);
+  return dde_pow_log_finish(ix, invc, logc, logctail, tail);
 }
 
 /* 0 = not an integer, 1 = odd integer, 2 = even integer */
@@ -339,31 +357,36 @@ DDE_HD_NOINLINE double dde_pow_slow(double x, double y) {
 /* The common path of dde_pow_main without a branch: the value when x is
  * positive normal and the exponent of the final exp() is ordinary, something
  * harmless (never a trap, never an out-of-range table index) otherwise;
- * *exp_rare tells which. */
-DDE_HD double dde_pow_common(uint64_t ix, double y, int *exp_rare) {
-  double lo;
-  const double hi = dde_pow_log_inline(ix, &lo);
+ * *exp_rare tells which.  In three parts around the two table reads
+ * (dde_pow_log_index/_finish above; the reduction of the exponent and the polynomial
+ * below), which dde_pow_common strings together for the default tables and
+ * dde_pow_shared for a kernel's copy in shared memory. */
+struct DdeExpReduced {
+  uint64_t ki; /* entry ki % 128; scale exponent ki << 45 */
+  double r;
+};
+
+DDE_HD struct DdeExpReduced dde_pow_exp_reduce(double y, double hi, double lo, int *exp_rare) {
   const double ehi = y * hi;
   const double elo = DDE_FMA(y, lo, DDE_FMA(hi, y, -ehi));
   const uint32_t abstop = dde_top12(ehi) & 0x7ff;
   *exp_rare = abstop - 0x3c9u >= 0x3fu;
   /* dde_exp_inline(ehi, elo, 0, 1), its common path */
   double kd = DDE_FMA(ehi, DDE_EXP_INVLN2N, DDE_EXP_SHIFT);
-  const uint64_t ki = dde_asuint64(kd);
+  struct DdeExpReduced red;
+  red.ki = dde_asuint64(kd);
   kd = kd - DDE_EXP_SHIFT;
   double r = DDE_FMA(kd, DDE_EXP_NEGLN2HIN, ehi);
   r = DDE_FMA(kd, DDE_EXP_NEGLN2LON, r);
-  r = elo + r;
-  const uint64_t top = ki << 45;
-#if defined(__CUDA_ARCH__)
-  const ulonglong2 entry = __ldg(&dde_exp_tab_d[ki % 128]);
-  const double tail = dde_asdouble((uint64_t) entry.x);
-  const uint64_t sbits = (uint64_t) entry.y + top;
-#else
-  const uint64_t idx = 2 * (ki % 128);
-  const double tail = dde_asdouble(DDE_EXP_TAB(idx));
-  const uint64_t sbits = DDE_EXP_TAB(idx + 1) + top;
-#endif
+  red.r = elo + r;
+  return red;
+}
+
+/* given entry ki % 128 = {tail, scale bits} */
+DDE_HD double dde_pow_exp_finish(struct DdeExpReduced red, double tail, uint64_t entry_sbits) {
+  const uint64_t top = red.ki << 45;
+  const uint64_t sbits = entry_sbits + top;
+  const double r = red.r;
   const double r2 = r * r;
   const double p23 = DDE_FMA(r, DDE_EXP_C3, DDE_EXP_C2);
   const double p45 = DDE_FMA(r, DDE_EXP_C5, DDE_EXP_C4);
@@ -371,6 +394,19 @@ DDE_HD double dde_pow_common(uint64_t ix, double y, int *exp_rare) {
   tmp = DDE_FMA(r2 * r2, p45, tmp);
   const double scale = dde_asdouble(sbits);
   return DDE_FMA(scale, tmp, scale);
+}
+
+DDE_HD double dde_pow_common(uint64_t ix, double y, int *exp_rare) {
+  double lo;
+  const double hi = dde_pow_log_inline(ix, &lo);
+  const struct DdeExpReduced red = dde_pow_exp_reduce(y, hi, lo, exp_rare);
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 entry = __ldg(&dde_exp_tab_d[red.ki % 128]);
+  return dde_pow_exp_finish(red, dde_asdouble((uint64_t) entry.x), (uint64_t) entry.y);
+#else
+  const uint64_t idx = 2 * (red.ki % 128);
+  return dde_pow_exp_finish(red, dde_asdouble(DDE_EXP_TAB(idx)), DDE_EXP_TAB(idx + 1));
+#endif
 }
 
 /* Everything dde_pow_common does not cover.  `common` is not used: taking it
@@ -399,5 +435,55 @@ DDE_HD double dde_pow(double x, double y) {
   }
   return common;
 }
+
+
+#if defined(__CUDACC__) || defined(DDE_HOST_EMU)
+/* ---- the same pow with the two tables in a kernel's shared memory --------------------
+ * at shared-window address `base`: {invc, logc} x 128, then logctail x 128, then
+ * {tail, scale bits} x 128 (DDE_TAB_SHARED_BYTES; filled by dde_tab_shared_fill).  The
+ * gathers are divergent (every lane its own entry): from shared memory they cost a
+ * fixed ~30 cycles and no cache capacity, where the global tables compete with the
+ * history rings for what little L1 a kernel with 220 KB of shared memory leaves. */
+#define DDE_TAB_SHARED_BYTES (128 * 16 + 128 * 8 + 128 * 16)
+#if defined(DDE_HOST_EMU)
+/* tests/emu: a shared-window address is a byte offset into the emulated shared memory */
+static inline char *dde_emu_shared(unsigned addr);
+#endif
+
+__device__ __forceinline__ double dde_pow_shared(unsigned base, double x, double y) {
+  const uint32_t topx = dde_top12(x);
+  const uint32_t topy = dde_top12(y);
+  const int rare =
+      (topx - 0x001u >= 0x7ffu - 0x001u) | ((topy & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  const uint64_t ix = dde_asuint64(x);
+  const unsigned i = (unsigned) dde_pow_log_index(ix);
+  double invc, logc, logctail;
+#if defined(DDE_HOST_EMU)
+  invc = ((const double *) dde_emu_shared(base + 16u * i))[0];
+  logc = ((const double *) dde_emu_shared(base + 16u * i))[1];
+  logctail = *(const double *) dde_emu_shared(base + 2048u + 8u * i);
+#else
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(base + 16u * i));
+  asm("ld.shared.f64 %0, [%1];" : "=d"(logctail) : "r"(base + 2048u + 8u * i));
+#endif
+  double lo;
+  const double hi = dde_pow_log_finish(ix, invc, logc, logctail, &lo);
+  int exp_rare;
+  const struct DdeExpReduced red = dde_pow_exp_reduce(y, hi, lo, &exp_rare);
+  const unsigned k = (unsigned) red.ki % 128u;
+  double tail, sb;
+#if defined(DDE_HOST_EMU)
+  tail = ((const double *) dde_emu_shared(base + 3072u + 16u * k))[0];
+  sb = ((const double *) dde_emu_shared(base + 3072u + 16u * k))[1];
+#else
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tail), "=d"(sb) : "r"(base + 3072u + 16u * k));
+#endif
+  const double common = dde_pow_exp_finish(red, tail, dde_asuint64(sb));
+  if (rare | exp_rare) {
+    return dde_pow_rare(x, y, common);
+  }
+  return common;
+}
+#endif
 
 #endif /* DDE_MATH_H */

@@ -69,6 +69,11 @@ inline int persistent_grid(Kernel kernel, long long n_items, int device_sms, siz
    instantiated for models it can (the branch that would launch it is never taken) */
 struct Dde1Placeholder {
   static constexpr int N = 1, NP = 0, N_OUT = 0, N_EVENTS = 0, N_LAGS = 1;
+  typedef Dde1Scope Scoped;
+  static __device__ __forceinline__ void deriv_scoped(Scoped &, size_t, double, const double *,
+                                                      double *dydt, const void *) {
+    dydt[0] = 0.0;
+  }
   static __device__ __forceinline__ void lags(double t, const void *, double *tlag) { tlag[0] = t; }
   static __device__ __forceinline__ void deriv(size_t, double, const double *, double *dydt,
                                                const void *) {
@@ -183,20 +188,24 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
 } /* namespace dde */
 
 #define DDE_REGISTER_DOPRI_EVENTS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS) \
-  DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, DDE_NO_LAGS, 0)
+  DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)          \
+  DDE_REGISTER_DOPRI_DESC(NAME, NEQ, NPARMS, NOUT, NEVENTS)
 
 /* ... with the model's lags declared (dde_model_def.h: M::lags), e.g.
  *     DDE_MODEL_FN void mackey_glass_lags(double t, const void *data, double *tlag) {
  *       tlag[0] = t - 17.0;
  *     }
+ * and the model's source compiled a second time inside a struct (dde_model_scoped.inc):
+ *     #define DDE_SCOPED_MODEL mackey_glass
+ *     #define DDE_SCOPED_SOURCE "mackey_glass.h"
+ *     #include "dde_model_scoped.inc"
  *     DDE_REGISTER_DOPRI_LAGS(mackey_glass, mackey_glass, 1, 3, mackey_glass_lags, 1) */
-#define DDE_REGISTER_DOPRI_LAGS(NAME, DERIV, NEQ, NPARMS, LAGS, NLAGS)                        \
-  DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0, LAGS, NLAGS)
-
-#define DDE_REGISTER_DOPRI_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, LAGS, \
-                                NLAGS)                                                         \
-  DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, LAGS,   \
+#define DDE_REGISTER_DOPRI_LAGS(NAME, DERIV, NEQ, NPARMS, LAGS, NLAGS)                          \
+  DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0, LAGS, \
                               NLAGS)                                                           \
+  DDE_REGISTER_DOPRI_DESC(NAME, NEQ, NPARMS, 0, 0)
+
+#define DDE_REGISTER_DOPRI_DESC(NAME, NEQ, NPARMS, NOUT, NEVENTS)                              \
   static dde::ModelDesc dde_dopri_desc_##NAME = {#NAME,                                        \
                                                  1,                                            \
                                                  (NEQ),                                        \

@@ -10,12 +10,15 @@
  *   M::N_LAGS, M::lags                   optional (an extension): the times at which
  *                                        deriv(t, ...) reads the history,
  *                                            void lags(double t, const void *data, double *tlag)
- *                                        (the `lags` argument of dde23-style solvers).  The
- *                                        kernel then answers the look-ups of a whole step
- *                                        attempt up front, next to each other, and ylag_1 uses
- *                                        an answer only when the model asks for exactly that
- *                                        time: a wrong or missing declaration costs speed,
- *                                        never correctness.
+ *                                        (the `lags` argument of dde23-style solvers).
+ *   M::Scoped, M::deriv_scoped           with M::lags: the model compiled inside a struct
+ *                                        (dde_model_scoped.inc), so that the kernel for one
+ *                                        delay equation (dopri_dde1_kernel.cuh) can make the
+ *                                        declared look-up itself, one evaluation ahead, and
+ *                                        hand the model the answer.  A look-up deriv makes
+ *                                        without having declared it ends the trajectory with
+ *                                        DDE_ERR_LAG_UNDECLARED (-11): a wrong declaration
+ *                                        is reported, never integrated.
  */
 #ifndef DDE_MODEL_DEF_H
 #define DDE_MODEL_DEF_H
@@ -58,12 +61,31 @@
 
 #define DDE_NO_LAGS(t, data, tlag) ((void) 0)
 
-#define DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS) \
-  DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, DDE_NO_LAGS, 0)
+/* a model without declared lags: never launched on the scoped kernel */
+#define DDE_NO_SCOPE_TYPE(NAME) ::dde::Dde1Scope
+#define DDE_NO_SCOPE_CALL(sc, DERIV) DERIV
+/* ... with: struct dde_scoped_NAME (dde_model_scoped.inc) */
+#define DDE_SCOPE_TYPE(NAME) dde_scoped_##NAME
+#define DDE_SCOPE_CALL(sc, DERIV) (sc).DERIV
+
+#define DDE_DEFINE_DOPRI_MODEL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS)        \
+  DDE_DEFINE_DOPRI_MODEL_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS,         \
+                              DDE_NO_LAGS, 0, DDE_NO_SCOPE_TYPE, DDE_NO_SCOPE_CALL)
 
 #define DDE_DEFINE_DOPRI_MODEL_LAGS(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS,   \
                                     LAGS, NLAGS)                                               \
+  DDE_DEFINE_DOPRI_MODEL_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS, LAGS,   \
+                              NLAGS, DDE_SCOPE_TYPE, DDE_SCOPE_CALL)
+
+#define DDE_DEFINE_DOPRI_MODEL_FULL(NAME, DERIV, NEQ, NPARMS, OUTPUT, NOUT, EVENTS, NEVENTS,   \
+                                    LAGS, NLAGS, SCOPE_TYPE, SCOPE_CALL)                       \
   struct dde_dopri_model_##NAME {                                                              \
+    typedef SCOPE_TYPE(NAME) Scoped;                                                           \
+    static __device__ __forceinline__ void deriv_scoped(Scoped &sc, size_t n, double t,        \
+                                                        const double *y, double *dydt,         \
+                                                        const void *data) {                    \
+      SCOPE_CALL(sc, DERIV)(n, t, y, dydt, data);                                              \
+    }                                                                                          \
     static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT), N_EVENTS = (NEVENTS);       \
     static constexpr int N_LAGS = (NLAGS);                                                     \
     static __device__ __forceinline__ void lags(double t, const void *data, double *tlag) {    \

@@ -56,7 +56,8 @@
 /* one window slot, all threads: 5 pairs x 16 bytes */
 #define DDE1_PAIR_BYTES (16u * DDE_TPB)
 #define DDE1_SLOT_BYTES (5u * DDE1_PAIR_BYTES)
-#define DDE1_SMEM_BYTES (DDE_CTX_HEAD_BYTES + DDE1_WIN * DDE1_SLOT_BYTES)
+/* shared memory of a block: the pow / exp tables, then the window */
+#define DDE1_SMEM_BYTES (DDE_TAB_SHARED_BYTES + DDE1_WIN * DDE1_SLOT_BYTES)
 
 namespace dde {
 
@@ -94,6 +95,57 @@ __device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
 }
 #endif
+
+/* What the model sees instead of the global history functions and libm when its source
+ * is compiled a second time INSIDE a struct derived from this one (dde_model_scoped.inc):
+ * unqualified calls to ylag_1 / pow / exp in the model's functions -- now member
+ * functions -- find these members first.  The solver's side of the model ABI
+ * (src/dopri.h:49-50 carries no solver handle; the reference uses a process global,
+ * src/dopri.c:245; the general kernels a per-thread block in shared memory) is then a few
+ * registers of the calling thread: the declared query and its answer, where the tables
+ * of pow are, whether the model asked for something it did not declare. */
+struct Dde1Scope {
+  double memo_t, memo_v; /* the query answered ahead of this evaluation, and the answer */
+  unsigned tab;          /* shared-window address of the pow / exp tables */
+  bool undeclared;       /* a look-up that was not declared (M::lags): DDE_ERR_LAG_UNDECLARED */
+  __device__ __forceinline__ double ylag_1(double t, size_t) {
+    const bool declared = t == memo_t;
+    undeclared |= !declared;
+    return declared ? memo_v : na_real();
+  }
+  __device__ __forceinline__ void ylag_all(double t, double *y) { y[0] = ylag_1(t, 0); }
+  __device__ __forceinline__ void ylag_vec(double t, const size_t *, size_t nidx, double *y) {
+    for (size_t i = 0; i < nidx; ++i) {
+      y[i] = ylag_1(t, 0);
+    }
+  }
+  __device__ __forceinline__ void ylag_vec_int(double t, const int *, size_t nidx, double *y) {
+    for (size_t i = 0; i < nidx; ++i) {
+      y[i] = ylag_1(t, 0);
+    }
+  }
+  __device__ __forceinline__ double dde_scope_pow(double x, double y) {
+    return dde_pow_shared(tab, x, y);
+  }
+  __device__ __forceinline__ double dde_scope_exp(double x) { return dde_exp(x); }
+};
+
+/* the block's copy of the tables (dde_math.h: dde_pow_shared); a barrier follows */
+__device__ __forceinline__ void dde1_tables_fill(unsigned base) {
+  for (unsigned i = threadIdx.x; i < 128u; i += blockDim.x) {
+    double invc, logc, logctail;
+    dde_pow_log_entry((int) i, &invc, &logc, &logctail);
+    dde1_sts2(base + 16u * i, invc, logc);
+    dde1_sts(base + 2048u + 8u * i, logctail);
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 e = dde_exp_tab_d[i];
+    dde1_sts2(base + 3072u + 16u * i, dde_asdouble((uint64_t) e.x), dde_asdouble((uint64_t) e.y));
+#else
+    dde1_sts2(base + 3072u + 16u * i, dde_asdouble(DDE_EXP_TAB(2 * i)),
+              dde_asdouble(DDE_EXP_TAB(2 * i + 1)));
+#endif
+  }
+}
 
 /* Time of right-hand-side evaluation j of a dop853 step (attempt: 0 .. 10; accepted steps
  * go on with 11 .. 15): src/dopri_853.c:178-240, src/dopri.c:400-403,
@@ -199,11 +251,19 @@ __device__ __forceinline__ double dde1_lookup(const Dde1Win &w, double t0, doubl
  * `wtop` its start time (+inf: there is none): a query at or above it -- a step attempt
  * that spans more old entries than the window holds -- is found by walking up from there,
  * two probes per round trip; anything else by bisection.  Out of line and by value. */
-static __device__ __noinline__ double dde1_lookup_ring(const double *ring, unsigned count, int cap,
-                                                       double t0, double y0v, double tq,
-                                                       unsigned top, double wtop) {
+struct Dde1Found {
+  double value;
+  bool failed; /* ERR_YLAG_FAIL */
+};
+
+static __device__ __noinline__ Dde1Found dde1_lookup_ring(const double *ring, unsigned count,
+                                                          int cap, double t0, double y0v,
+                                                          double tq, unsigned top, double wtop) {
+  Dde1Found f;
+  f.failed = false;
+  f.value = y0v;
   if (tq <= t0) {
-    return y0v;
+    return f;
   }
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   unsigned lo = count - used, hi = count;
@@ -222,10 +282,9 @@ static __device__ __noinline__ double dde1_lookup_ring(const double *ring, unsig
     }
   } else {
     if (used == 0 || !(DDE1_TIME(lo) <= tq)) {
-      const int s = threadIdx.x;
-      s_error[s] = 1;
-      s_code[s] = -6; /* ERR_YLAG_FAIL */
-      return na_real();
+      f.failed = true;
+      f.value = na_real();
+      return f;
     }
     while (hi - lo > 1) {
       const unsigned mid = lo + (hi - lo) / 2;
@@ -240,7 +299,8 @@ static __device__ __noinline__ double dde1_lookup_ring(const double *ring, unsig
   const double *c = ring + (size_t) (lo % (unsigned) cap) * 10u;
   const double theta = (tq - c[8]) / c[9];
   const double theta1 = 1 - theta;
-  return interp853(1, theta, theta1, c);
+  f.value = interp853(1, theta, theta1, c);
+  return f;
 }
 
 /* Once per step attempt, all lanes together: slide the window so that it starts at the
@@ -331,7 +391,6 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
   static_assert(M::N == 1 && M::N_LAGS == 1 && M::NP >= 0, "one equation, one declared lag");
   constexpr int ORDER = 8;
   constexpr int PMAX = M::NP > 0 ? M::NP : 1;
-  constexpr int CFG = 1 | (ORDER << 16) | (1 << 24) | DDE_CFG_MEMO;
   constexpr int NST_STEP = 11, NST = 16;
   constexpr int hl = ORDER + 2;
   const int s = threadIdx.x;
@@ -346,12 +405,19 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
   const double t_end = a.times[n_times - 1];
   const int cap = a.n_history;
 
-  Dde1Win w;
-  w.first = (unsigned) __cvta_generic_to_shared(dde_smem) + (unsigned) DDE_CTX_HEAD_BYTES +
-            16u * (unsigned) s;
+  /* shared memory: the block's copy of the pow / exp tables, then the window */
+  unsigned smem = (unsigned) __cvta_generic_to_shared(dde_smem);
 #ifndef DDE_HOST_EMU
-  asm volatile("" : "+r"(w.first)); /* opaque: formed once, not re-derived at every use */
+  asm volatile("" : "+r"(smem)); /* opaque: formed once, not re-derived at every use */
 #endif
+  dde1_tables_fill(smem);
+  __syncthreads();
+  typename M::Scoped sc; /* the model's side of the solver (Dde1Scope) */
+  sc.tab = smem;
+  sc.undeclared = false;
+  sc.memo_t = sc.memo_v = 0.0;
+  Dde1Win w;
+  w.first = smem + (unsigned) DDE_TAB_SHARED_BYTES + 16u * (unsigned) s;
   w.below = w.first;
   w.wbase = w.wn = 0;
   w.wtop = pos_inf();
@@ -359,6 +425,8 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
   /* ---- per-lane solver object (src/dopri.h:55-161) ---- */
   long long traj = -1;
   bool active = false, done = false;
+  bool error = false; /* obj->error */
+  int code = 0;       /* obj->code */
   double p[PMAX];
   double y = 0.0, k1 = 0.0, y0v = 0.0;
   double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
@@ -398,10 +466,9 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       count = 0;
       head = 0;
       dde1_window_reset(w);
-      s_cfg[s] = CFG;
-      s_memo_t[s] = na_real();
-      s_code[s] = 0;
-      s_error[s] = 0;
+      sc.undeclared = false;
+      code = 0;
+      error = false;
       fac_old = 1e-4;
       stop = last = reject = false;
       h_save = 0.0;
@@ -411,11 +478,11 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       n_eval0 = a.stats[4 * traj + 0];
       const int code0 = a.code[traj];
       if (code0 == -8 || code0 == -10) {
-        s_code[s] = code0;
+        code = code0;
         done = true;
       } else if (code0 != 0) { /* a lag look-up failed during start-up */
-        s_code[s] = code0;
-        s_error[s] = 1;
+        code = code0;
+        error = true;
       }
     }
 
@@ -424,21 +491,21 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
     bool force_this_step = false;
     if (run) {
       if ((unsigned long long) n_step > a.step_max_n) {
-        s_error[s] = 1;
-        s_code[s] = -3; /* ERR_TOO_MANY_STEPS */
+        error = true;
+        code = -3; /* ERR_TOO_MANY_STEPS */
         done = true;
       } else if (fabs(h) <= a.step_size_min) {
         if (a.step_size_min_allow) {
           h = copysign(a.step_size_min, 1.0);
           force_this_step = true;
         } else {
-          s_error[s] = 1;
-          s_code[s] = -4; /* ERR_STEP_SIZE_TOO_SMALL */
+          error = true;
+          code = -4; /* ERR_STEP_SIZE_TOO_SMALL */
           done = true;
         }
       } else if (fabs(h) <= fabs(t) * DBL_EPSILON) {
-        s_error[s] = 1;
-        s_code[s] = -5; /* ERR_STEP_SIZE_VANISHED */
+        error = true;
+        code = -5; /* ERR_STEP_SIZE_VANISHED */
         done = true;
       }
       run = !done;
@@ -493,7 +560,13 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       M::lags(tt, p, &tq);
       double z = zn;
       if (!okn) {
-        z = dde1_lookup_ring(ring, count, cap, t0, y0v, tq, w.wbase + w.wn, w.wtop);
+        const Dde1Found f =
+            dde1_lookup_ring(ring, count, cap, t0, y0v, tq, w.wbase + w.wn, w.wtop);
+        z = f.value;
+        if (f.failed && !error) {
+          error = true;
+          code = -6; /* ERR_YLAG_FAIL */
+        }
       }
       {
         /* the next evaluation's (the last one's goes nowhere) */
@@ -504,10 +577,9 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
 
       /* -- dopri_eval, src/dopri.c:831-835: the one copy of the model -- */
       double kt;
-      s_memo_t[s] = tq;
-      s_memo_v[s] = z;
-      __builtin_assume(s_cfg[s] == CFG);
-      M::deriv((size_t) 1, tt, &yin, &kt, p);
+      sc.memo_t = tq;
+      sc.memo_v = z;
+      M::deriv_scoped(sc, (size_t) 1, tt, &yin, &kt, p);
 
       /* -- file the result and form the input of the next evaluation (one warp-uniform
             switch per evaluation), src/dopri_853.c:178-246,304,330-347 -- */
@@ -611,7 +683,11 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       }
 
       if (attempt_done) {
-        if (s_error[s]) {
+        if (sc.undeclared && !error) {
+          error = true;
+          code = -11; /* DDE_ERR_LAG_UNDECLARED */
+        }
+        if (error) {
           done = true; /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
           my_stages = 0;
           continue;
@@ -639,7 +715,12 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           /* the redundant evaluation at the OLD time, src/dopri.c:400-403 (SURVEY.md
              A.1#2): it counts (n_eval below), and its look-up can fail */
           if (!lo_ok) {
-            (void) dde1_lookup_ring(ring, count, cap, t0, y0v, lo, w.wbase + w.wn, w.wtop);
+            const Dde1Found f =
+                dde1_lookup_ring(ring, count, cap, t0, y0v, lo, w.wbase + w.wn, w.wtop);
+            if (f.failed && !error) {
+              error = true;
+              code = -6; /* ERR_YLAG_FAIL */
+            }
           }
           /* input of evaluation 12, src/dopri_853.c:304 */
           yin = k5;
@@ -719,7 +800,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
         }
 
         if (last) {
-          s_code[s] = 1; /* OK_COMPLETE */
+          code = 1; /* OK_COMPLETE */
           done = true;
           my_stages = 0;
           continue;
@@ -746,7 +827,6 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       a.stats[4 * traj + 1] = n_step;
       a.stats[4 * traj + 2] = n_accept;
       a.stats[4 * traj + 3] = n_reject;
-      const int code = s_code[s];
       a.code[traj] = code;
       a.step_size[traj] = code == 1 ? h_save /* src/dopri.c:463 */ : a.step_size_initial;
       if (code != -10) {

@@ -48,6 +48,14 @@
    window keeps only step times and sizes and coefficients are read from HBM */
 #define DDE_WIN_COEF_BUDGET (72 * 1024 * (DDE_TPB / 128))
 
+#ifdef DDE_HOST_EMU
+namespace dde {
+alignas(16) static double dde_smem[24 * 1024];
+}
+/* tests/emu: a shared-window address is a byte offset into the emulated shared memory */
+static inline char *dde_emu_shared(unsigned addr) { return (char *) dde::dde_smem + addr; }
+#endif
+
 namespace dde {
 
 /* batch-uniform part */
@@ -105,9 +113,7 @@ enum {
  * thread-dependent base address; every launch of a kernel that includes this file
  * passes at least DDE_CTX_HEAD_BYTES (the shared head) or DDE_CTX_BYTES (all of it) of
  * dynamic shared memory. */
-#ifdef DDE_HOST_EMU /* tests/emu: the device code compiled by g++, one lane at a time */
-alignas(16) static double dde_smem[24 * 1024];
-#else
+#ifndef DDE_HOST_EMU /* tests/emu (the device code compiled by g++): a static array, above */
 extern __shared__ __align__(16) double dde_smem[];
 #endif
 #define DDE_CTX_HEAD_BYTES \

@@ -14,6 +14,12 @@
 #include "../models/rossler.h"
 #include "../models/seir.h"
 
+/* the Mackey-Glass model declares its lag: compiled once more inside a struct, for the
+   kernel that answers the look-up itself (dopri_dde1_kernel.cuh) */
+#define DDE_SCOPED_MODEL mackey_glass
+#define DDE_SCOPED_SOURCE "../models/mackey_glass.h"
+#include "dde_model_scoped.inc"
+
 /*                         name            deriv           n  n_parms  output        n_out */
 DDE_REGISTER_DOPRI_OUTPUT(lorenz,         lorenz,         3, 3,       lorenz_output, 2)
 DDE_REGISTER_DOPRI(       rossler,        rossler,        3, 3)

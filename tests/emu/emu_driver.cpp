@@ -32,6 +32,10 @@
 #include "../../dde_b200/models/rossler.h"
 #include "../../dde_b200/models/seir.h"
 
+#define DDE_SCOPED_MODEL mackey_glass
+#define DDE_SCOPED_SOURCE "../../dde_b200/models/mackey_glass.h"
+#include "dde_model_scoped.inc"
+
 DDE_DEFINE_DOPRI_MODEL(lorenz, lorenz, 3, 3, lorenz_output, 2, DDE_NO_EVENTS, 0)
 DDE_DEFINE_DOPRI_MODEL(rossler, rossler, 3, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0)
 DDE_DEFINE_DOPRI_MODEL_LAGS(mackey_glass, mackey_glass, 1, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0,
