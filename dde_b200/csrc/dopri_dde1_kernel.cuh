@@ -418,6 +418,9 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
   sc.memo_t = sc.memo_v = 0.0;
   Dde1Win w;
   w.first = smem + (unsigned) DDE_TAB_SHARED_BYTES + 16u * (unsigned) s;
+#ifndef DDE_HOST_EMU
+  asm volatile("" : "+r"(w.first)); /* ... nor this thread's column from the thread index */
+#endif
   w.below = w.first;
   w.wbase = w.wn = 0;
   w.wtop = pos_inf();
