@@ -10,9 +10,9 @@ per-trajectory HBM ring-buffer history for delay look-ups (`ylag`),
 from .api import (DOPRI_5, DOPRI_853, OK_COMPLETE, DdeError, DifeqResult, DopriBatchResult,  # noqa: F401
                   DopriHistory, DopriResult, difeq, difeq_replicate, dopri, dopri5, dopri853,
                   dopri_batch, dopri_continue, dopri_interpolate, models, strerror)
-from .batch import DifeqBatch, DopriBatch  # noqa: F401
+from .batch import DifeqBatch, DopriBatch, DopriShards  # noqa: F401
 
 __all__ = [
     "dopri", "dopri5", "dopri853", "dopri_batch", "dopri_continue", "dopri_interpolate", "difeq",
-    "difeq_replicate", "DopriBatch", "DifeqBatch", "models", "strerror", "DdeError",
+    "difeq_replicate", "DopriBatch", "DopriShards", "DifeqBatch", "models", "strerror", "DdeError",
 ]

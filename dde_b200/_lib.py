@@ -95,7 +95,18 @@ SYMBOLS = [
     ("dde_difeq_batch_last_ms", C.c_double, [C.c_void_p]),
     ("dde_device_count", C.c_int, []),
     ("dde_dopri_batch_sharded", C.c_int, _DOPRI_BATCH_ARGS + [c_int32_p, _SZ]),
+    ("dde_dopri_batch_sharded_events", C.c_int,
+     _DOPRI_BATCH_ARGS[:13] + [c_int32_p] + _DOPRI_BATCH_ARGS[13:] + [c_int32_p, _SZ]),
     ("dde_difeq_batch_sharded", C.c_int, _DIFEQ_BATCH_ARGS + [c_int32_p, _SZ]),
+    ("dde_dopri_shards_alloc", C.c_void_p, [C.c_char_p, C.POINTER(DopriControl), _SZ, _SZ, _SZ, _SZ,
+                                            c_int32_p, _SZ]),
+    ("dde_dopri_shards_free", None, [C.c_void_p]),
+    ("dde_dopri_shards_count", _SZ, [C.c_void_p]),
+    ("dde_dopri_shards_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _SZ]),
+    ("dde_dopri_shards_set_times", C.c_int, [C.c_void_p, c_double_p, _SZ, c_double_p, _SZ]),
+    ("dde_dopri_shards_set_events", C.c_int, [C.c_void_p, c_int32_p, _SZ]),
+    ("dde_dopri_shards_run_download", C.c_int, [C.c_void_p] + [C.c_void_p] * 6),
+    ("dde_dopri_shards_last_ms", C.c_double, [C.c_void_p]),
     ("dde_shard_range", None, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("dde_host_alloc", C.c_void_p, [_SZ]),
     ("dde_host_free", None, [C.c_void_p]),

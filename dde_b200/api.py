@@ -168,7 +168,7 @@ def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, st
     shard the trajectories over those GPUs (dde_dopri_batch_sharded).
     `events`: one entry per critical time -- the position of the event function
     in the model's event table, or -1 for a plain stop (R/events.R merges
-    `event_time` into `tcrit` the same way); single device only.
+    `event_time` into `tcrit` the same way).
     """
     lib = _lib.load()
     y, parms_arr, n_traj, n, n_parms, stride = _prep_batch_inputs(y, parms)
@@ -189,9 +189,17 @@ def dopri_batch(y, times, func, parms=None, *, n_out=0, rtol=1e-6, atol=1e-6, st
             _dp(parms_arr) if n_parms else None, n_parms, stride, _dp(times), times.shape[0],
             _dp(tc), 0 if tc is None else tc.shape[0], _dp(y_out), _dp(out), _ip(stats),
             _ip(code), _dp(t_last), _dp(step_size)]
+    if events is not None and devices is not None:
+        ev = np.ascontiguousarray(events, dtype=np.int32).ravel()
+        if tc is None or ev.shape[0] != tc.shape[0]:
+            raise DdeError("one event index per critical time is required")
+        dev = _device_list(devices)
+        rc = lib.dde_dopri_batch_sharded_events(*args[:13], _ip(ev), *args[13:], _ip(dev),
+                                                0 if dev is None else dev.shape[0])
+        if rc != 0:
+            raise DdeError(_lib.last_error())
+        return DopriBatchResult(y_out, out, stats, code, t_last, step_size, times, int(n_history))
     if events is not None:
-        if devices is not None:
-            raise DdeError("events are not supported together with 'devices'")
         from .batch import DopriBatch
         b = DopriBatch(func, n, n_traj, n_parms=n_parms, n_out=n_out, method=method, rtol=rtol,
                        atol=atol, step_size_min=step_size_min, step_size_max=step_size_max,

@@ -173,6 +173,73 @@ class DopriBatch:
             pass
 
 
+class DopriShards:
+    """One batch resident on several GPUs of the box (dde_dopri_shards_*): a DopriBatch per
+    device over contiguous blocks of trajectories, allocated once; run_download_into
+    integrates all shards concurrently and streams every shard's results into its slice
+    of the caller's (pinned) host arrays.  devices: None = all visible devices."""
+
+    def __init__(self, func, n, n_traj, *, devices=None, n_parms=0, n_out=0, method="dopri5",
+                 rtol=1e-6, atol=1e-6, step_size_min=0.0, step_size_max=float("inf"),
+                 step_size_initial=0.0, step_max_n=100000, step_size_min_allow=False,
+                 stiff_check=0, n_history=0, grow_history=False, return_initial=True):
+        self._lib = _lib.load()
+        self.ctl = _control(method, rtol, atol, step_size_min, step_size_max, step_size_initial,
+                            step_max_n, step_size_min_allow, stiff_check, n_history, grow_history,
+                            return_initial)
+        self.n, self.n_traj, self.n_parms, self.n_out = int(n), int(n_traj), int(n_parms), int(n_out)
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32).ravel()
+        self._h = self._lib.dde_dopri_shards_alloc(
+            func.encode(), C.byref(self.ctl), self.n, self.n_out, self.n_parms, self.n_traj,
+            None if dev is None else dev.ctypes.data_as(_lib.c_int32_p),
+            0 if dev is None else dev.shape[0])
+        if not self._h:
+            raise DdeError(_lib.last_error())
+        self.n_shards = int(self._lib.dde_dopri_shards_count(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DdeError(_lib.last_error())
+
+    def upload(self, y0=None, parms=None, shared_parms=False):
+        stride = 0 if shared_parms else self.n_parms
+        self._check(self._lib.dde_dopri_shards_upload(self._h, _ptr(y0), _ptr(parms), stride))
+
+    def set_times(self, times, tcrit=None):
+        times = _f64(times, "times").ravel()
+        tc = None if tcrit is None else _f64(tcrit, "tcrit").ravel()
+        self._check(self._lib.dde_dopri_shards_set_times(
+            self._h, times.ctypes.data_as(c_double_p), times.shape[0],
+            None if tc is None else tc.ctypes.data_as(c_double_p), 0 if tc is None else tc.shape[0]))
+        self.times = times
+
+    def set_events(self, events):
+        ev = np.ascontiguousarray(events, dtype=np.int32).ravel()
+        self._check(self._lib.dde_dopri_shards_set_events(
+            self._h, ev.ctypes.data_as(_lib.c_int32_p), ev.shape[0]))
+
+    def run_download_into(self, y_out=None, out=None, stats=None, code=None, t_last=None,
+                          step_size=None):
+        self._check(self._lib.dde_dopri_shards_run_download(
+            self._h, _ptr(y_out), _ptr(out), _ptr(stats), _ptr(code), _ptr(t_last),
+            _ptr(step_size)))
+
+    def last_ms(self):
+        """device time of the slowest shard's last run"""
+        return self._lib.dde_dopri_shards_last_ms(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dde_dopri_shards_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DifeqBatch:
     def __init__(self, target, n, n_rep, *, n_parms=0, n_out=0, n_history=0, restartable=False):
         self._lib = _lib.load()

@@ -1938,23 +1938,235 @@ T *offset(T *p, size_t k) {
 
 extern "C" {
 
+int dde_dopri_batch_sharded_events(const char *model, const dde_dopri_control *ctl, size_t n,
+                                   size_t n_out, size_t n_traj, const double *y0,
+                                   const double *parms, size_t n_parms, size_t parms_stride,
+                                   const double *times, size_t n_times, const double *tcrit,
+                                   size_t n_tcrit, const int32_t *event, double *y_out,
+                                   double *out, int32_t *stats, int32_t *code, double *t_last,
+                                   double *step_size, const int32_t *devices, size_t n_devices) {
+  if (ctl == nullptr || n_times < 2) {
+    return fail("ctl must not be NULL and at least two times must be given");
+  }
+  if (y0 == nullptr) {
+    return fail("y0 must not be NULL");
+  }
+  if (n_parms > 0 && parms == nullptr) {
+    return fail("parms must not be NULL when n_parms > 0");
+  }
+  const size_t nt = ctl->return_initial ? n_times : n_times - 1;
+  return run_sharded(n_traj, devices, n_devices, [&](size_t first, size_t count) {
+    dde_dopri_batch_t *b = dde_dopri_batch_alloc(model, ctl, n, n_out, n_parms, count);
+    if (b == nullptr) {
+      return 1;
+    }
+    int rc = dde_dopri_batch_upload(b, offset(y0, first * n), offset(parms, first * parms_stride),
+                                    parms_stride);
+    rc = rc ? rc : dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
+    if (rc == 0 && event != nullptr) {
+      rc = dde_dopri_batch_set_events(b, event, n_tcrit);
+    }
+    rc = rc ? rc
+            : dde_dopri_batch_run_download(b, offset(y_out, first * n * nt),
+                                           offset(out, first * n_out * nt),
+                                           offset(stats, first * 4), offset(code, first),
+                                           offset(t_last, first), offset(step_size, first));
+    dde_dopri_batch_free(b);
+    return rc;
+  });
+}
+
 int dde_dopri_batch_sharded(const char *model, const dde_dopri_control *ctl, size_t n,
                             size_t n_out, size_t n_traj, const double *y0, const double *parms,
                             size_t n_parms, size_t parms_stride, const double *times,
                             size_t n_times, const double *tcrit, size_t n_tcrit, double *y_out,
                             double *out, int32_t *stats, int32_t *code, double *t_last,
                             double *step_size, const int32_t *devices, size_t n_devices) {
-  if (ctl == nullptr || n_times < 2) {
-    return fail("ctl must not be NULL and at least two times must be given");
+  return dde_dopri_batch_sharded_events(model, ctl, n, n_out, n_traj, y0, parms, n_parms,
+                                        parms_stride, times, n_times, tcrit, n_tcrit, nullptr,
+                                        y_out, out, stats, code, t_last, step_size, devices,
+                                        n_devices);
+}
+
+/* ---- a batch resident on several GPUs: one dde_dopri_batch_t per device -------- */
+
+struct dde_dopri_shards_s {
+  std::vector<dde_dopri_batch_t *> shard;
+  std::vector<int> device;
+  std::vector<size_t> first, count;
+  size_t n = 0, n_out = 0, n_traj = 0, nt = 0;
+};
+
+void dde_dopri_shards_free(dde_dopri_shards_t *h) {
+  if (h == nullptr) {
+    return;
   }
-  const size_t nt = ctl->return_initial ? n_times : n_times - 1;
-  return run_sharded(n_traj, devices, n_devices, [&](size_t first, size_t count) {
-    return dde_dopri_batch(model, ctl, n, n_out, count, offset(y0, first * n),
-                           offset(parms, first * parms_stride), n_parms, parms_stride, times,
-                           n_times, tcrit, n_tcrit, offset(y_out, first * n * nt),
-                           offset(out, first * n_out * nt), offset(stats, first * 4),
-                           offset(code, first), offset(t_last, first), offset(step_size, first));
+  int current = 0;
+  (void) cudaGetDevice(&current);
+  for (size_t r = 0; r < h->shard.size(); ++r) {
+    if (h->shard[r] != nullptr) {
+      (void) cudaSetDevice(h->device[r]);
+      dde_dopri_batch_free(h->shard[r]);
+    }
+  }
+  (void) cudaSetDevice(current);
+  delete h;
+}
+
+dde_dopri_shards_t *dde_dopri_shards_alloc(const char *model, const dde_dopri_control *ctl,
+                                           size_t n, size_t n_out, size_t n_parms, size_t n_traj,
+                                           const int32_t *devices, size_t n_devices) {
+  std::vector<int> devs;
+  if (devices != nullptr && n_devices > 0) {
+    devs.assign(devices, devices + n_devices);
+  } else {
+    for (int d = 0; d < dde_device_count(); ++d) {
+      devs.push_back(d);
+    }
+  }
+  if (devs.empty()) {
+    fail("no CUDA device available: dde_b200 has no CPU fallback");
+    return nullptr;
+  }
+  const int visible = dde_device_count();
+  int current = 0;
+  (void) cudaGetDevice(&current);
+  dde_dopri_shards_t *h = new dde_dopri_shards_s();
+  h->n = n;
+  h->n_out = n_out;
+  h->n_traj = n_traj;
+  for (size_t r = 0; r < devs.size(); ++r) {
+    size_t first = 0, count = 0;
+    dde_shard_range(n_traj, devs.size(), r, &first, &count);
+    if (count == 0) {
+      continue;
+    }
+    if (devs[r] < 0 || devs[r] >= visible) {
+      fail("device %d is not visible (%d devices)", devs[r], visible);
+      dde_dopri_shards_free(h);
+      return nullptr;
+    }
+    (void) cudaSetDevice(devs[r]);
+    dde_dopri_batch_t *b = dde_dopri_batch_alloc(model, ctl, n, n_out, n_parms, count);
+    if (b == nullptr) {
+      const std::string msg = g_last_error;
+      (void) cudaSetDevice(current);
+      dde_dopri_shards_free(h);
+      fail("shard %zu (device %d): %s", r, devs[r], msg.c_str());
+      return nullptr;
+    }
+    h->shard.push_back(b);
+    h->device.push_back(devs[r]);
+    h->first.push_back(first);
+    h->count.push_back(count);
+  }
+  (void) cudaSetDevice(current);
+  return h;
+}
+
+size_t dde_dopri_shards_count(dde_dopri_shards_t *h) { return h ? h->shard.size() : 0; }
+
+} /* extern "C" */
+
+namespace {
+/* `work(r)` for every shard, with its device current: in turn (asynchronous calls), or on
+   one host thread each (blocking calls); the first failure is reported */
+template <class Work>
+int for_each_shard(dde_dopri_shards_t *h, bool threads, Work work) {
+  if (h == nullptr) {
+    return fail("handle must not be NULL");
+  }
+  const size_t world = h->shard.size();
+  std::vector<int> rc(world, 0);
+  std::vector<std::string> msg(world);
+  int current = 0;
+  (void) cudaGetDevice(&current);
+  auto one = [&](size_t r) {
+    if (cudaSetDevice(h->device[r]) != cudaSuccess) {
+      (void) cudaGetLastError();
+      rc[r] = 1;
+      msg[r] = "cudaSetDevice failed";
+      return;
+    }
+    rc[r] = work(r);
+    if (rc[r] != 0) {
+      msg[r] = g_last_error; /* thread-local */
+    }
+  };
+  if (threads && world > 1) {
+    std::vector<std::thread> pool;
+    for (size_t r = 0; r < world; ++r) {
+      pool.emplace_back(one, r);
+    }
+    for (std::thread &t : pool) {
+      t.join();
+    }
+  } else {
+    for (size_t r = 0; r < world; ++r) {
+      one(r);
+    }
+    (void) cudaSetDevice(current);
+  }
+  for (size_t r = 0; r < world; ++r) {
+    if (rc[r] != 0) {
+      return fail("shard %zu (device %d): %s", r, h->device[r], msg[r].c_str());
+    }
+  }
+  return 0;
+}
+} /* namespace */
+
+extern "C" {
+
+int dde_dopri_shards_upload(dde_dopri_shards_t *h, const double *y0, const double *parms,
+                            size_t parms_stride) {
+  return for_each_shard(h, false, [&](size_t r) {
+    return dde_dopri_batch_upload(h->shard[r], offset(y0, h->first[r] * h->n),
+                                  offset(parms, h->first[r] * parms_stride), parms_stride);
   });
+}
+
+int dde_dopri_shards_set_times(dde_dopri_shards_t *h, const double *times, size_t n_times,
+                               const double *tcrit, size_t n_tcrit) {
+  const int rc = for_each_shard(h, false, [&](size_t r) {
+    return dde_dopri_batch_set_times(h->shard[r], times, n_times, tcrit, n_tcrit);
+  });
+  if (rc == 0) {
+    h->nt = h->shard.empty() ? 0 : h->shard[0]->nt;
+  }
+  return rc;
+}
+
+int dde_dopri_shards_set_events(dde_dopri_shards_t *h, const int32_t *event, size_t n_tcrit) {
+  return for_each_shard(h, false, [&](size_t r) {
+    return dde_dopri_batch_set_events(h->shard[r], event, n_tcrit);
+  });
+}
+
+int dde_dopri_shards_run_download(dde_dopri_shards_t *h, double *y_out, double *out,
+                                  int32_t *stats, int32_t *code, double *t_last,
+                                  double *step_size) {
+  return for_each_shard(h, true, [&](size_t r) {
+    const size_t f = h->first[r];
+    return dde_dopri_batch_run_download(h->shard[r], offset(y_out, f * h->n * h->nt),
+                                        offset(out, f * h->n_out * h->nt), offset(stats, f * 4),
+                                        offset(code, f), offset(t_last, f), offset(step_size, f));
+  });
+}
+
+double dde_dopri_shards_last_ms(dde_dopri_shards_t *h) {
+  double ms = 0.0;
+  if (h != nullptr) {
+    int current = 0;
+    (void) cudaGetDevice(&current);
+    for (size_t r = 0; r < h->shard.size(); ++r) {
+      (void) cudaSetDevice(h->device[r]);
+      const double m = dde_dopri_batch_last_ms(h->shard[r]);
+      ms = m > ms ? m : ms;
+    }
+    (void) cudaSetDevice(current);
+  }
+  return ms;
 }
 
 int dde_difeq_batch_sharded(const char *model, size_t n, size_t n_out, size_t n_rep,

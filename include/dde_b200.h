@@ -319,6 +319,18 @@ int dde_dopri_batch_sharded(const char *model, const dde_dopri_control *ctl,
                             double *out, int32_t *stats, int32_t *code,
                             double *t_last, double *step_size,
                             const int32_t *devices, size_t n_devices);
+/* ... with the model's events at the critical times (dde_dopri_batch_set_events;
+ * event == NULL: plain stops), src/dopri.c:476-491 */
+int dde_dopri_batch_sharded_events(const char *model, const dde_dopri_control *ctl,
+                                   size_t n, size_t n_out, size_t n_traj,
+                                   const double *y0, const double *parms,
+                                   size_t n_parms, size_t parms_stride,
+                                   const double *times, size_t n_times,
+                                   const double *tcrit, size_t n_tcrit,
+                                   const int32_t *event, double *y_out,
+                                   double *out, int32_t *stats, int32_t *code,
+                                   double *t_last, double *step_size,
+                                   const int32_t *devices, size_t n_devices);
 int dde_difeq_batch_sharded(const char *model, size_t n, size_t n_out,
                             size_t n_rep, const double *y0,
                             const double *parms, size_t n_parms,
@@ -327,6 +339,34 @@ int dde_difeq_batch_sharded(const char *model, size_t n, size_t n_out,
                             int32_t return_initial, double *y_out, double *out,
                             int32_t *code, double *y_final,
                             const int32_t *devices, size_t n_devices);
+/* The same batch as a handle: one dde_dopri_batch_t per device, allocated once
+ * (rings included), so that repeated solves of one batch shape -- a parameter
+ * scan, the strong-scaling measurement of bench.py -- pay for allocation once.
+ * upload / set_times / set_events address every shard in turn (asynchronous
+ * copies on each shard's stream); run_download integrates all shards
+ * concurrently, one host thread per device, each streaming its results into its
+ * slice of the caller's arrays, and returns when all have finished.  last_ms:
+ * the slowest shard's device time of the last run. */
+typedef struct dde_dopri_shards_s dde_dopri_shards_t;
+dde_dopri_shards_t *dde_dopri_shards_alloc(const char *model,
+                                           const dde_dopri_control *ctl, size_t n,
+                                           size_t n_out, size_t n_parms,
+                                           size_t n_traj, const int32_t *devices,
+                                           size_t n_devices);
+void dde_dopri_shards_free(dde_dopri_shards_t *h);
+size_t dde_dopri_shards_count(dde_dopri_shards_t *h);
+int dde_dopri_shards_upload(dde_dopri_shards_t *h, const double *y0,
+                            const double *parms, size_t parms_stride);
+int dde_dopri_shards_set_times(dde_dopri_shards_t *h, const double *times,
+                               size_t n_times, const double *tcrit,
+                               size_t n_tcrit);
+int dde_dopri_shards_set_events(dde_dopri_shards_t *h, const int32_t *event,
+                                size_t n_tcrit);
+int dde_dopri_shards_run_download(dde_dopri_shards_t *h, double *y_out,
+                                  double *out, int32_t *stats, int32_t *code,
+                                  double *t_last, double *step_size);
+double dde_dopri_shards_last_ms(dde_dopri_shards_t *h);
+
 /* The block of a batch of n_total that shard `rank` of `world` owns:
  * [*first, *first + *count).  Blocks differ in size by at most one. */
 void dde_shard_range(size_t n_total, size_t world, size_t rank, size_t *first,

@@ -124,9 +124,23 @@ def test_critical_times(backend):
 def test_controls(backend):
     lor = ("lorenz", [[10.0, 1.0, 1.0]], np.linspace(0, 3, 31), [10.0, 28.0, 8.0 / 3.0])
     # n_eval drops by exactly 1 with step_size_initial (tests/testthat/test-ode.R:398-404)
-    a, _ = check_dopri(backend, *lor)
-    b, _ = check_dopri(backend, *lor, step_size_initial=1e-3)
-    assert b.statistics[0, 0] < a.statistics[0, 0] + 100
+    # when the given initial step is the one dopri_h_init would have chosen: its one
+    # extra evaluation (src/dopri.c:555) is all that goes
+    # (tests/testthat/test-ode.R:384-404: the first step read off the history)
+    tt = np.linspace(0, 1, 200)
+    lor1 = ("lorenz", [[10.0, 1.0, 1.0]], tt, [10.0, 28.0, 8.0 / 3.0])
+    a, _ = check_dopri(backend, *lor1, n_history=500)
+    hb = dde_b200.DopriBatch("lorenz", 3, 1, n_parms=3, n_history=500)
+    hb.upload(np.array([[10.0, 1.0, 1.0]]), np.array([[10.0, 28.0, 8.0 / 3.0]]))
+    hb.set_times(tt)
+    hb.run()
+    h0 = float(hb.history(0)[0, -1])
+    hb.close()
+    b, _ = check_dopri(backend, *lor1, n_history=500, step_size_initial=h0)
+    assert b.statistics[0, 0] == a.statistics[0, 0] - 1
+    np.testing.assert_array_equal(b.statistics[0, 1:], a.statistics[0, 1:])
+    assert_bits_equal(a.y, b.y, "y")
+    check_dopri(backend, *lor, step_size_initial=1e-3)
     got, _ = check_dopri(backend, *lor, step_max_n=10)
     assert got.code[0] == -3
     check_dopri(backend, *lor, step_size_max=0.01)
@@ -296,6 +310,60 @@ def test_sharded_equals_single_device(backend):
     with pytest.raises(dde_b200.DdeError, match="not visible"):
         dde_b200.dopri_batch(y0[:, :1], times, "mackey_glass", parms[:, :1].repeat(3, 1),
                              devices=[99], method="dopri853", n_history=8)
+
+
+def test_shards_handle_and_sharded_events(backend):
+    """the resident form of the sharded batch (dde_dopri_shards_*: one handle per device,
+    allocated once, run twice) and events through the sharded entry points"""
+    model, y0, parms, times, kw = workloads.mackey_glass(3000)
+    one = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+    nt = times.shape[0]
+    for devices in ([0], None, [0, 0, 0]):  # the same device three times: three shards
+        h = dde_b200.DopriShards(model, 1, 3000, devices=devices, n_parms=3, **kw)
+        h.set_times(times)
+        y = np.empty((3000, nt, 1))
+        stats = np.empty((3000, 4), dtype=np.int32)
+        code = np.empty((3000,), dtype=np.int32)
+        t_last = np.empty((3000,))
+        step = np.empty((3000,))
+        for rep in range(2):
+            h.upload(y0, parms)
+            y.fill(np.nan)
+            h.run_download_into(y, None, stats, code, t_last, step)
+            np.testing.assert_array_equal(stats, one.statistics)
+            np.testing.assert_array_equal(code, one.code)
+            assert_bits_equal(y, one.y, "y")
+            assert_bits_equal(t_last, one.t_last, "t_last")
+            assert_bits_equal(step, one.step_size, "step_size")
+        assert h.last_ms() > 0
+        if devices == [0, 0, 0]:
+            assert h.n_shards == 3
+        h.close()
+    with pytest.raises(dde_b200.DdeError, match="not visible"):
+        dde_b200.DopriShards(model, 1, 10, devices=[99], n_parms=3, **kw)
+    # events (src/dopri.c:476-491) on a sharded batch
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(0.5, 2.0, size=(7, 3))
+    r = rng.uniform(0.1, 1.0, size=(7, 3))
+    times = np.linspace(0, 3, 13)
+    for method in ("dopri5", "dopri853"):
+        want = pyoracle.dopri_batch(backend, "exponential", y0, times, r, tcrit=[0.5, 1.0, 2.0],
+                                    events=[1, -1, 3], method=method)
+        for devices in ("all", [0, 0]):
+            got = dde_b200.dopri_batch(y0, times, "exponential", r, tcrit=[0.5, 1.0, 2.0],
+                                       events=[1, -1, 3], method=method, devices=devices)
+            np.testing.assert_array_equal(got.statistics, want.statistics)
+            assert_bits_equal(got.y, want.y, "y")
+        h = dde_b200.DopriShards("exponential", 3, 7, devices=[0, 0], n_parms=3, method=method)
+        h.upload(y0, r)
+        h.set_times(times, [0.5, 1.0, 2.0])
+        h.set_events([1, -1, 3])
+        y = np.empty((7, 13, 3))
+        stats = np.empty((7, 4), dtype=np.int32)
+        h.run_download_into(y, None, stats, None, None, None)
+        np.testing.assert_array_equal(stats, want.statistics)
+        assert_bits_equal(y, want.y, "y")
+        h.close()
 
 
 # ---- the staged lag window under stress -------------------------------------------
