@@ -127,9 +127,13 @@ def main():
                        "d2h_GBps": n_e2e * (args.c3_times - 1) * 24 / (e2e_ms * 1e-3) / 1e9}
         print(json.dumps(line))
 
-    # C4: delayed SIR map through difeq_replicate
-    model, y0, parms, steps, kw = workloads.sir_delay(args.c4_rep, n_steps=args.c4_steps)
-    b = dde_b200.DifeqBatch(model, 3, args.c4_rep, n_parms=2, n_history=kw["n_history"])
+    print(json.dumps(c4(args.c4_rep, args.c4_steps)))
+
+
+def c4(n_rep, n_steps):
+    """C4: delayed SIR map through difeq_replicate; returns the result line"""
+    model, y0, parms, steps, kw = workloads.sir_delay(n_rep, n_steps=n_steps)
+    b = dde_b200.DifeqBatch(model, 3, n_rep, n_parms=2, n_history=kw["n_history"])
     b.upload(y0, parms)
     b.set_steps(steps, kw["return_initial"])
     b.run()
@@ -150,15 +154,16 @@ def main():
         b.download()
         t.append(1e3 * (time.perf_counter() - t0))
     b.close()
-    n_steps_total = float(args.c4_rep) * args.c4_steps
-    line = {"workload": "C4 delayed SIR difeq_replicate", "n_rep": args.c4_rep,
-            "n_steps": args.c4_steps, "ms": ms, "e2e_ms": float(np.median(t[1:])),
+    n_steps_total = float(n_rep) * n_steps
+    line = {"workload": "C4 delayed SIR difeq_replicate", "n_rep": n_rep,
+            "n_steps": n_steps, "ms": ms, "e2e_ms": float(np.median(t[1:])),
             "steps_per_s": n_steps_total / (ms * 1e-3),
-            "replicates_per_s": args.c4_rep / (ms * 1e-3),
+            "replicates_per_s": n_rep / (ms * 1e-3),
             "history": "on chip (shared memory); the ring figure is what an HBM ring would move",
+            "bound": "issue latency of the 8-flop recurrence (FP64 fraction of the FMA-free rate)",
             "failed": int((code != 1).sum()), "checksum": float(y.sum())}
     line.update(rates(8.0 * n_steps_total, 40.0 * n_steps_total, ms))
-    print(json.dumps(line))
+    return line
 
 
 def c5(n_traj):
@@ -174,8 +179,9 @@ def c5(n_traj):
     line = {"workload": "C5 seir_age dop853 n=512 block-per-trajectory", "n_traj": n_traj,
             "ms": ms, "e2e_ms": e2e_ms, "trajectories_per_s": n_traj / (ms * 1e-3),
             "accepted_steps_per_s": A / (ms * 1e-3), "failed": int((code != 1).sum())}
+    line["bound"] = "block barriers around the ordered norms, then FP64 issue"
     line.update(rates(flops, ring_bytes, ms))
-    print(json.dumps(line))
+    return line
 
 
 if __name__ == "__main__":
@@ -184,5 +190,5 @@ if __name__ == "__main__":
     if "--c5-traj" in " ".join(sys.argv) or True:
         ap = argparse.ArgumentParser()
         ap.add_argument("--c5-traj", type=int, default=4096)
-        c5(ap.parse_known_args()[0].c5_traj)
+        print(json.dumps(c5(ap.parse_known_args()[0].c5_traj)))
     print("elapsed %.1f s" % (time.time() - t0), file=sys.stderr)

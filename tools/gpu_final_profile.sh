@@ -12,6 +12,6 @@ python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_$tag.l
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
   > gpurun_out/ncu_launches_$tag.log 2>&1
-timeout 1500 ncu --set full --import-source on --clock-control none -k regex:dopri_tpt -s 1 -c 1 \
+timeout 1500 ncu --set full --import-source on --clock-control none -k regex:"dopri_tpt|dopri_dde1" -s 1 -c 1 \
   -f -o gpurun_out/prof_${tag}_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline \
   > gpurun_out/ncu_full_$tag.log 2>&1
