@@ -182,11 +182,11 @@ def algorithmic_work(stats, n=1, n_parms=3, n_lags=1, n_lag_idx=1, nt=11, order=
 
 
 def source_hash():
-    """sha256 over the device sources (dde_b200/csrc, dde_b200/models): what a committed
+    """sha256 over the device sources (include/dde_b200, dde_b200/csrc, dde_b200/models): what a committed
     ncu capture is valid for"""
     import hashlib
     h = hashlib.sha256()
-    for d in ("dde_b200/csrc", "dde_b200/models"):
+    for d in ("include/dde_b200", "dde_b200/csrc", "dde_b200/models"):
         for f in sorted((ROOT / d).iterdir()):
             if f.is_file():
                 h.update(f.name.encode())

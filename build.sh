@@ -6,7 +6,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false
        -Xcompiler -fPIC,-mfma,-ffp-contract=off,-Wall,-Wno-unused-function
-       -Iinclude -Idde_b200/csrc ${DDE_NVCC_EXTRA:-})
+       -Iinclude -Iinclude/dde_b200 -Idde_b200/models ${DDE_NVCC_EXTRA:-})
 # DDE_OUT / DDE_TAG: build an experimental variant next to the product library
 OUT=${DDE_OUT:-dde_b200/libdde_b200.so}
 TAG=${DDE_TAG:-}

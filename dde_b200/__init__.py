@@ -11,8 +11,9 @@ from .api import (DOPRI_5, DOPRI_853, OK_COMPLETE, DdeError, DifeqResult, DopriB
                   DopriHistory, DopriResult, difeq, difeq_replicate, dopri, dopri5, dopri853,
                   dopri_batch, dopri_continue, dopri_interpolate, models, strerror)
 from .batch import DifeqBatch, DopriBatch, DopriShards  # noqa: F401
+from ._lib import load_model_library  # noqa: F401
 
 __all__ = [
     "dopri", "dopri5", "dopri853", "dopri_batch", "dopri_continue", "dopri_interpolate", "difeq",
-    "difeq_replicate", "DopriBatch", "DopriShards", "DifeqBatch", "models", "strerror", "DdeError",
+    "difeq_replicate", "DopriBatch", "DopriShards", "DifeqBatch", "load_model_library", "models", "strerror", "DdeError",
 ]

@@ -134,7 +134,25 @@ def load():
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib
+    for path in filter(None, os.environ.get("DDE_B200_MODEL_LIBS", "").split(os.pathsep)):
+        load_model_library(path)
     return lib
+
+
+_model_libs = {}
+
+
+def load_model_library(path):
+    """dyn.load() for a dde_b200 model library (R/common.R:89-98): a shared object built
+    from a model translation unit (include/dde_b200/dde_model.cuh).  Its
+    static initialisers register its models by name with the product library
+    (dde_register_model); they are then available to every entry point.  Libraries named
+    in DDE_B200_MODEL_LIBS (os.pathsep-separated) are loaded with the product library."""
+    load()
+    path = str(Path(path).resolve())
+    if path not in _model_libs:
+        _model_libs[path] = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    return _model_libs[path]
 
 
 def last_error():

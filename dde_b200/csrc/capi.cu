@@ -211,7 +211,8 @@ struct dde_dopri_batch_s {
   int *d_stats = nullptr, *d_code = nullptr;
   double *d_ring = nullptr;
   double *d_init_k1 = nullptr, *d_init_h = nullptr, *d_y_final = nullptr;
-  int *d_event = nullptr; /* [cap_tcrit] event index per critical time, or none set */
+  int *d_event = nullptr; /* [cap_event] event index per critical time, or none set */
+  size_t cap_event = 0;
   bool have_events = false;
   unsigned *d_ring_count = nullptr;
   unsigned long long *d_next = nullptr;
@@ -534,8 +535,32 @@ dde_dopri_batch_t *dde_dopri_batch_alloc(const char *model, const dde_dopri_cont
   return b;
 }
 
+} /* extern "C" */
+
+namespace {
+int dopri_upload_async(dde_dopri_batch_t *b, const double *y0, const double *parms,
+                       size_t parms_stride);
+}
+
+extern "C" {
+
 int dde_dopri_batch_upload(dde_dopri_batch_t *b, const double *y0, const double *parms,
                            size_t parms_stride) {
+  const int rc = dopri_upload_async(b, y0, parms, parms_stride);
+  if (rc != 0) {
+    return rc;
+  }
+  /* the caller's buffers are the caller's again on return (pinned memory makes the
+     copies truly asynchronous) */
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+} /* extern "C" */
+
+namespace {
+int dopri_upload_async(dde_dopri_batch_t *b, const double *y0, const double *parms,
+                       size_t parms_stride) {
   if (b == nullptr) {
     return fail("NULL handle");
   }
@@ -556,6 +581,9 @@ int dde_dopri_batch_upload(dde_dopri_batch_t *b, const double *y0, const double 
   }
   return 0;
 }
+} /* namespace */
+
+extern "C" {
 
 int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times, size_t n_times,
                               const double *tcrit, size_t n_tcrit) {
@@ -645,6 +673,9 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
   }
   if (!b->have_times || !b->have_y0) {
     return fail("upload y0 and set times before running");
+  }
+  if (b->ctl.n_history > 0 && b->d_ring == nullptr) {
+    return fail("the handle has no history rings (a failed grow_history): free it");
   }
   DDE_CUDA(cudaSetDevice(b->device));
   DDE_CUDA(cudaEventRecord(b->ev0, b->stream));
@@ -760,13 +791,23 @@ static int dopri_run_grow(dde_dopri_batch_t *b) {
     if ((size_t) most <= cap) {
       return 0;
     }
-    const size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
+    size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
+    bigger = bigger > 0x7fffffffu ? 0x7fffffffu : bigger; /* the kernels index entries with int */
     const size_t hl = (size_t) b->order * b->n + 2;
+    /* the old rings go first (the run is repeated from scratch, and both sizes together
+       may not fit); a failure leaves the handle without rings, which dopri_run_impl
+       refuses to run on until the rings can be allocated again */
     free_dev(b->d_ring);
+    b->d_ring = nullptr;
     if (cudaMalloc(&b->d_ring, sizeof(double) * hl * bigger * b->n_traj) != cudaSuccess) {
       (void) cudaGetLastError();
       b->d_ring = nullptr;
       b->ran = false;
+      /* back to the capacity asked for, so that a later run starts over from there */
+      if (cudaMalloc(&b->d_ring, sizeof(double) * hl * cap * b->n_traj) != cudaSuccess) {
+        (void) cudaGetLastError();
+        b->d_ring = nullptr;
+      }
       return fail("grow_history: cannot allocate %.2f GB of history rings (%zu entries per "
                   "trajectory)", (double) (sizeof(double) * hl * bigger * b->n_traj) / 1e9, bigger);
     }
@@ -880,6 +921,9 @@ int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event, size_
     return fail("events must name one entry per critical time (%zu), got %zu", b->n_tcrit,
                 n_tcrit);
   }
+  if (event == nullptr && n_tcrit > 0) {
+    return fail("event must not be NULL when there are critical times");
+  }
   bool any = false;
   for (size_t i = 0; i < n_tcrit; ++i) {
     if (event[i] >= b->model->n_events) {
@@ -890,8 +934,16 @@ int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event, size_
   }
   DDE_CUDA(cudaSetDevice(b->device));
   if (any) {
+    if (n_tcrit > b->cap_event) { /* one buffer per handle, grown when needed */
+      free_dev(b->d_event);
+      b->d_event = nullptr;
+      b->cap_event = 0;
       DDE_CUDA(cudaMalloc(&b->d_event, sizeof(int) * n_tcrit));
-    DDE_CUDA(cudaMemcpy(b->d_event, event, sizeof(int) * n_tcrit, cudaMemcpyHostToDevice));
+      b->cap_event = n_tcrit;
+    }
+    DDE_CUDA(cudaMemcpyAsync(b->d_event, event, sizeof(int) * n_tcrit, cudaMemcpyHostToDevice,
+                             b->stream));
+    DDE_CUDA(cudaStreamSynchronize(b->stream));
   }
   b->have_events = any;
   return 0;
@@ -957,14 +1009,24 @@ int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double
     }
   }
   for (;;) {
-    if (y != nullptr) { /* a new state: it is also the pre-history from now on, src/dopri.c:157 */
-      DDE_CUDA(cudaMemcpyAsync(b->d_y0, y, sizeof(double) * n * nt, cudaMemcpyHostToDevice,
-                               b->stream));
-    } else {
-      DDE_CUDA(cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * n * nt,
-                               cudaMemcpyDeviceToDevice, b->stream));
-    }
+    /* the times first: a refused set of times leaves the state as it was */
     int rc = dde_dopri_batch_set_times(b, times, n_times, tcrit, n_tcrit);
+    if (rc == 0) {
+      cudaError_t e1;
+      if (y != nullptr) { /* a new state: also the pre-history from now on, src/dopri.c:157 */
+        e1 = cudaMemcpyAsync(b->d_y0, y, sizeof(double) * n * nt, cudaMemcpyHostToDevice,
+                             b->stream);
+        /* the caller's buffer is the caller's again on return */
+        e1 = e1 != cudaSuccess ? e1 : cudaStreamSynchronize(b->stream);
+      } else {
+        e1 = cudaMemcpyAsync(b->d_y0, b->d_y_final, sizeof(double) * n * nt,
+                             cudaMemcpyDeviceToDevice, b->stream);
+      }
+      if (e1 != cudaSuccess) {
+        release();
+        return fail("CUDA error: %s", cudaGetErrorString(e1));
+      }
+    }
     rc = rc ? rc : dopri_run_impl(b, 1);
     if (rc != 0 || !grow) {
       release();
@@ -991,16 +1053,38 @@ int dde_dopri_batch_continue(dde_dopri_batch_t *b, const double *y, const double
       return 0;
     }
     /* a ring wrapped: back to the state before the continuation, in larger rings */
-    const size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
-    free_dev(b->d_ring);
-    if (cudaMalloc(&b->d_ring, sizeof(double) * hl * bigger * nt) != cudaSuccess) {
+    size_t bigger = (size_t) most > 2 * cap ? (size_t) most : 2 * cap;
+    bigger = bigger > 0x7fffffffu ? 0x7fffffffu : bigger;
+    double *new_ring = nullptr;
+    if (cudaMalloc(&new_ring, sizeof(double) * hl * bigger * nt) != cudaSuccess) {
       (void) cudaGetLastError();
-      b->d_ring = nullptr;
-      b->ran = false;
+      /* put the state the continuation started from back (rings of the old capacity: the
+         kept copy), so that the handle is what it was before the call */
+      cudaError_t e2 = cudaMemcpyAsync(b->d_ring, kept_ring, sizeof(double) * hl * snap_cap * nt,
+                                       cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaMemcpyAsync(b->d_t_last, kept_t_last, sizeof(double) * nt,
+                                                    cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaMemcpyAsync(b->d_step_size, kept_step, sizeof(double) * nt,
+                                                    cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaMemcpyAsync(b->d_y_final, kept_y_final,
+                                                    sizeof(double) * n * nt,
+                                                    cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaMemcpyAsync(b->d_code, kept_code, sizeof(int) * nt,
+                                                    cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaMemcpyAsync(b->d_ring_count, kept_count,
+                                                    sizeof(unsigned) * nt,
+                                                    cudaMemcpyDeviceToDevice, b->stream);
+      e2 = e2 != cudaSuccess ? e2 : cudaStreamSynchronize(b->stream);
+      if (e2 != cudaSuccess || b->ctl.n_history != snap_cap) {
+        (void) cudaGetLastError();
+        b->ran = false; /* the state could not be restored: nothing to continue from */
+      }
       release();
       return fail("grow_history: cannot allocate %.2f GB of history rings (%zu entries per "
                   "trajectory)", (double) (sizeof(double) * hl * bigger * nt) / 1e9, bigger);
     }
+    free_dev(b->d_ring);
+    b->d_ring = new_ring;
     const long long cells = (long long) nt * (long long) snap_cap;
     ring_regrow_kernel<<<(unsigned) ((cells + threads - 1) / threads), threads, 0, b->stream>>>(
         kept_ring, b->d_ring, kept_count, (long long) nt, (unsigned) snap_cap, (unsigned) bigger,
@@ -1486,6 +1570,7 @@ int dde_difeq_batch_upload(dde_difeq_batch_t *b, const double *y0, const double 
                              b->stream));
     b->parms_stride = parms_stride;
   }
+  DDE_CUDA(cudaStreamSynchronize(b->stream)); /* the caller's buffers are the caller's again */
   return 0;
 }
 
@@ -2120,10 +2205,15 @@ extern "C" {
 
 int dde_dopri_shards_upload(dde_dopri_shards_t *h, const double *y0, const double *parms,
                             size_t parms_stride) {
-  return for_each_shard(h, false, [&](size_t r) {
-    return dde_dopri_batch_upload(h->shard[r], offset(y0, h->first[r] * h->n),
-                                  offset(parms, h->first[r] * parms_stride), parms_stride);
+  /* every shard's copies are queued before the first is waited for */
+  const int rc = for_each_shard(h, false, [&](size_t r) {
+    return dopri_upload_async(h->shard[r], offset(y0, h->first[r] * h->n),
+                              offset(parms, h->first[r] * parms_stride), parms_stride);
   });
+  if (rc != 0) {
+    return rc;
+  }
+  return for_each_shard(h, false, [&](size_t r) { return dde_dopri_batch_sync(h->shard[r]); });
 }
 
 int dde_dopri_shards_set_times(dde_dopri_shards_t *h, const double *times, size_t n_times,

@@ -22,7 +22,7 @@
  * The only addition is the DDE_MODEL_FN decoration on the model's own
  * functions (empty for C, `__device__` for nvcc).  Where the reference asks
  * for `#include <dde/dde.c>` once per shared library (inst/include/dde/dde.c),
- * a dde_b200 model file ends with DDE_REGISTER_* (dde_b200/csrc/dde_model.cuh).
+ * a dde_b200 model file ends with DDE_REGISTER_* (include/dde_b200/dde_model.cuh).
  */
 #ifndef DDE_DDE_H
 #define DDE_DDE_H
@@ -33,7 +33,7 @@
 /* ---- large models: cooperative evaluation (an extension, optional) --------
  *
  * A model with hundreds of equations is integrated by a whole thread block
- * per trajectory (dde_b200/csrc/dopri_coop_kernel.cuh), and its deriv() is
+ * per trajectory (include/dde_b200/dopri_coop_kernel.cuh), and its deriv() is
  * then called by all threads of the block at once.  Written with the three
  * macros below the same source still compiles as plain sequential C (for the
  * reference solver / the oracle) and as a thread-per-trajectory device

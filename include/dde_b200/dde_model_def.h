@@ -84,7 +84,7 @@
     static __device__ __forceinline__ void deriv_scoped(Scoped &sc, size_t n, double t,        \
                                                         const double *y, double *dydt,         \
                                                         const void *data) {                    \
-      SCOPE_CALL(sc, DERIV)(n, t, y, dydt, data);                                              \
+      SCOPE_CALL(sc, DERIV)(n, t, (double *) y, dydt, (void *) data);                          \
     }                                                                                          \
     static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT), N_EVENTS = (NEVENTS);       \
     static constexpr int N_LAGS = (NLAGS);                                                     \
@@ -93,7 +93,9 @@
     }                                                                                          \
     static __device__ __forceinline__ void deriv(size_t n, double t, const double *y,          \
                                                  double *dydt, const void *data) {             \
-      DERIV(n, t, y, dydt, data);                                                              \
+      /* the casts: a model written for the reference may take y and data without const  \
+         (inst/examples/seir.c:5), which C lets through a function pointer */                \
+      DERIV(n, t, (double *) y, dydt, (void *) data);                                          \
     }                                                                                          \
     static __device__ __forceinline__ void output(size_t n, double t, const double *y,         \
                                                   size_t n_out, double *out,                   \

@@ -115,7 +115,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         p[i] = a.parms[rep * a.parms_stride + i];
       }
     }
-    double y[NMAX], y_next[NMAX], o[OMAX];
+    /* rows of one array: see the note on the model's dydt in dopri_init_kernel
+       (dopri_kernels.cuh) -- here a local array of the inlined target against y_next / out */
+    struct {
+      double y[NMAX], y_next[NMAX], o[OMAX];
+    } loc;
+    double *const y = loc.y, *const y_next = loc.y_next, *const o = loc.o;
     const double *y0 = a.y0 + rep * n;
 #pragma unroll
     for (int i = 0; i < n; ++i) {

@@ -214,7 +214,12 @@ dopri_tpt_kernel(const DopriArgs a) {
   bool active = false; /* this lane holds a trajectory */
   bool done = false;   /* ... whose integration has ended */
   double p[PMAX];
-  double y[NMAX], k1[NMAX];
+  /* y, k1 and the vectors every evaluation is handed (its input, its result) are rows of
+     ONE array that is live from the first line to the last, so that the compiler cannot
+     give a local array of the inlined model the stack slot of the model's own dydt (the
+     note in dopri_init_kernel below) */
+  double loc[4][NMAX];
+  double *const y = loc[0], *const k1 = loc[1], *const yin = loc[2], *const kt = loc[3];
   double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
   bool stop = false, last = false, reject = false;
   int times_idx = 1, tcrit_idx = 0;
@@ -246,9 +251,16 @@ dopri_tpt_kernel(const DopriArgs a) {
 
   for (;;) {
     if (STAGE_OUT) {
+      /* the lanes that arrive here together flush together.  Any subset of the warp is a
+         correct group (a lane's buffer is only ever read by the group its owner is in, and
+         an owner that arrives alone writes its own rows), so the set the hardware reports
+         as converged is taken as it is. */
       const unsigned am = __activemask();
       unsigned want = __ballot_sync(am, st_count >= DDE_STAGE_FLUSH_AT(STAGE_DOUBLES));
       if (want) {
+        /* votes and shuffles are not memory barriers: order every owner's row stores
+           before its peers' loads */
+        __syncwarp(am);
         const unsigned lane = threadIdx.x & 31u;
         const int rank = __popc(am & ((1u << lane) - 1u)), nact = __popc(am);
         do {
@@ -389,7 +401,7 @@ dopri_tpt_kernel(const DopriArgs a) {
     bool accepted = false;
     double h_new = 0.0;
     /* the stage input and its time, prepared one evaluation ahead */
-    double yin[NMAX], kt[NMAX], tt = t;
+    double tt = t;
     if (run) { /* input of evaluation 0: src/dopri_5.c:54-57, src/dopri_853.c:178-181 */
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -1027,7 +1039,15 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
   const double ssi = a.restart ? a.step_size[traj] : a.step_size_initial;
   const double sign = a.sign, atol = a.atol, rtol = a.rtol;
   const int nt = a.return_initial ? a.n_times : a.n_times - 1;
-  double p[PMAX], y[NMAX], k1[NMAX];
+  /* y, k1 and the vectors of dopri_h_init's second evaluation are rows of ONE array.  The
+     model's dydt must be: nvcc 12.9 gives a local array of the inlined model (e.g.
+     `double lagged[16]` filled by ylag_all) the stack slot of a dydt array of its own when
+     it can place the two in different live ranges elsewhere, although the model reads the
+     one while it writes the other (seen with a model that reads lagged[n - 1 - i] for
+     dydt[i]: tests/models/growth.h, delayed_growth_all).  Rows of an array that is live
+     from the first line to the last cannot be shared out. */
+  double p[PMAX], loc[4][NMAX];
+  double *const y = loc[0], *const k1 = loc[1], *const f1 = loc[2], *const ye = loc[3];
 #pragma unroll
   for (int i = 0; i < PMAX; ++i) {
     if (i < n_parms) {
@@ -1096,7 +1116,6 @@ __global__ void __launch_bounds__(DDE_TPB) dopri_init_kernel(const DopriArgs a) 
     }
     h = (norm_f <= 1e-10 || norm_y <= 1e-10) ? 1e-6 : sqrt(norm_y / norm_f) * 0.01;
     h = copysign(fmin(h, a.step_size_max), sign);
-    double f1[NMAX], ye[NMAX];
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       ye[i] = y[i] + h * k1[i];

@@ -29,7 +29,7 @@
  *                         not under /root/reference: semantics restated from
  *                         the call sites -> hist_*
  *   pow                   third-party glibc 2.39 libm (src/dopri.c:500,517,
- *                         521,569) -> dde_pow (dde_b200/csrc/dde_math.h), itself
+ *                         521,569) -> dde_pow (include/dde_b200/dde_math.h), itself
  *                         pinned against libm by tests/test_math_cpu.py
  *
  * The structure is deliberately unlike the reference's hand-unrolled stage
@@ -147,15 +147,16 @@ typedef void target_fn(size_t n, size_t step, const double *y, double *y_next, s
                        double *out, const void *data);
 
 /* the shared model sources call libm by name; give them the restated pow/exp
-   exactly as the device build does (dde_b200/csrc/dde_model.cuh) */
+   exactly as the device build does (include/dde_b200/dde_model.cuh) */
 #define pow(x, y) dde_pow((x), (y))
 #define exp(x) dde_exp((x))
-#include "../dde_b200/models/difeq_models.h"
-#include "../dde_b200/models/growth.h"
+#include "../tests/models/difeq_fixtures.h"
+#include "../dde_b200/models/sir_delay.h"
+#include "../tests/models/growth.h"
 #include "../dde_b200/models/lorenz.h"
 #include "../dde_b200/models/mackey_glass.h"
 #include "../dde_b200/models/rossler.h"
-#include "../dde_b200/models/seir.h"
+#include "../tests/models/seir.h"
 #include "../dde_b200/models/seir_age.h"
 #undef pow
 #undef exp
@@ -194,6 +195,7 @@ static const model_entry MODELS[] = {
     {"linear", linear, NULL, NULL, growth_event_table, 5},
     {"delayed_growth", delayed_growth, NULL, NULL},
     {"delayed_growth_vec", delayed_growth_vec, NULL, NULL},
+    {"delayed_growth_all", delayed_growth_all, NULL, NULL},
     {"exponential_wide", exponential_wide, NULL, NULL},
     {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
     {"seir_age", seir_age, NULL, NULL},

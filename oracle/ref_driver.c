@@ -133,9 +133,10 @@ DL_FUNC R_GetCCallable(const char *package, const char *name) {
 #include "../dde_b200/models/lorenz.h"
 #include "../dde_b200/models/rossler.h"
 #include "../dde_b200/models/mackey_glass.h"
-#include "../dde_b200/models/seir.h"
-#include "../dde_b200/models/growth.h"
-#include "../dde_b200/models/difeq_models.h"
+#include "../tests/models/seir.h"
+#include "../tests/models/growth.h"
+#include "../tests/models/difeq_fixtures.h"
+#include "../dde_b200/models/sir_delay.h"
 #include "../dde_b200/models/seir_age.h"
 
 typedef struct {
@@ -172,6 +173,7 @@ static const model_entry models[] = {
     {"linear", linear, NULL, NULL, growth_event_table, 5},
     {"delayed_growth", delayed_growth, NULL, NULL},
     {"delayed_growth_vec", delayed_growth_vec, NULL, NULL},
+    {"delayed_growth_all", delayed_growth_all, NULL, NULL},
     {"exponential_wide", exponential_wide, NULL, NULL},
     {"delayed_growth_wide", delayed_growth_wide, NULL, NULL},
     {"seir_age", seir_age, NULL, NULL},

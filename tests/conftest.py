@@ -10,8 +10,22 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 
+TEST_MODELS = ROOT / "tests" / "models" / "libdde_test_models.so"
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def test_model_library():
+    """The reference's fixture models (seir, the growth family, logistic, fibonacci ...) are an
+    out-of-tree model library (tests/models/build.sh), loaded here the way a user's is: the
+    product library has none of them compiled in."""
+    if TEST_MODELS.exists():
+        import dde_b200
+        dde_b200.load_model_library(TEST_MODELS)
+    return TEST_MODELS
 
 
 def bits_equal(a, b):

@@ -1,7 +1,7 @@
 /* cuda_emu.h -- TEST INFRASTRUCTURE ONLY.
  *
  * Just enough of the CUDA device vocabulary for g++ to compile the stepping
- * kernels of dde_b200/csrc as ordinary host functions, ONE lane at a time
+ * kernels of include/dde_b200 as ordinary host functions, ONE lane at a time
  * (a warp of one thread, a block whose threads run one after the other), so
  * that the control flow and the arithmetic of the device code can be checked
  * against the oracle in this container, which has no GPU.  It exercises

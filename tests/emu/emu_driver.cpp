@@ -1,6 +1,6 @@
 /* emu_driver.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_emu.h).
  *
- * The thread-per-trajectory dopri kernels of dde_b200/csrc compiled by g++ and
+ * The thread-per-trajectory dopri kernels of include/dde_b200 compiled by g++ and
  * run one lane at a time over host arrays, behind the batch signature of the
  * checkers (oracle/pyoracle.py): tests/test_emu_cpu.py compares the result
  * with the oracle bit for bit.  This checks the device code's control flow and
@@ -30,10 +30,11 @@
 #include "../../dde_b200/models/lorenz.h"
 #include "../../dde_b200/models/mackey_glass.h"
 #include "../../dde_b200/models/rossler.h"
-#include "../../dde_b200/models/seir.h"
+#include "../models/growth.h"
+#include "../models/seir.h"
 
 #define DDE_SCOPED_MODEL mackey_glass
-#define DDE_SCOPED_SOURCE "../../dde_b200/models/mackey_glass.h"
+#define DDE_SCOPED_SOURCE "mackey_glass.h"
 #include "dde_model_scoped.inc"
 
 DDE_DEFINE_DOPRI_MODEL(lorenz, lorenz, 3, 3, lorenz_output, 2, DDE_NO_EVENTS, 0)
@@ -41,6 +42,8 @@ DDE_DEFINE_DOPRI_MODEL(rossler, rossler, 3, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 
 DDE_DEFINE_DOPRI_MODEL_LAGS(mackey_glass, mackey_glass, 1, 3, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0,
                             mackey_glass_lags, 1)
 DDE_DEFINE_DOPRI_MODEL(seir, seir, 4, -1, seir_output, 1, DDE_NO_EVENTS, 0)
+DDE_DEFINE_DOPRI_MODEL(delayed_growth_vec, delayed_growth_vec, 0, -1, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0)
+DDE_DEFINE_DOPRI_MODEL(delayed_growth_all, delayed_growth_all, 0, -1, DDE_NO_OUTPUT, 0, DDE_NO_EVENTS, 0)
 
 namespace {
 
@@ -208,6 +211,10 @@ int emu_dopri_batch(const char *model, const dde_dopri_control *ctl, size_t n, s
     }
   } else if (name == "seir") {
     EMU_RUN(dde_dopri_model_seir, 0);
+  } else if (name == "delayed_growth_vec") {
+    EMU_RUN(dde_dopri_model_delayed_growth_vec, 0);
+  } else if (name == "delayed_growth_all") {
+    EMU_RUN(dde_dopri_model_delayed_growth_all, 0);
   } else {
     g_message = "emu: unknown model " + name;
     return 1;

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY: ctypes access to tests/emu/libdde_emu.so, the device
-code of dde_b200/csrc compiled by g++ and run one lane at a time (cuda_emu.h)."""
+code of include/dde_b200 compiled by g++ and run one lane at a time (cuda_emu.h)."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -27,7 +27,7 @@ def load(tag="", extra=""):
     if key not in _libs:
         path = HERE / ("libdde_emu%s.so" % tag)
         src_time = max(p.stat().st_mtime for p in list(HERE.glob("*.cpp")) + list(HERE.glob("*.h")) +
-                       list((HERE.parent.parent / "dde_b200" / "csrc").glob("*")) +
+                       list((HERE.parent.parent / "include" / "dde_b200").glob("*")) +
                        list((HERE.parent.parent / "dde_b200" / "models").glob("*")))
         if not path.exists() or path.stat().st_mtime < src_time:
             build(tag, extra)

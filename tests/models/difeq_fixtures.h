@@ -1,4 +1,5 @@
-/* Difference-equation targets (model ABI src/difeq.h:19-21).
+/* Difference-equation test fixtures (model ABI src/difeq.h:19-21): compiled into
+ * tests/models/libdde_test_models.so, not into the product library.
  *
  *   logistic   -- y' = r y (1 - y), any n, parms = r[n]
  *                 (/root/reference/tests/testthat/logistic.c:4-11)
@@ -13,8 +14,6 @@
  *   fib_all    -- y' = y + y(step - 1) through yprev_all, n <= 16
  *   fib_vec    -- y'_i = y_i + y_{n-1-i}(step - 1) through yprev_vec (size_t
  *                 indices), n <= 16
- *   sir_delay  -- delayed SIR map, n = 3, parms = (beta, gamma), lag 14 steps
- *                 (BASELINE.json configs[3])
  */
 #include <dde/dde.h>
 
@@ -80,18 +79,4 @@ DDE_MODEL_FN void fib_vec(size_t n, size_t step, const double *y,
   for (size_t i = 0; i < n; ++i) {
     y_next[i] = y[i] + prev[i];
   }
-}
-
-DDE_MODEL_FN void sir_delay(size_t n, size_t step, const double *y,
-                            double *y_next, size_t n_out, double *output,
-                            const void *data) {
-  const double *p = (const double *) data;
-  const double beta = p[0], gamma = p[1];
-  const double I_lag = yprev_1((int) step - 14, 1);
-  const double S = y[0], I = y[1], R = y[2];
-  const double inf = beta * S * I_lag;
-  const double rec = gamma * I;
-  y_next[0] = S - inf;
-  y_next[1] = I + inf - rec;
-  y_next[2] = R + rec;
 }

@@ -46,6 +46,18 @@ DDE_MODEL_FN void delayed_growth_vec(size_t n, double t, const double *y,
   }
 }
 
+/* ... the whole lagged state fetched with ylag_all (src/dopri.c:790-800) by a
+   thread-per-trajectory model; n <= 16 */
+DDE_MODEL_FN void delayed_growth_all(size_t n, double t, const double *y,
+                                     double *dydt, const void *data) {
+  const double *r = (const double *) data;
+  double lagged[16];
+  ylag_all(t - 1.0, lagged);
+  for (size_t i = 0; i < n; ++i) {
+    dydt[i] = r[i] * lagged[n - 1 - i];
+  }
+}
+
 /* The reference's event fixtures (/root/reference/tests/testthat/growth.c:20-49):
  * applied to the state -- or to the parameters -- at critical times. */
 DDE_MODEL_FN void identity(size_t n, double t, double *y, void *data) {

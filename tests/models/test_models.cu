@@ -1,0 +1,33 @@
+/* test_models.cu -- TEST INFRASTRUCTURE: the reference's own fixture models as an
+ * out-of-tree dde_b200 model library (tests/models/libdde_test_models.so), built by
+ * tests/models/build.sh against include/ only -- the way a user's model library is built
+ * (the reference loads a model .so at run time, R/common.R:89-98,
+ * inst/include/dde/dde.c:10-78).  Loading the library registers the models by name
+ * (dde_register_model); the GPU parity tests then run them through the C-ABI of the
+ * product library, which contains none of them.
+ */
+#include <dde_b200/dde_model.cuh>
+
+#include "difeq_fixtures.h"
+#include "growth.h"
+#include "seir.h"
+
+/*                         name            deriv           n  n_parms  output        n_out */
+DDE_REGISTER_DOPRI_OUTPUT(seir,           seir,           4, -1,      seir_output,   1)
+DDE_REGISTER_DOPRI_OUTPUT(seir_int,       seir_int,       4, -1,      seir_output,   1)
+/* the reference's growth fixtures come with five event functions */
+DDE_EVENT_TABLE(growth_events, identity, double_variables, halve_variables, double_parameters,
+                halve_parameters)
+DDE_REGISTER_DOPRI_EVENTS(exponential,    exponential,    0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
+DDE_REGISTER_DOPRI_EVENTS(linear,         linear,         0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
+DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
+DDE_REGISTER_DOPRI(       delayed_growth_vec, delayed_growth_vec, 0, -1)
+DDE_REGISTER_DOPRI(       delayed_growth_all, delayed_growth_all, 0, -1)
+
+/*                  name       target     n  n_parms n_out */
+DDE_REGISTER_DIFEQ(logistic,  logistic,  0, -1,     0)
+DDE_REGISTER_DIFEQ(additive,  additive,  0, -1,     -1)
+DDE_REGISTER_DIFEQ(fibonacci, fibonacci, 5, -1,     0)
+DDE_REGISTER_DIFEQ(fib_out,   fib_out,   1, -1,     1)
+DDE_REGISTER_DIFEQ(fib_all,   fib_all,   0, -1,     0)
+DDE_REGISTER_DIFEQ(fib_vec,   fib_vec,   0, -1,     0)

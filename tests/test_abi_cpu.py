@@ -30,6 +30,58 @@ def test_library_exports_every_declared_symbol():
     assert sorted(n for n, _, _ in _lib.SYMBOLS) == names
 
 
+PRODUCT_MODELS = {"lorenz", "rossler", "mackey_glass", "sir_delay", "seir_age"}
+FIXTURE_MODELS = {"seir", "seir_int", "exponential", "linear", "delayed_growth", "delayed_growth_vec",
+                  "delayed_growth_all", "logistic", "additive", "fibonacci", "fib_out", "fib_all",
+                  "fib_vec", "exponential_wide", "delayed_growth_wide"}
+
+
+def test_model_plugin_boundary():
+    """The product library holds the BASELINE.json workloads only; the reference's fixture
+    models come from a model library built out of tree against include/ and loaded at run
+    time (R/common.R:89-98, inst/include/dde/dde.c:10-78).  Checked in a fresh process:
+    before / after loading the plug-in."""
+    import subprocess
+    import sys
+    plug = ROOT / "tests" / "models" / "libdde_test_models.so"
+    if not plug.exists():
+        pytest.skip("tests/models/libdde_test_models.so not built (tests/models/build.sh)")
+    code = ("import dde_b200, json; a = sorted(dde_b200.models()); "
+            "dde_b200.load_model_library(%r); b = sorted(dde_b200.models()); "
+            "print(json.dumps([a, b]))" % str(plug))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True,
+                         cwd=str(ROOT)).stdout
+    import json
+    before, after = json.loads(out.strip().splitlines()[-1])
+    assert set(before) == PRODUCT_MODELS
+    assert set(after) == PRODUCT_MODELS | FIXTURE_MODELS
+    # the plug-in is built from the public headers alone
+    recipe = (ROOT / "tests" / "models" / "build.sh").read_text()
+    assert "-I../../include" in recipe and "csrc" not in recipe
+
+
+def test_reference_example_compiles_with_only_the_decoration_injected(tmp_path):
+    """tools/decorate_model.py changes nothing but the DDE_MODEL_FN prefix of the function
+    definitions, and the recipe turns the reference's example into a loadable model library
+    (cross-compiled here; run on the GPU by test_reference_example_model_as_plugin)."""
+    import subprocess
+    import sys
+    src = Path("/root/reference/inst/examples/seir.c")
+    if not src.exists():
+        pytest.skip("no reference tree")
+    sys.path.insert(0, str(ROOT / "tools"))
+    import decorate_model
+    text = src.read_text()
+    dec = decorate_model.decorate(text)
+    assert dec.replace("DDE_MODEL_FN ", "") == text
+    assert dec.count("DDE_MODEL_FN ") == 2  # seir, seir_output
+    subprocess.run(["bash", str(ROOT / "tests" / "models" / "build_ref_example.sh")], check=True)
+    plug = ROOT / "tests" / "models" / "_ref" / "libdde_ref_example.so"
+    code = ("import dde_b200; dde_b200.load_model_library(%r); "
+            "assert 'seir_reference_example' in dde_b200.models()" % str(plug))
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=str(ROOT))
+
+
 def test_model_header_is_source_compatible():
     # the eight history functions of inst/include/dde/dde.h:3-13, same signatures
     text = (ROOT / "include" / "dde" / "dde.h").read_text()

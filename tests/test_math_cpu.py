@@ -1,4 +1,4 @@
-"""dde_pow / dde_exp (dde_b200/csrc/dde_math.h), host build, against this
+"""dde_pow / dde_exp (include/dde_b200/dde_math.h), host build, against this
 platform's libm -- the pow the reference's step controller links to
 (src/dopri.c:500,517,521,569).  Bit-exact on every input; the same source runs
 on the device."""

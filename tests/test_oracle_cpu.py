@@ -164,6 +164,12 @@ def test_oracle_matches_reference_on_fresh_inputs():
                              n_history=200)
     np.testing.assert_array_equal(a.statistics, b.statistics)
     assert_bits_equal(a.y, b.y, "y")
+    a = pyoracle.dopri_batch("oracle", "delayed_growth_all", y0, np.linspace(0, 3, 13), r,
+                             n_history=200)
+    b = pyoracle.dopri_batch("ref", "delayed_growth_all", y0, np.linspace(0, 3, 13), r,
+                             n_history=200)
+    np.testing.assert_array_equal(a.statistics, b.statistics)
+    assert_bits_equal(a.y, b.y, "y")
     for model in ("fib_all", "fib_vec"):
         a = pyoracle.difeq_batch("oracle", model, y0, np.arange(0, 30), None, n_history=3)
         b = pyoracle.difeq_batch("ref", model, y0, np.arange(0, 30), None, n_history=3)

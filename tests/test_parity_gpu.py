@@ -102,6 +102,34 @@ def test_growth_models_runtime_n(backend, method):
         # the same through ylag_vec (size_t indices), mirrored components
         check_dopri(backend, "delayed_growth_vec", y0, np.linspace(0, 3, 13), r, method=method,
                     n_history=200)
+        # ... and through ylag_all by a thread-per-trajectory model (src/dopri.c:790-800;
+        # lag_ctx.cuh ylag_all: pre-history, staged window and ring paths)
+        check_dopri(backend, "delayed_growth_all", y0, np.linspace(0, 3, 13), r, method=method,
+                    n_history=200)
+        check_dopri(backend, "delayed_growth_all", y0, np.linspace(0, 6, 7), r, method=method,
+                    n_history=4)  # a ring the lag outruns: ERR_YLAG_FAIL where the reference has it
+
+
+def test_reference_example_model_as_plugin(backend):
+    """/root/reference/inst/examples/seir.c itself, compiled as a model library with only the
+    DDE_MODEL_FN decoration injected (tests/models/build_ref_example.sh), loaded at run time:
+    the same bits as the reference solver running the reference's build of that file."""
+    from conftest import ROOT
+    plug = ROOT / "tests" / "models" / "_ref" / "libdde_ref_example.so"
+    if not plug.exists():
+        pytest.skip("tests/models/_ref/libdde_ref_example.so not built (needs the reference tree)")
+    dde_b200.load_model_library(plug)
+    assert "seir_reference_example" in dde_b200.models()
+    y0 = np.array([[1e7 - 1, 0.0, 1.0, 0.0], [9e6, 5e5, 2e5, 3e5]])
+    times = np.linspace(0, 365, 74)
+    for method in ("dopri5", "dopri853"):
+        kw = dict(n_out=1, method=method, n_history=1000)
+        got = dde_b200.dopri_batch(y0, times, "seir_reference_example", None, **kw)
+        want = pyoracle.dopri_batch(backend, "seir", y0, times, None, **kw)
+        np.testing.assert_array_equal(got.statistics, want.statistics)
+        np.testing.assert_array_equal(got.code, want.code)
+        assert_bits_equal(got.y, want.y, "y")
+        assert_bits_equal(got.output, want.output, "output")
 
 
 def test_negative_time(backend):
