@@ -79,6 +79,7 @@ SYMBOLS = [
     ("dde_dopri_batch_device_ptr", C.c_void_p, [C.c_void_p, C.c_int]),
     ("dde_dopri_interpolate_batch", C.c_int, [c_double_p, _SZ, _SZ, _SZ, _SZ, c_double_p, _SZ,
                                               c_double_p]),
+    ("dde_dopri_batch_interpolate", C.c_int, [C.c_void_p, c_double_p, _SZ, c_double_p]),
     ("dde_difeq_batch", C.c_int, _DIFEQ_BATCH_ARGS),
     ("dde_difeq_batch_alloc", C.c_void_p, [C.c_char_p, _SZ, _SZ, _SZ, _SZ, _SZ]),
     ("dde_difeq_batch_free", None, [C.c_void_p]),

@@ -158,6 +158,15 @@ class DopriBatch:
             raise DdeError(_lib.last_error())
         return buf[:used].copy()
 
+    def interpolate(self, t):
+        """dopri_interpolate (R/dopri.R:577-642) for every trajectory of the batch, from the
+        history rings in device memory: [n_traj, n, len(t)]."""
+        t = _f64(t, "t").ravel()
+        y = np.empty((self.n_traj, self.n, t.shape[0]))
+        self._check(self._lib.dde_dopri_batch_interpolate(
+            self._h, t.ctypes.data_as(c_double_p), t.shape[0], y.ctypes.data_as(c_double_p)))
+        return y
+
     def device_ptr(self, which):
         return self._lib.dde_dopri_batch_device_ptr(self._h, int(which))
 
@@ -295,7 +304,8 @@ class DifeqBatch:
 
     def history(self, j):
         """The `history` attribute of replicate j: [entries, 1 + n + n_out] = step, y, out
-        (out columns NA), oldest first.  The run must have been restartable."""
+        (the out columns as the reference leaves them, include/dde_b200.h), oldest first.
+        The run must have been restartable."""
         hl = 1 + self.n + self.n_out
         cap = max(self.n_history, 1)
         buf = np.empty((cap, hl))

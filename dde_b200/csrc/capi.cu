@@ -242,6 +242,8 @@ struct dde_difeq_batch_s {
   unsigned *d_ring_count = nullptr;
   bool restartable = false, kept_history = false;
   unsigned long long steps_first = 0, steps_last = 0; /* of the steps set last */
+  std::vector<unsigned long long> h_steps;            /* ... and the steps themselves */
+  bool continued = false; /* the history holds more than one run (difeq_continue) */
   unsigned long long step_origin = 0; /* first step of the handle's first run */
   unsigned long long last_step = 0;   /* obj->step after the last run */
 };
@@ -1399,6 +1401,59 @@ __global__ void interpolate_kernel(const double *history, int hl, int n_entries,
   }
 }
 
+/* The same for trajectories whose history is still where the solver left it: the rings of
+ * a batch handle, read in place (logical entry e of trajectory j in slot e % cap; the
+ * oldest surviving one is count - min(count, cap)).  The range check of R/dopri.R:596-600
+ * is made here too: a time outside [first entry's start, last entry's end] gives NaN and
+ * records the lowest offending trajectory in *bad. */
+__global__ void interpolate_rings_kernel(const double *ring, const unsigned *ring_count, int cap,
+                                         int hl, int n, long long n_traj, const double *t,
+                                         int n_t, double *y, unsigned long long *bad) {
+  const long long gid = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if (gid >= n_traj * n_t) {
+    return;
+  }
+  const long long j = gid / n_t;
+  const int q = (int) (gid % n_t);
+  const int order = (hl - 2) / n;
+  const int it = hl - 2;
+  const double *r = ring + (size_t) j * (size_t) cap * (size_t) hl;
+  const unsigned count = ring_count[j];
+  const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
+  const double tq = t[q];
+  double *dst = y + (size_t) j * (size_t) n * (size_t) n_t;
+#define DDE_RING_ENTRY(e) (r + (size_t) ((e) % (unsigned) cap) * (size_t) hl)
+  bool inside = used > 0;
+  if (inside) {
+    const double *le = DDE_RING_ENTRY(count - 1);
+    inside = !(tq < DDE_RING_ENTRY(count - used)[it] || tq > le[it] + le[it + 1]);
+  }
+  if (!inside) {
+    atomicMin(bad, (unsigned long long) j);
+    for (int i = 0; i < n; ++i) {
+      dst[(size_t) i * n_t + q] = dde::na_real();
+    }
+    return;
+  }
+  unsigned lo = count - used, hi = count; /* last entry with time <= tq */
+  while (hi - lo > 1) {
+    const unsigned mid = lo + (hi - lo) / 2;
+    if (DDE_RING_ENTRY(mid)[it] <= tq) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  const double *e = DDE_RING_ENTRY(lo);
+#undef DDE_RING_ENTRY
+  const double theta = (tq - e[it]) / e[it + 1];
+  const double theta1 = 1.0 - theta;
+  for (int i = 0; i < n; ++i) {
+    dst[(size_t) i * n_t + q] = order == 5 ? dde::interp5(n, theta, theta1, e + i)
+                                           : dde::interp853(n, theta, theta1, e + i);
+  }
+}
+
 } /* namespace */
 
 extern "C" {
@@ -1456,6 +1511,65 @@ int dde_dopri_interpolate_batch(const double *history, size_t history_len, size_
   if (err != cudaSuccess) {
     (void) cudaGetLastError();
     return fail("CUDA error in dde_dopri_interpolate_batch: %s", cudaGetErrorString(err));
+  }
+  return 0;
+}
+
+int dde_dopri_batch_interpolate(dde_dopri_batch_t *b, const double *t, size_t n_t, double *y) {
+  if (b == nullptr || t == nullptr || y == nullptr) {
+    return fail("NULL argument");
+  }
+  if (!b->ran) {
+    return fail("nothing has been run on this handle: there is no history");
+  }
+  if (b->ctl.n_history == 0) {
+    return fail("the handle keeps no history (n_history = 0)");
+  }
+  if (n_t == 0) {
+    return fail("empty history or no times");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  const size_t hl = (size_t) b->order * b->n + 2;
+  const size_t yb = sizeof(double) * n_t * b->n * b->n_traj;
+  double *d_t = nullptr, *d_y = nullptr;
+  unsigned long long *d_bad = nullptr;
+  unsigned long long bad = ~0ULL;
+  cudaError_t err = cudaMalloc(&d_t, sizeof(double) * n_t);
+  err = err ? err : cudaMalloc(&d_y, yb);
+  err = err ? err : cudaMalloc(&d_bad, sizeof bad);
+  err = err ? err : cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice,
+                                    b->stream);
+  err = err ? err : cudaMemcpyAsync(d_bad, &bad, sizeof bad, cudaMemcpyHostToDevice, b->stream);
+  if (err == cudaSuccess) {
+    /* on the handle's stream: after the run that writes the rings */
+    const long long total = (long long) b->n_traj * (long long) n_t;
+    const int threads = 128;
+    interpolate_rings_kernel<<<(unsigned) ((total + threads - 1) / threads), threads, 0,
+                               b->stream>>>(b->d_ring, b->d_ring_count, (int) b->ctl.n_history,
+                                            (int) hl, (int) b->n, (long long) b->n_traj, d_t,
+                                            (int) n_t, d_y, d_bad);
+    err = cudaGetLastError();
+  }
+  err = err ? err : cudaMemcpyAsync(y, d_y, yb, cudaMemcpyDeviceToHost, b->stream);
+  err = err ? err : cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, b->stream);
+  err = err ? err : cudaStreamSynchronize(b->stream);
+  cudaFree(d_t);
+  cudaFree(d_y);
+  cudaFree(d_bad);
+  if (err != cudaSuccess) {
+    (void) cudaGetLastError();
+    return fail("CUDA error in dde_dopri_batch_interpolate: %s", cudaGetErrorString(err));
+  }
+  if (bad != ~0ULL) { /* R/dopri.R:596-600, for the first trajectory it applies to */
+    double first = 0.0, end = 0.0;
+    std::vector<double> h((size_t) b->ctl.n_history * hl);
+    const long used = dde_dopri_batch_history(b, (size_t) bad, h.data(), (size_t) b->ctl.n_history);
+    if (used > 0) {
+      first = h[hl - 2];
+      end = h[(size_t) (used - 1) * hl + hl - 2] + h[(size_t) (used - 1) * hl + hl - 1];
+    }
+    return fail("Time falls outside of range of known history [%g, %g] (trajectory %llu)", first,
+                end, bad);
   }
   return 0;
 }
@@ -1607,6 +1721,7 @@ int dde_difeq_batch_set_steps(dde_difeq_batch_t *b, const uint64_t *steps, size_
   b->n_steps = n_steps;
   b->steps_first = steps[0];
   b->steps_last = steps[n_steps - 1];
+  b->h_steps.assign(steps, steps + n_steps);
   b->return_initial = return_initial != 0;
   b->nt = return_initial ? n_steps : n_steps - 1;
   const size_t need_y = b->n * b->nt * b->n_rep;
@@ -1674,6 +1789,7 @@ int difeq_run_impl(dde_difeq_batch_t *b, int restart) {
   if (!restart) {
     b->step_origin = b->steps_first;
   }
+  b->continued = restart != 0;
   b->kept_history = b->restartable;
   a.step_origin = b->step_origin;
   int launches = 0;
@@ -1874,6 +1990,53 @@ long dde_difeq_batch_history(dde_difeq_batch_t *b, size_t j, double *history,
       fail("CUDA error in history export");
       return -1;
     }
+    /* The output columns.  The reference writes a step's outputs through a pointer
+       (out_next, src/difeq.c:154-156,203-213,249-255) that moves to the entry being written
+       only when an output ROW is stored, so what an entry's columns end up holding is an
+       artefact of which steps were asked for: the row stored while the pointer rested on
+       the entry's ring slot (later steps overwrite it until then), zeros where it never
+       rested (the ring is calloc'ed), NA in the first entry (fill_na, :144) -- reproduced
+       here from the stored rows for a first run; after difeq_continue (the pointer is set
+       up again per run) the columns are NA. */
+    const unsigned long long na_bits = 0x7FF00000000007A2ULL;
+    std::vector<double> slot_out;
+    if (b->n_out > 0 && !b->continued && b->h_steps.size() == b->n_steps && b->n_steps >= 2) {
+      const size_t n_out = b->n_out, nt = b->nt;
+      std::vector<double> rows(nt * n_out);
+      if (cudaMemcpy(rows.data(), b->d_out + j * nt * n_out, sizeof(double) * nt * n_out,
+                     cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail("CUDA error in history export");
+        return -1;
+      }
+      /* the reference's ring has one slot more than it holds entries (mrc-ide/ring keeps
+         the slot under the head free: SURVEY.md appendix C), and the pointer is into that
+         memory: entry e lives in slot e % (cap + 1) there */
+      const size_t phys = cap + 1;
+      slot_out.assign(phys * n_out, 0.0);
+      for (size_t i = 0; i < n_out; ++i) {
+        memcpy(&slot_out[i], &na_bits, sizeof(double)); /* entry 0, slot 0 */
+      }
+      size_t ptr_slot = 1 % phys; /* out_next after the first advance: entry 1 */
+      bool store_next = b->return_initial != 0;
+      size_t row = 0, idx = 1; /* steps[0] is the start; steps[idx] the next output step */
+      const unsigned long long s0 = b->h_steps[0], s_last = b->h_steps[b->n_steps - 1];
+      for (unsigned long long st = s0; st < s_last; ++st) {
+        /* target(y(st)) has written its outputs to the pointer's slot */
+        if (store_next) {
+          memcpy(&slot_out[ptr_slot * n_out], &rows[row * n_out], sizeof(double) * n_out);
+          ++row;
+          ptr_slot = (size_t) ((st - s0 + 1) % phys); /* the entry y(st + 1) goes to */
+          store_next = false;
+        }
+        if (idx < b->n_steps && st + 1 == b->h_steps[idx]) {
+          store_next = true;
+          ++idx;
+        }
+      }
+      if (store_next && row < nt) { /* src/difeq.c:249-255 */
+        memcpy(&slot_out[ptr_slot * n_out], &rows[row * n_out], sizeof(double) * n_out);
+      }
+    }
     const size_t first = count - used;
     for (size_t e = 0; e < used && e < max_entries; ++e) {
       const size_t slot = (first + e) % cap;
@@ -1881,12 +2044,12 @@ long dde_difeq_batch_history(dde_difeq_batch_t *b, size_t j, double *history,
       /* entry idx holds the state after idx steps from the handle's first step */
       dst[0] = (double) (b->step_origin + first + e);
       memcpy(dst + 1, ring.data() + slot * hl + 1, sizeof(double) * b->n);
-      /* the output columns are not reproduced: the reference writes them
-         through a pointer that lags the ring head (src/difeq.c:203-206,
-         out_next), NA_real_ here */
-      const unsigned long long na_bits = 0x7FF00000000007A2ULL;
       for (size_t i = 0; i < b->n_out; ++i) {
-        memcpy(dst + 1 + b->n + i, &na_bits, sizeof(double));
+        if (slot_out.empty()) {
+          memcpy(dst + 1 + b->n + i, &na_bits, sizeof(double));
+        } else {
+          dst[1 + b->n + i] = slot_out[((first + e) % (cap + 1)) * b->n_out + i];
+        }
       }
     }
   }

@@ -241,6 +241,14 @@ void *dde_dopri_batch_device_ptr(dde_dopri_batch_t *b, int which);
 int dde_dopri_interpolate_batch(const double *history, size_t history_len,
                                 size_t n_entries, size_t n, size_t n_traj,
                                 const double *t, size_t n_t, double *y);
+/* The same for the trajectories of a batch handle, from the history rings where the
+ * solver left them in HBM: no history travels to the host and back, the range check
+ * runs on the device.  t [n_t] and y [n_t x n x n_traj] are host arrays.  A time
+ * outside a trajectory's surviving history (entries the ring has overwritten are
+ * gone, src/dopri.h:94-126) gives NaN for that trajectory and time, and the call
+ * returns non-zero naming the first such trajectory's range (R/dopri.R:596-600). */
+int dde_dopri_batch_interpolate(dde_dopri_batch_t *b, const double *t, size_t n_t,
+                                double *y);
 
 /* ---- difeq -------------------------------------------------------------- */
 
@@ -294,8 +302,11 @@ int dde_difeq_batch_download(dde_difeq_batch_t *b, double *y_out, double *out,
  * {step, y[n], out[n_out]} oldest first, [max_entries x (1 + n + n_out)];
  * returns the number of entries the ring holds, < 0 on error.  Needs a
  * restartable run (dde_difeq_batch_restartable), which keeps the history in
- * HBM.  The out columns are NA_real_: the reference fills them through a
- * pointer that lags the ring head, which is not reproduced. */
+ * HBM.  The out columns hold what the reference's do (src/difeq.c:203-213,
+ * 249-255: the stored output row that was written last while the lagging
+ * out_next pointer rested on the entry's slot, zeros elsewhere, NA in the
+ * first entry) for a first run; after dde_difeq_batch_continue they are
+ * NA_real_. */
 long dde_difeq_batch_history(dde_difeq_batch_t *b, size_t j, double *history,
                              size_t max_entries);
 double dde_difeq_batch_last_ms(dde_difeq_batch_t *b);

@@ -220,6 +220,58 @@ def test_history_and_interpolate(backend, method):
         dde_b200.dopri_interpolate(res, [2.5])
 
 
+@pytest.mark.parametrize("method", ["dopri5", "dopri853"])
+def test_interpolate_matches_the_restated_r_function(method):
+    """dopri_interpolate (R/dopri.R:577-642) restated in numpy (oracle/pyinterp.py), against
+    both interpolation entry points, bit for bit: the host-history one
+    (dde_dopri_interpolate_batch) and the one that reads the rings of a live batch handle in
+    device memory (dde_dopri_batch_interpolate), rings that have wrapped included."""
+    from oracle import pyinterp
+    rng = np.random.default_rng(17)
+    # a three-equation system, histories that fit the ring
+    n_traj = 9
+    model, y0, parms, times, kw = workloads.lorenz_sweep(n_traj, n_times=11, t_end=2.0)
+    kw = dict(kw, method=method, n_history=2000)
+    b = dde_b200.DopriBatch(model, 3, n_traj, n_parms=3, **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    tq = np.concatenate([[0.0, 2.0], rng.uniform(0.0, 2.0, 300)])
+    got = b.interpolate(tq)                       # [n_traj, n, n_t]
+    for j in range(n_traj):
+        h = b.history(j)
+        want = pyinterp.dopri_interpolate(h, 3, tq)   # [n_t, n]
+        assert_bits_equal(got[j].T, want, "from the rings, trajectory %d" % j)
+        hist = h.view(dde_b200.DopriHistory)
+        hist.n = 3
+        assert_bits_equal(dde_b200.dopri_interpolate(hist, tq), want, "from a host history")
+    with pytest.raises(dde_b200.DdeError, match="outside of range of known history"):
+        b.interpolate([2.5])
+    b.close()
+    # the Mackey-Glass batch with rings that wrap: only the surviving entries answer
+    model, y0, parms, times, kw = workloads.mackey_glass(96)
+    kw = dict(kw, method=method, n_history=16)
+    probe = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+    keep = np.flatnonzero(probe.code == 1)       # trajectories that reach t = 500
+    assert 10 < keep.shape[0] < 96 or keep.shape[0] == 96
+    y0, parms, n_traj = y0[keep], parms[keep], keep.shape[0]
+    b = dde_b200.DopriBatch(model, 1, n_traj, n_parms=3, **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    hs = [b.history(j) for j in range(n_traj)]
+    assert all(h.shape[0] == 16 for h in hs)
+    lo = max(h[0, -2] for h in hs)                # inside every surviving history
+    tq = np.concatenate([[lo, 500.0], rng.uniform(lo, 500.0, 200)])
+    got = b.interpolate(tq)
+    for j in range(n_traj):
+        assert_bits_equal(got[j].T, pyinterp.dopri_interpolate(hs[j], 1, tq), "wrapped ring")
+    # before the oldest surviving entry of some trajectory: refused, as R does
+    with pytest.raises(dde_b200.DdeError, match="outside of range of known history"):
+        b.interpolate([min(h[0, -2] for h in hs) - 1.0])
+    b.close()
+
+
 def test_ring_overwrite_history(backend):
     # overwrite policy: the ring keeps the newest n_history entries, oldest first
     y0 = [10.0, 1.0, 1.0]
@@ -856,9 +908,43 @@ def test_difeq_history(backend, grow):
         assert_bits_equal(y[j], ref.y, "y")
         assert_bits_equal(b.history(j), ref.history, "history %d" % j)
     b.close()
-    # with outputs: steps and states as the reference's, the out columns are NA
-    got = dde_b200.difeq([1.0], 12, "fib_out", None, n_out=1, n_history=4)
-    ref = pyoracle.difeq_history(backend, "fib_out", [[1.0]], np.arange(0, 13), None, n_out=1,
-                                 n_history=4, max_entries=16)
-    assert_bits_equal(got.history[:, :2], ref.history[:, :2], "history step, y")
-    assert np.isnan(got.history[:, 2]).all()
+    # with outputs: the out columns are what the reference's lagging out_next pointer leaves
+    # in them (src/difeq.c:203-213,249-255) -- every step asked for, a few, with and without
+    # the initial row, rings that hold the run and rings that wrap.  (The plain-C
+    # restatement keeps NA there, oracle/dde_oracle.c: against it, steps and states only.)
+    def same_history(got, ref, n, what):
+        if backend == "ref":
+            assert_bits_equal(got, ref, what)
+        else:
+            assert_bits_equal(got[:, :1 + n], ref[:, :1 + n], what)
+
+    for steps in (np.arange(0, 13), np.array([0, 3, 4, 9, 12]), np.array([2, 3, 11, 30]),
+                  np.array([0, 40])):
+        for return_initial in (True, False):
+            for n_history in (64, 4, 2):
+                b = dde_b200.DifeqBatch("fib_out", 1, 3, n_out=1, n_history=n_history,
+                                        restartable=True)
+                b.upload(np.array([[1.0], [2.0], [0.5]]), None)
+                b.set_steps(steps, return_initial=return_initial)
+                b.run()
+                for j, y0 in enumerate((1.0, 2.0, 0.5)):
+                    ref = pyoracle.difeq_history(backend, "fib_out", [[y0]], steps, None, n_out=1,
+                                                 n_history=n_history, max_entries=64,
+                                                 return_initial=return_initial)
+                    same_history(b.history(j), ref.history, 1,
+                                 "history %s %s %d" % (steps.tolist(), return_initial, n_history))
+                b.close()
+    # the additive model: two outputs per step, several replicates
+    rng = np.random.default_rng(3)
+    y0 = rng.integers(1, 9, size=(4, 2)).astype(float)
+    p = rng.integers(1, 5, size=(4, 2)).astype(float)
+    steps = np.array([0, 1, 5, 6, 20])
+    b = dde_b200.DifeqBatch("additive", 2, 4, n_parms=2, n_out=3, n_history=8, restartable=True)
+    b.upload(y0, p)
+    b.set_steps(steps, return_initial=True)
+    b.run()
+    for j in range(4):
+        ref = pyoracle.difeq_history(backend, "additive", y0[j:j + 1], steps, p[j:j + 1], n_out=3,
+                                     n_history=8, max_entries=64)
+        same_history(b.history(j), ref.history, 2, "additive history %d" % j)
+    b.close()
