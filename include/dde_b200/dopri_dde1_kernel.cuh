@@ -227,6 +227,8 @@ __device__ __forceinline__ double dde1_lookup(const Dde1Win &w, double t0, doubl
   }
   /* the entry's slot: in range whatever cnt is */
   const unsigned ea = dde1_wrap(w, w.below + cnt * DDE1_SLOT_BYTES);
+  DDE_CHECK(ea >= w.first && ea < w.first + DDE1_WIN * DDE1_SLOT_BYTES &&
+            (ea - w.first) % DDE1_SLOT_BYTES == 0 && cnt <= DDE1_WIN);
   double c0, c1, c2, c3, c4, c5, c6, c7, ts, hh;
   dde1_lds2(ea, c0, c1);
   dde1_lds2(ea + DDE1_PAIR_BYTES, c2, c3);
@@ -262,13 +264,18 @@ static __device__ __noinline__ Dde1Found dde1_lookup_ring(const double *ring, un
   Dde1Found f;
   f.failed = false;
   f.value = y0v;
+  DDE_LAG_COUNT(6);
   if (tq <= t0) {
     return f;
   }
   const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
   unsigned lo = count - used, hi = count;
-#define DDE1_TIME(j) (ring[(size_t) ((j) % (unsigned) cap) * 10u + 8u])
+#define DDE1_TIME(j)                                                                       \
+  (DDE_LAG_COUNT(5), DDE_CHECK((j) < count && count - (j) <= (unsigned) cap),              \
+   ring[(size_t) ((j) % (unsigned) cap) * 10u + 8u])
   if (tq >= wtop) { /* entry `top` exists and starts at wtop */
+    DDE_LAG_COUNT(0);
+    DDE_CHECK(top < count && count - top <= (unsigned) cap);
     lo = top;
     for (;;) {
       const double t1 = lo + 1 < count ? DDE1_TIME(lo + 1) : pos_inf();
@@ -281,7 +288,9 @@ static __device__ __noinline__ Dde1Found dde1_lookup_ring(const double *ring, un
       }
     }
   } else {
+    DDE_LAG_COUNT(1);
     if (used == 0 || !(DDE1_TIME(lo) <= tq)) {
+      DDE_LAG_COUNT(4);
       f.failed = true;
       f.value = na_real();
       return f;
@@ -296,6 +305,7 @@ static __device__ __noinline__ Dde1Found dde1_lookup_ring(const double *ring, un
     }
   }
 #undef DDE1_TIME
+  DDE_CHECK(lo < count && count - lo <= (unsigned) cap);
   const double *c = ring + (size_t) (lo % (unsigned) cap) * 10u;
   const double theta = (tq - c[8]) / c[9];
   const double theta1 = 1 - theta;
@@ -326,6 +336,9 @@ __device__ __forceinline__ bool dde1_window_ensure(Dde1Win &w, const double *rin
       double te = 0.0, he = 0.0;
 #pragma unroll 1
       do {
+        DDE_LAG_COUNT(3);
+        DDE_CHECK(slot < (unsigned) cap && idx < count && count - idx <= (unsigned) cap &&
+                  dst >= w.first && dst < w.first + DDE1_WIN * DDE1_SLOT_BYTES);
         const double2 p0 = *(const double2 *) (e), p1 = *(const double2 *) (e + 2),
                       p2 = *(const double2 *) (e + 4), p3 = *(const double2 *) (e + 6),
                       p4 = *(const double2 *) (e + 8);
@@ -376,6 +389,7 @@ __device__ __forceinline__ void dde1_window_commit(Dde1Win &w, unsigned count, i
   }
   if (append) {
     const unsigned dst = dde1_slot(w, w.wn);
+    DDE_CHECK(w.wn < DDE1_WIN && dst >= w.first && dst < w.first + DDE1_WIN * DDE1_SLOT_BYTES);
     dde1_sts2(dst, hd[0], hd[1]);
     dde1_sts2(dst + DDE1_PAIR_BYTES, hd[2], hd[3]);
     dde1_sts2(dst + 2u * DDE1_PAIR_BYTES, hd[4], hd[5]);
@@ -791,6 +805,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
 
         /* ring_buffer_head_advance, src/dopri.c:460 */
         {
+          DDE_CHECK(head >= 0 && head < cap && (unsigned) head == count % (unsigned) cap);
           double *dst = ring + (size_t) head * (size_t) hl;
           *(double2 *) (dst) = make_double2(hd[0], hd[1]);
           *(double2 *) (dst + 2) = make_double2(hd[2], hd[3]);
@@ -799,6 +814,18 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           *(double2 *) (dst + 8) = make_double2(t_old, h);
           head = head + 1 == cap ? 0 : head + 1;
           ++count;
+          /* make room first: the entries no query of the NEXT attempt reaches (it starts at
+             the new t, so its lowest query is lags(t)) go now, not at that attempt's start,
+             so that the new entry still finds a slot and the window stays at the head of the
+             ring -- appended to from registers, never re-read from HBM */
+          {
+            double lo_next;
+            M::lags(t, p, &lo_next);
+#pragma unroll 1
+            while (w.wn > 1 && dde1_lds(dde1_slot(w, 1) + 4u * DDE1_PAIR_BYTES) <= lo_next) {
+              dde1_window_evict(w);
+            }
+          }
           dde1_window_commit(w, count, cap, hd, t_old, h);
         }
 
