@@ -585,18 +585,23 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           code = -6; /* ERR_YLAG_FAIL */
         }
       }
-      {
-        /* the next evaluation's (the last one's goes nowhere) */
-        double tqn;
-        M::lags(tn, p, &tqn);
-        zn = dde1_lookup(w, t0, y0v, tqn, &okn);
-      }
-
-      /* -- dopri_eval, src/dopri.c:831-835: the one copy of the model -- */
+      /* -- dopri_eval, src/dopri.c:831-835, next to the look-up of the evaluation after it.
+            Two copies of the model: evaluation 10 has nothing to look up ahead (12 asks what
+            it asked itself) and the last one nothing at all, and a branch around the look-up
+            would take it out of pow's basic block in the other thirteen. -- */
       double kt;
       sc.memo_t = tq;
       sc.memo_v = z;
-      M::deriv_scoped(sc, (size_t) 1, tt, &yin, &kt, p);
+      if (st == NST_STEP - 1 || st == NST - 2) {
+        zn = z;
+        okn = true;
+        M::deriv_scoped(sc, (size_t) 1, tt, &yin, &kt, p);
+      } else {
+        double tqn;
+        M::lags(tn, p, &tqn);
+        zn = dde1_lookup(w, t0, y0v, tqn, &okn);
+        M::deriv_scoped(sc, (size_t) 1, tt, &yin, &kt, p);
+      }
 
       /* -- file the result and form the input of the next evaluation (one warp-uniform
             switch per evaluation), src/dopri_853.c:178-246,304,330-347 -- */
