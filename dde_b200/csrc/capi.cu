@@ -342,6 +342,11 @@ int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf, si
     case DDE_ERR_RESTART: /* src/r_dopri.c:216 */
       snprintf(buf, len, "Incorrect initial time on integration restart");
       break;
+    case DDE_ERR_LAG_UNDECLARED: /* an extension: include/dde_b200/dde_model_def.h, M::lags */
+      snprintf(buf, len,
+               "Integration failure: the model made a history look-up it did not declare "
+               "(at t = %2.5f)", t);
+      break;
     case DDE_OK_COMPLETE:
     case DDE_OK_INTERRUPTED:
       snprintf(buf, len, "OK");

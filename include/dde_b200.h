@@ -56,6 +56,9 @@ extern "C" {
 /* dopri_continue from a time the trajectory did not stop at (or from a failed
  * solve): "Incorrect initial time on integration restart", src/r_dopri.c:215-217 */
 #define DDE_ERR_RESTART (-10)
+/* an extension: a model registered with its lags declared (DDE_REGISTER_DOPRI_LAGS,
+ * include/dde_b200/dde_model_def.h) made a history look-up it did not declare */
+#define DDE_ERR_LAG_UNDECLARED (-11)
 
 /* index into stats[4 x n_traj]; order of the `statistics` attribute,
  * src/r_dopri.c:415-422 */

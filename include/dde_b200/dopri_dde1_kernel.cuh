@@ -109,7 +109,11 @@ struct Dde1Scope {
   unsigned tab;          /* shared-window address of the pow / exp tables */
   bool undeclared;       /* a look-up that was not declared (M::lags): DDE_ERR_LAG_UNDECLARED */
   __device__ __forceinline__ double ylag_1(double t, size_t) {
-    const bool declared = t == memo_t;
+    /* "exactly that time": the same bits.  (Compared as integers, so that the compiler,
+       which sees the model compute t - tau twice from the same operands, can tell that a
+       value equals itself -- as doubles it would have to allow for NaN -- and folds the
+       whole test away for a model that keeps its declaration.) */
+    const bool declared = __double_as_longlong(t) == __double_as_longlong(memo_t);
     undeclared |= !declared;
     return declared ? memo_v : na_real();
   }

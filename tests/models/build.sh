@@ -7,7 +7,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false
-       -Xcompiler -fPIC,-mfma,-ffp-contract=off,-Wall,-Wno-unused-function -I../../include)
+       -Xcompiler -fPIC,-mfma,-ffp-contract=off,-Wall,-Wno-unused-function -I../../include -I.)
 mkdir -p ../../build
 "$NVCC" "${FLAGS[@]}" -c test_models.cu -o ../../build/test_models.o 2> ../../build/nvcc_test_models.log &
 "$NVCC" "${FLAGS[@]}" -c test_models_coop.cu -o ../../build/test_models_coop.o 2> ../../build/nvcc_test_models_coop.log &

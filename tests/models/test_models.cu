@@ -11,6 +11,13 @@
 #include "difeq_fixtures.h"
 #include "growth.h"
 #include "seir.h"
+#include "mg_wrong_lag.h"
+
+/* a model with a (wrong) lag declaration: compiled once more inside a struct, like any
+   model registered with DDE_REGISTER_DOPRI_LAGS (dde_model_scoped.inc) */
+#define DDE_SCOPED_MODEL mg_wrong_lag
+#define DDE_SCOPED_SOURCE "mg_wrong_lag.h"
+#include <dde_b200/dde_model_scoped.inc>
 
 /*                         name            deriv           n  n_parms  output        n_out */
 DDE_REGISTER_DOPRI_OUTPUT(seir,           seir,           4, -1,      seir_output,   1)
@@ -23,6 +30,7 @@ DDE_REGISTER_DOPRI_EVENTS(linear,         linear,         0, -1,      DDE_NO_OUT
 DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
 DDE_REGISTER_DOPRI(       delayed_growth_vec, delayed_growth_vec, 0, -1)
 DDE_REGISTER_DOPRI(       delayed_growth_all, delayed_growth_all, 0, -1)
+DDE_REGISTER_DOPRI_LAGS(  mg_wrong_lag,   mg_wrong_lag,   1, 3,       mg_wrong_lag_lags, 1)
 
 /*                  name       target     n  n_parms n_out */
 DDE_REGISTER_DIFEQ(logistic,  logistic,  0, -1,     0)

@@ -110,6 +110,23 @@ def test_growth_models_runtime_n(backend, method):
                     n_history=4)  # a ring the lag outruns: ERR_YLAG_FAIL where the reference has it
 
 
+def test_a_wrong_lag_declaration_is_reported_not_integrated():
+    """the kernel for one delay equation with a declared lag (dopri_dde1_kernel.cuh) answers the
+    declared look-up itself; a model that then asks for something else ends with
+    DDE_ERR_LAG_UNDECLARED, on the general kernel (which does not use the declaration) it runs"""
+    model, y0, parms, times, kw = workloads.mackey_glass(300)
+    got = dde_b200.dopri_batch(y0, times, "mg_wrong_lag", parms, **kw)
+    # (where the first step is longer than the declared lag, the declared look-up itself
+    # already fails: ERR_YLAG_FAIL comes first, as it would in the reference)
+    assert np.isin(got.code, (-11, -6)).all() and (got.code == -11).sum() > 250
+    assert (got.statistics[:, 1] == 1).all() and (got.statistics[:, 2] == 0).all()
+    assert "did not declare" in dde_b200.strerror(-11)
+    ok = dde_b200.dopri_batch(y0, times, "mg_wrong_lag", parms, **dict(kw, stiff_check=1000000))
+    right = dde_b200.dopri_batch(y0, times, model, parms, **dict(kw, stiff_check=1000000))
+    np.testing.assert_array_equal(ok.code, right.code)
+    assert_bits_equal(ok.y, right.y, "y")
+
+
 def test_reference_example_model_as_plugin(backend):
     """/root/reference/inst/examples/seir.c itself, compiled as a model library with only the
     DDE_MODEL_FN decoration injected (tests/models/build_ref_example.sh), loaded at run time:
