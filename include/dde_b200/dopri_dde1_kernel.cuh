@@ -134,6 +134,12 @@ struct Dde1Scope {
   __device__ __forceinline__ double dde_scope_exp(double x) { return dde_exp(x); }
 };
 
+/* the step-size controller's pow (once per attempt), out of line like dde_pow_ctrl, from the
+   block's copy of the tables */
+static __device__ __noinline__ double dde1_pow_ctrl(unsigned tab, double x, double y) {
+  return dde_pow_shared(tab, x, y);
+}
+
 /* the block's copy of the tables (dde_math.h: dde_pow_shared); a barrier follows */
 __device__ __forceinline__ void dde1_tables_fill(unsigned base) {
   for (unsigned i = threadIdx.x; i < 128u; i += blockDim.x) {
@@ -730,7 +736,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
         deno = deno < 0 ? 1.0 : deno;
         err = 1.0 * err * sqrt(1.0 / ((double) 1 * deno));
         /* dopri_h_new, src/dopri.c:516-525 (step_beta = 0: pow(fac_old, 0) == 1) */
-        const double fac11 = dde_pow_ctrl(err, step_constant);
+        const double fac11 = dde1_pow_ctrl(smem, err, step_constant);
         double fac = fac11 / 1.0;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
         h_new = h / fac;
