@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       double tq;
       M::lags(tt, p, &tq);
       double z = zn;
-      if (!okn) {
+      if (__builtin_expect(!okn, 0)) {
         const Dde1Found f =
             dde1_lookup_ring(ring, count, cap, t0, y0v, tq, w.wbase + w.wn, w.wtop);
         z = f.value;
@@ -715,11 +715,11 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       }
 
       if (attempt_done) {
-        if (sc.undeclared && !error) {
+        if (__builtin_expect(sc.undeclared && !error, 0)) {
           error = true;
           code = -11; /* DDE_ERR_LAG_UNDECLARED */
         }
-        if (error) {
+        if (__builtin_expect(error, 0)) {
           done = true; /* a lag look-up failed during dopri_step, src/dopri.c:387-389 */
           my_stages = 0;
           continue;
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           ++n_accept;
           /* the redundant evaluation at the OLD time, src/dopri.c:400-403 (SURVEY.md
              A.1#2): it counts (n_eval below), and its look-up can fail */
-          if (!lo_ok) {
+          if (__builtin_expect(!lo_ok, 0)) {
             const Dde1Found f =
                 dde1_lookup_ring(ring, count, cap, t0, y0v, lo, w.wbase + w.wn, w.wtop);
             if (f.failed && !error) {
