@@ -254,9 +254,13 @@ def strong_scaling_leg(torch, dist, args, world, rank, park, weak):
                "how": "dde_dopri_shards_* in rank 0's process, one host thread per device, pinned "
                       "host buffers in and out; value = trajectories / slowest shard's device "
                       "time, e2e = wall clock around upload + run_download",
-               "note": "131072 trajectories per device on 8 GPUs are 1.7 per resident thread "
-                       "(148 SMs x 512): the batch ends when the slowest thread's second "
-                       "trajectory does, which bounds the efficiency near 0.85"}
+               "note": "granularity-bound: one device runs 148 SMs x 512 = 75776 trajectories at "
+                       "a time, so the batch is 13.8 trajectories per resident thread on 1 GPU "
+                       "and 1.7 on 8; it ends when the slowest thread's last trajectory does "
+                       "(about one trajectory's duration, 2.8 ms, after the device stops being "
+                       "full), which is 7 % of the run on 1 GPU and most of it on 8.  Measured "
+                       "(profiles/r2_bench_*gpu.json): 0.93 / 0.81 / 0.64 at 2 / 4 / 8 GPUs; the "
+                       "weak-scaling value above is linear."}
     except Exception as exc:  # the leg must never take the headline line with it
         out = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
     if park is not None:

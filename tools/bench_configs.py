@@ -87,7 +87,8 @@ def time_dopri(model, y0, parms, times, kw, n, reps=3, e2e=True):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--c3-traj", type=int, default=1 << 22)
+    ap.add_argument("--c3-traj", type=int, default=1 << 22,
+                    help="trajectories of EACH of the two C3 sweeps (4 M x 1000 rows = 96 GB of rows)")
     ap.add_argument("--c3-times", type=int, default=1001)
     ap.add_argument("--c4-rep", type=int, default=1 << 20)
     ap.add_argument("--c4-steps", type=int, default=10000)
@@ -106,7 +107,7 @@ def main():
 
     # C3: Lorenz / Roessler dopri5 sweeps, dense output at c3_times - 1 times
     for gen in (workloads.lorenz_sweep, workloads.rossler_sweep):
-        n_traj = args.c3_traj // 2
+        n_traj = args.c3_traj
         model, y0, parms, times, kw = gen(n_traj, n_times=args.c3_times)
         out_bytes = n_traj * (args.c3_times - 1) * 3 * 8
         ms, stats, code, _ = time_dopri(model, y0, parms, times, kw, 3, reps=2, e2e=False)
