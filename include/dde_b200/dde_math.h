@@ -22,7 +22,10 @@
  * everywhere.  Compile device code with -fmad=false and host code with
  * -ffp-contract=off so the compiler adds no contractions of its own.
  *
- * Pinned by tests/test_math.py against libm on >= 10^7 inputs per domain
+ * Licence of the upstream algorithm: MIT OR Apache-2.0 WITH LLVM-exception (ARM
+ * optimized-routines); the notice is carried in THIRD_PARTY_NOTICES.md.
+ *
+ * Pinned by tests/test_math_cpu.py against libm on >= 10^7 inputs per domain
  * plus the special-value lattice; errno / FP exception flags are not kept.
  */
 #ifndef DDE_MATH_H
