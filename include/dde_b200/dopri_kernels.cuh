@@ -54,12 +54,6 @@ namespace dde {
    compile-time n keep their whole state in registers instead (1 block). */
 #define DDE_MIN_BLOCKS 3
 #endif
-#ifndef DDE_STAGE_FLUSH_AT
-/* a thread's buffer is written out by its warp once it holds this much (rows that
-   find it full are written directly); Lorenz 1 M x 1000 rows: 43.6 ms at 1/2, 42.3 at
-   3/4, 41.4 at 7/8 */
-#define DDE_STAGE_FLUSH_AT(cap) ((cap) * 7 / 8)
-#endif
 #ifndef DDE_MIN_BLOCKS_SMALL
 #define DDE_MIN_BLOCKS_SMALL 2 /* the same for compile-time n = 2 .. 4 */
 #endif
@@ -71,9 +65,9 @@ namespace dde {
 #define DDE_MIN_BLOCKS_UNROLLED 3
 #endif
 #ifndef DDE_STAGE_ROW_DOUBLES
-/* doubles of output rows a thread of the unrolled kernel stages before its warp
-   writes them out (48: 16 rows of a three-equation system; pitch 49) */
-#define DDE_STAGE_ROW_DOUBLES 48
+/* doubles of output rows a thread of the unrolled kernel holds back until they fill an
+   aligned 32-byte sector of the result array (lcm(n, 4) for n <= 4; pitch 13) */
+#define DDE_STAGE_ROW_DOUBLES 12
 #endif
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
@@ -94,6 +88,19 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 #endif
+
+/* four doubles to one aligned 32-byte sector of global memory: one 256-bit store */
+__device__ __forceinline__ void stg_sector(double *dst, double a, double b, double c, double d) {
+#ifdef DDE_HOST_EMU
+  dst[0] = a;
+  dst[1] = b;
+  dst[2] = c;
+  dst[3] = d;
+#else
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d)
+               : "memory");
+#endif
+}
 
 /* the step-size controller's pow (once per attempt) is out of line, so that the hot
    loop holds one copy of pow, the model's (measured: +1.2 %) */
@@ -227,59 +234,37 @@ dopri_tpt_kernel(const DopriArgs a) {
      before the previous row's interpolation so that a dense output grid does not
      wait for it */
   double t_out = 0.0;
+  double t_out2 = 0.0; /* times[times_idx + 1]: the sector path emits rows two at a time */
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
 
-  /* Output rows of the unrolled kernel are staged: a thread's rows go to its own
-     buffer in shared memory (where a model with history keeps its lag window) and
-     the warp writes a buffer out together, as one contiguous run of the
-     trajectory's result block -- a few full-line stores instead of one 8-byte
-     transaction per component, row and lane (the dense grids of a parameter sweep
-     are bound by exactly those transactions).  Rows that do not fit (one step
-     crossing more than the buffer holds) and a retiring trajectory's remainder are
-     written directly. */
-  constexpr bool STAGE_OUT = MODE == 1 && NC > 0;
-  constexpr int STAGE_DOUBLES = STAGE_OUT ? DDE_STAGE_ROW_DOUBLES / NMAX * NMAX : 1;
+  /* Output rows of the unrolled kernel leave as whole 32-byte sectors.  A dense output grid
+     is bound by the transactions of its row stores (three 8-byte stores per row and lane,
+     each a partial write of a sector another store completes); so a thread keeps the
+     doubles of its rows in a small buffer of its own in shared memory (where a model with
+     history keeps its lag window), addressed by their position in the result array modulo
+     lcm(n, 4), and whenever the four doubles of an aligned sector are there it writes them
+     with one 256-bit store.  Nothing is shared between lanes: no votes, no shuffles, no
+     second pass over the rows.  The doubles before the first and after the last aligned
+     sector of a trajectory's block (there are none when n * n_rows is a multiple of four)
+     are written one by one. */
+  constexpr bool STAGE_OUT = MODE == 1 && NC > 0 && NC <= 4;
+  constexpr int SBUF = NC == 3 ? 12 : 4; /* lcm(n, 4), n = 1 .. 4 */
+  static_assert(!STAGE_OUT || SBUF <= DDE_STAGE_ROW_DOUBLES, "sector buffer");
   /* the thread's buffer as a shared-window address (odd pitch), opaque to the
      optimiser: it would otherwise re-derive it from the special registers per row */
   unsigned stage =
       (unsigned) __cvta_generic_to_shared(s_wc + (size_t) s * (DDE_STAGE_ROW_DOUBLES + 1));
+#ifndef DDE_HOST_EMU
   asm volatile("" : "+r"(stage));
+#endif
   double *yo_next = nullptr; /* where the trajectory's next output row goes */
-  int st_count = 0;          /* doubles pending */
-  double *st_dst = nullptr;  /* where the first of them goes */
+  double *sec_dst = nullptr; /* the aligned sector the oldest double held back belongs to */
+  int sec_have = 0;          /* doubles of the result array from sec_dst up to yo_next */
+  int sec_skip = 0;          /* ... of which the first are not this trajectory's */
+  int sec_rd = 0, sec_wr = 0; /* buffer positions of sec_dst and of yo_next */
 
   for (;;) {
-    if (STAGE_OUT) {
-      /* the lanes that arrive here together flush together.  Any subset of the warp is a
-         correct group (a lane's buffer is only ever read by the group its owner is in, and
-         an owner that arrives alone writes its own rows), so the set the hardware reports
-         as converged is taken as it is. */
-      const unsigned am = __activemask();
-      unsigned want = __ballot_sync(am, st_count >= DDE_STAGE_FLUSH_AT(STAGE_DOUBLES));
-      if (want) {
-        /* votes and shuffles are not memory barriers: order every owner's row stores
-           before its peers' loads */
-        __syncwarp(am);
-        const unsigned lane = threadIdx.x & 31u;
-        const int rank = __popc(am & ((1u << lane) - 1u)), nact = __popc(am);
-        do {
-          const int src_lane = __ffs(want) - 1;
-          want &= want - 1;
-          const int cnt = __shfl_sync(am, st_count, src_lane);
-          double *const dst =
-              (double *) __shfl_sync(am, (unsigned long long) st_dst, src_lane);
-          const unsigned src = __shfl_sync(am, stage, src_lane);
-          for (int k = rank; k < cnt; k += nact) {
-            dst[k] = lds_f64(src + 8u * (unsigned) k);
-          }
-          if ((int) lane == src_lane) {
-            st_count = 0;
-          }
-        } while (want);
-        __syncwarp(am); /* orders the rows before their owner's retirement fence */
-      }
-    }
     if (!active) {
       /* persistent threads: take the next trajectory, or leave */
       traj = (long long) atomicAdd(a.next_traj, 1ULL);
@@ -304,7 +289,17 @@ dopri_tpt_kernel(const DopriArgs a) {
       t = a.times[0];
       times_idx = 1;
       yo_next = a.y_out + ((size_t) traj * (size_t) nt + (a.return_initial ? 1u : 0u)) * (size_t) n;
+      if (STAGE_OUT) {
+        /* position of the trajectory's first row in the result array, in doubles */
+        const unsigned long long g = (unsigned long long) (yo_next - a.y_out);
+        sec_skip = (int) (g & 3ull);
+        sec_have = sec_skip;
+        sec_dst = yo_next - sec_skip;
+        sec_wr = (int) (g % (unsigned) SBUF);
+        sec_rd = sec_wr - sec_skip; /* >= 0: SBUF is a multiple of four */
+      }
       t_out = n_times > 1 ? a.times[1] : 0.0;
+      t_out2 = STAGE_OUT && n_times > 2 ? a.times[2] : 0.0;
       tcrit_idx = a.tcrit_idx0;
       n_eval = n_step = n_accept = n_reject = 0;
       stiff_n_stiff = stiff_n_nonstiff = 0;
@@ -860,7 +855,71 @@ dopri_tpt_kernel(const DopriArgs a) {
         const double t_old = t;
         t += h;
 
-        /* output rows, src/dopri.c:437-456: interpolate from the head */
+        /* output rows, src/dopri.c:437-456: interpolate from the head.  The rows of a step
+           all divide by its h: the divisor's half of the division is done once */
+        /* a row into the thread's sector buffer; the sector it completes, if any, out */
+        auto put_row = [&](const double *row) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            sts_f64(stage + 8u * (unsigned) (sec_wr + i), row[i]);
+          }
+          sec_wr = sec_wr + n == SBUF ? 0 : sec_wr + n;
+          sec_have += n;
+          if (sec_have >= 4) { /* n <= 4: at most one sector per row */
+            const unsigned src = stage + 8u * (unsigned) sec_rd;
+            const double d0 = lds_f64(src), d1 = lds_f64(src + 8u), d2 = lds_f64(src + 16u),
+                         d3 = lds_f64(src + 24u);
+            if (__builtin_expect(sec_skip == 0, 1)) {
+              stg_sector(sec_dst, d0, d1, d2, d3);
+            } else { /* the trajectory's block starts inside this sector */
+              if (sec_skip <= 1) {
+                sec_dst[1] = d1;
+              }
+              if (sec_skip <= 2) {
+                sec_dst[2] = d2;
+              }
+              sec_dst[3] = d3;
+              sec_skip = 0;
+            }
+            sec_dst += 4;
+            sec_rd = sec_rd + 4 == SBUF ? 0 : sec_rd + 4;
+            sec_have -= 4;
+          }
+        };
+        double h_rcp = 0.0;
+        if (STAGE_OUT && times_idx < n_times && (last || sign * t_out <= sign * t)) {
+          h_rcp = dde_div_prepare(h);
+        }
+        if (STAGE_OUT && n_out == 0) {
+          /* two rows per trip: a dense grid asks for a few rows per step, a different number
+             in every lane, and a row is one dependent chain (its time, the quotient, the
+             Horner form); in pairs the warp makes half the trips and each trip overlaps two
+             chains.  The second row is computed whether it is due or not, and kept if it is. */
+          while (times_idx < n_times && (last || sign * t_out <= sign * t)) {
+            const double t3 = times_idx + 2 < n_times ? a.times[times_idx + 2] : 0.0;
+            const double t4 = times_idx + 3 < n_times ? a.times[times_idx + 3] : 0.0;
+            const bool due2 = times_idx + 1 < n_times && (last || sign * t_out2 <= sign * t);
+            const double theta_a = dde_div_prepared(t_out - t_old, h, h_rcp);
+            const double theta_b = dde_div_prepared(t_out2 - t_old, h, h_rcp);
+            const double theta1_a = 1 - theta_a, theta1_b = 1 - theta_b;
+            double row_a[NMAX], row_b[NMAX];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              row_a[i] = METHOD == 0 ? interp5(n, theta_a, theta1_a, hd + i)
+                                     : interp853(n, theta_a, theta1_a, hd + i);
+              row_b[i] = METHOD == 0 ? interp5(n, theta_b, theta1_b, hd + i)
+                                     : interp853(n, theta_b, theta1_b, hd + i);
+            }
+            put_row(row_a);
+            if (due2) {
+              put_row(row_b);
+            }
+            yo_next += due2 ? 2 * n : n;
+            times_idx += due2 ? 2 : 1;
+            t_out = due2 ? t3 : t_out2;
+            t_out2 = due2 ? t4 : t3;
+          }
+        }
         for (;;) {
           if (times_idx >= n_times) {
             break;
@@ -870,7 +929,8 @@ dopri_tpt_kernel(const DopriArgs a) {
             break;
           }
           const double t_next = times_idx + 1 < n_times ? a.times[times_idx + 1] : 0.0;
-          const double theta = (tq - t_old) / h;
+          const double theta =
+              STAGE_OUT ? dde_div_prepared(tq - t_old, h, h_rcp) : (tq - t_old) / h;
           const double theta1 = 1 - theta;
           double row[NMAX];
           /* row of this time: times_idx, shifted by one without the initial row; rows
@@ -882,15 +942,8 @@ dopri_tpt_kernel(const DopriArgs a) {
             row[i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
                                  : interp853(n, theta, theta1, hd + i);
           }
-          if (STAGE_OUT && st_count + n <= STAGE_DOUBLES) {
-            if (st_count == 0) {
-              st_dst = yo;
-            }
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              sts_f64(stage + 8u * (unsigned) (st_count + i), row[i]);
-            }
-            st_count += n;
+          if (STAGE_OUT) {
+            put_row(row);
           } else {
 #pragma unroll
             for (int i = 0; i < n; ++i) {
@@ -961,11 +1014,11 @@ dopri_tpt_kernel(const DopriArgs a) {
     }
 
     if (done) {
-      if (STAGE_OUT) { /* the rows still staged */
-        for (int k = 0; k < st_count; ++k) {
-          st_dst[k] = lds_f64(stage + 8u * (unsigned) k);
+      if (STAGE_OUT) { /* the doubles past the last whole sector */
+        for (int k = sec_skip; k < sec_have; ++k) {
+          sec_dst[k] = lds_f64(stage + 8u * (unsigned) (sec_rd + k));
         }
-        st_count = 0;
+        sec_have = sec_skip = 0;
       }
       /* retire: statistics as r_dopri_cleanup reads them, src/r_dopri.c:412-428 */
       a.stats[4 * traj + 0] = n_eval;

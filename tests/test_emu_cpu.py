@@ -65,6 +65,19 @@ def test_lorenz_sweep(mode):
 
 
 @needs_oracle
+@pytest.mark.parametrize("n_times,return_initial", [(12, False), (12, True), (14, True), (102, True),
+                                                     (2, False), (2, True)])
+def test_lorenz_rows_by_sector(n_times, return_initial):
+    """the unrolled kernel writes its rows as aligned 32-byte sectors of the result array
+    (dopri_kernels.cuh, STAGE_OUT): blocks of rows that start or end inside a sector"""
+    model, y0, parms, times, kw = workloads.lorenz_sweep(37, n_times=n_times, t_end=2.0)
+    kw = dict(kw, return_initial=return_initial)
+    got = pyemu.dopri_batch(model, y0, times, parms, mode=1, **kw)
+    want = pyoracle.dopri_batch("oracle", model, y0, times, parms, **kw)
+    compare(got, want)
+
+
+@needs_oracle
 @pytest.mark.parametrize("kwargs", [
     dict(step_size_max=0.5, step_max_n=400),
     dict(step_size_min=0.05, step_size_min_allow=True),

@@ -798,10 +798,10 @@ def test_streamed_download_equals_run_then_download(backend, n_traj):
 @pytest.mark.parametrize("model_fn,n_times", [("lorenz_sweep", 41), ("rossler_sweep", 1001),
                                               ("lorenz_sweep", 6001)])
 def test_staged_rows_of_the_unrolled_kernel(backend, model_fn, n_times):
-    """Small models without history run the unrolled kernel, whose output rows are staged
-    in shared memory and written out by the warp (dopri_kernels.cuh, MODE 1): same bits as
-    the reference for sparse grids, dense grids, and grids so dense that one step crosses
-    more rows than a thread stages (written directly); the streamed download (several
+    """Small models without history run the unrolled kernel, whose output rows are held
+    back in shared memory until they fill an aligned sector of the result array
+    (dopri_kernels.cuh, MODE 1): same bits as the reference for sparse grids, dense grids,
+    and grids so dense that one step crosses many rows; the streamed download (several
     completion blocks, a ragged last one) sees every row before its block is flagged."""
     n_traj = 70001 if n_times == 41 else 300
     model, y0, parms, times, kw = getattr(workloads, model_fn)(n_traj, first=17, n_times=n_times)
@@ -820,6 +820,31 @@ def test_staged_rows_of_the_unrolled_kernel(backend, model_fn, n_times):
         np.testing.assert_array_equal(got.code[sl], want.code)
         np.testing.assert_array_equal(got.statistics[sl], want.statistics)
         assert_bits_equal(got.y[sl], want.y, "y vs reference")
+
+
+@pytest.mark.parametrize("n_times,return_initial", [(12, False), (12, True), (14, True),
+                                                     (1002, True), (2, False)])
+def test_rows_by_sector_blocks_that_straddle_sectors(backend, n_times, return_initial):
+    """The unrolled kernel writes rows as aligned 32-byte sectors of the result array; a
+    trajectory's block of rows that starts or ends inside a sector (n * n_rows not a multiple
+    of four, or the initial row written by the start-up kernel) shares that sector with its
+    neighbour's block, written by another thread: every double, once, by its owner."""
+    n_traj = 5000
+    model, y0, parms, times, kw = workloads.lorenz_sweep(n_traj, first=3, n_times=n_times,
+                                                         t_end=3.0)
+    kw = dict(kw, return_initial=return_initial)
+    got = dde_b200.dopri_batch(y0, times, model, parms, **kw)
+    assert not np.isnan(got.y[got.code == 1]).any()
+    k = 96
+    for sl in (slice(0, k), slice(n_traj - k, n_traj)):
+        want = pyoracle.dopri_batch(backend, model, y0[sl], times, parms[sl], **kw)
+        np.testing.assert_array_equal(got.code[sl], want.code)
+        np.testing.assert_array_equal(got.statistics[sl], want.statistics)
+        assert_bits_equal(got.y[sl], want.y, "y vs reference")
+    # the whole batch against a run without its first trajectory: the same blocks of rows
+    # at other offsets in the result array
+    half = dde_b200.dopri_batch(y0[1:], times, model, parms[1:], **kw)
+    assert_bits_equal(got.y[1:], half.y, "the same trajectories at shifted offsets")
 
 
 def test_streamed_download_large_model(backend):
