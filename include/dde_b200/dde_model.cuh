@@ -117,7 +117,9 @@ cudaError_t launch_dopri_method(const DopriArgs &args_in, int device_sms, cudaSt
   auto kernel = dopri_tpt_kernel<M, METHOD, 0>;
   if (CAN_UNROLL && args.n_history == 0) {
     kernel = dopri_tpt_kernel<M, METHOD, CAN_UNROLL ? 1 : 0>;
-    dyn = DDE_CTX_BYTES + sizeof(double) * (DDE_STAGE_ROW_DOUBLES + 1) * DDE_TPB; /* staged rows */
+    /* the threads' row buffers, then the block's copy of the pow tables */
+    dyn = DDE_CTX_BYTES + sizeof(double) * (DDE_STAGE_ROW_DOUBLES + 1) * DDE_TPB + 16 +
+          DDE_TAB_SHARED_BYTES;
   }
 #ifndef DDE_NO_CALL_DERIV
   /* one equation, a few parameters, a history: unrolled stages around ONE

@@ -61,41 +61,6 @@
 
 namespace dde {
 
-/* shared memory by shared-window address: 64- and 128-bit accesses.  volatile, so the
-   compiler keeps them in program order (the window is written and read by the same
-   thread in different phases of a step); ptxas schedules them like any other access */
-#ifdef DDE_HOST_EMU
-__device__ __forceinline__ double dde1_lds(unsigned addr) {
-  return *(const double *) ((const char *) dde_smem + addr);
-}
-__device__ __forceinline__ void dde1_sts(unsigned addr, double v) {
-  *(double *) ((char *) dde_smem + addr) = v;
-}
-__device__ __forceinline__ void dde1_lds2(unsigned addr, double &a, double &b) {
-  a = dde1_lds(addr);
-  b = dde1_lds(addr + 8);
-}
-__device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
-  dde1_sts(addr, a);
-  dde1_sts(addr + 8, b);
-}
-#else
-__device__ __forceinline__ double dde1_lds(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void dde1_sts(unsigned addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-__device__ __forceinline__ void dde1_lds2(unsigned addr, double &a, double &b) {
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
-}
-__device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-}
-#endif
-
 /* What the model sees instead of the global history functions and libm when its source
  * is compiled a second time INSIDE a struct derived from this one (dde_model_scoped.inc):
  * unqualified calls to ylag_1 / pow / exp in the model's functions -- now member
@@ -133,29 +98,6 @@ struct Dde1Scope {
   }
   __device__ __forceinline__ double dde_scope_exp(double x) { return dde_exp(x); }
 };
-
-/* the step-size controller's pow (once per attempt), out of line like dde_pow_ctrl, from the
-   block's copy of the tables */
-static __device__ __noinline__ double dde1_pow_ctrl(unsigned tab, double x, double y) {
-  return dde_pow_shared(tab, x, y);
-}
-
-/* the block's copy of the tables (dde_math.h: dde_pow_shared); a barrier follows */
-__device__ __forceinline__ void dde1_tables_fill(unsigned base) {
-  for (unsigned i = threadIdx.x; i < 128u; i += blockDim.x) {
-    double invc, logc, logctail;
-    dde_pow_log_entry((int) i, &invc, &logc, &logctail);
-    dde1_sts2(base + 16u * i, invc, logc);
-    dde1_sts(base + 2048u + 8u * i, logctail);
-#if defined(__CUDA_ARCH__)
-    const ulonglong2 e = dde_exp_tab_d[i];
-    dde1_sts2(base + 3072u + 16u * i, dde_asdouble((uint64_t) e.x), dde_asdouble((uint64_t) e.y));
-#else
-    dde1_sts2(base + 3072u + 16u * i, dde_asdouble(DDE_EXP_TAB(2 * i)),
-              dde_asdouble(DDE_EXP_TAB(2 * i + 1)));
-#endif
-  }
-}
 
 /* Time of right-hand-side evaluation j of a dop853 step (attempt: 0 .. 10; accepted steps
  * go on with 11 .. 15): src/dopri_853.c:178-240, src/dopri.c:400-403,

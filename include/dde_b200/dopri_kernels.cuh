@@ -110,6 +110,64 @@ static __device__ __noinline__ double dde_pow_ctrl(double x, double y) { return 
 #define dde_pow_ctrl dde_pow
 #endif
 
+/* shared memory by shared-window address: 64- and 128-bit accesses.  volatile, so the
+   compiler keeps them in program order (the window is written and read by the same
+   thread in different phases of a step); ptxas schedules them like any other access */
+#ifdef DDE_HOST_EMU
+__device__ __forceinline__ double dde1_lds(unsigned addr) {
+  return *(const double *) ((const char *) dde_smem + addr);
+}
+__device__ __forceinline__ void dde1_sts(unsigned addr, double v) {
+  *(double *) ((char *) dde_smem + addr) = v;
+}
+__device__ __forceinline__ void dde1_lds2(unsigned addr, double &a, double &b) {
+  a = dde1_lds(addr);
+  b = dde1_lds(addr + 8);
+}
+__device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
+  dde1_sts(addr, a);
+  dde1_sts(addr + 8, b);
+}
+#else
+__device__ __forceinline__ double dde1_lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void dde1_sts(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dde1_lds2(unsigned addr, double &a, double &b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+#endif
+
+/* the step-size controller's pow (once per attempt), out of line like dde_pow_ctrl, from the
+   block's copy of the tables */
+static __device__ __noinline__ double dde1_pow_ctrl(unsigned tab, double x, double y) {
+  return dde_pow_shared(tab, x, y);
+}
+
+/* the block's copy of the tables (dde_math.h: dde_pow_shared); a barrier follows */
+__device__ __forceinline__ void dde1_tables_fill(unsigned base) {
+  for (unsigned i = threadIdx.x; i < 128u; i += blockDim.x) {
+    double invc, logc, logctail;
+    dde_pow_log_entry((int) i, &invc, &logc, &logctail);
+    dde1_sts2(base + 16u * i, invc, logc);
+    dde1_sts(base + 2048u + 8u * i, logctail);
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 e = dde_exp_tab_d[i];
+    dde1_sts2(base + 3072u + 16u * i, dde_asdouble((uint64_t) e.x), dde_asdouble((uint64_t) e.y));
+#else
+    dde1_sts2(base + 3072u + 16u * i, dde_asdouble(DDE_EXP_TAB(2 * i)),
+              dde_asdouble(DDE_EXP_TAB(2 * i + 1)));
+#endif
+  }
+}
+
 /* Ring state a trajectory starts from: empty, or -- on a restart -- what the
  * previous run left, in which case t0 is the oldest surviving entry's time
  * (dopri_data_reset, src/dopri.c:185-191). */
@@ -201,6 +259,21 @@ dopri_tpt_kernel(const DopriArgs a) {
     s_lag_u.hl = hl;
     s_lag_u.order = ORDER;
     s_lag_u.staged = NC > 0 ? (STAGED ? 1 : 0) : a.win_staged;
+  }
+  /* the unrolled kernel has shared memory to spare (no lag window): the step-size
+     controller's pow reads a copy of its tables there, behind the threads' row buffers --
+     a fixed ~30 cycles per gather instead of an L1 miss now and then (6 % of the stall
+     samples of the Lorenz sweep) */
+  constexpr bool TAB_SHARED = MODE == 1 && NC > 0 && NC <= 4;
+  unsigned tab = 0;
+  if (TAB_SHARED) {
+    tab = (unsigned) __cvta_generic_to_shared(s_wc) +
+          8u * (unsigned) ((DDE_STAGE_ROW_DOUBLES + 1) * DDE_TPB);
+    tab = (tab + 15u) & ~15u;
+#ifndef DDE_HOST_EMU
+    asm volatile("" : "+r"(tab));
+#endif
+    dde1_tables_fill(tab);
   }
   __syncthreads();
 
@@ -748,9 +821,13 @@ dopri_tpt_kernel(const DopriArgs a) {
           err = sign * err * sqrt(1.0 / ((double) n * deno));
         }
         /* dopri_h_new, src/dopri.c:516-525 */
-        const double fac11 = dde_pow_ctrl(err, step_constant);
+        const double fac11 =
+            TAB_SHARED ? dde1_pow_ctrl(tab, err, step_constant) : dde_pow_ctrl(err, step_constant);
         /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
-        const double facb = METHOD == 0 ? dde_pow_ctrl(fac_old, step_beta) : 1.0;
+        const double facb =
+            METHOD != 0 ? 1.0
+                        : (TAB_SHARED ? dde1_pow_ctrl(tab, fac_old, step_beta)
+                                      : dde_pow_ctrl(fac_old, step_beta));
         double fac = fac11 / facb;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
         h_new = h / fac;
