@@ -25,8 +25,15 @@ DDE_REGISTER_DOPRI_OUTPUT(lorenz,         lorenz,         3, 3,       lorenz_out
 DDE_REGISTER_DOPRI(       rossler,        rossler,        3, 3)
 DDE_REGISTER_DOPRI_LAGS(  mackey_glass,   mackey_glass,   1, 3,       mackey_glass_lags, 1)
 
-/*                  name       target     n  n_parms n_out */
-DDE_REGISTER_DIFEQ(sir_delay, sir_delay, 3, 2,      0)
+/* the delayed SIR map compiled once more in scope too: its look-back reads the history
+   state from registers (difeq_kernels.cuh: DifeqScope) */
+#define DDE_SCOPED_MODEL sir_delay
+#define DDE_SCOPED_SOURCE "sir_delay.h"
+#define DDE_SCOPED_BASE ::dde::DifeqScope
+#include <dde_b200/dde_model_scoped.inc>
+
+/*                         name       target     n  n_parms n_out */
+DDE_REGISTER_DIFEQ_SCOPED(sir_delay, sir_delay, 3, 2,      0)
 
 #ifdef DDE_LAG_STATS
 /* debug build only: read and clear the lag-window counters of this module */

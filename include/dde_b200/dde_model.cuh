@@ -228,9 +228,30 @@ cudaError_t launch_difeq_model(const DifeqArgs &args_in, int device_sms, cudaStr
 #define DDE_REGISTER_DOPRI(NAME, DERIV, NEQ, NPARMS) \
   DDE_REGISTER_DOPRI_OUTPUT(NAME, DERIV, NEQ, NPARMS, DDE_NO_OUTPUT, 0)
 
-#define DDE_REGISTER_DIFEQ(NAME, TARGET, NEQ, NPARMS, NOUT)                                    \
+#define DDE_REGISTER_DIFEQ(NAME, TARGET, NEQ, NPARMS, NOUT) \
+  DDE_REGISTER_DIFEQ_FULL(NAME, TARGET, NEQ, NPARMS, NOUT, false, DDE_NO_DIFEQ_SCOPE_TYPE, \
+                          DDE_NO_SCOPE_CALL)
+
+/* ... with the model's source compiled a second time inside a struct (dde_model_scoped.inc,
+ *     #define DDE_SCOPED_BASE ::dde::DifeqScope): the history state yprev_* read travels in
+ *     registers of the iterating thread instead of shared memory (difeq_kernels.cuh) */
+#define DDE_REGISTER_DIFEQ_SCOPED(NAME, TARGET, NEQ, NPARMS, NOUT) \
+  DDE_REGISTER_DIFEQ_FULL(NAME, TARGET, NEQ, NPARMS, NOUT, true, DDE_SCOPE_TYPE, DDE_SCOPE_CALL)
+
+#define DDE_NO_DIFEQ_SCOPE_TYPE(NAME) ::dde::DifeqScope
+
+#define DDE_REGISTER_DIFEQ_FULL(NAME, TARGET, NEQ, NPARMS, NOUT, IS_SCOPED, SCOPE_TYPE,        \
+                                SCOPE_CALL)                                                    \
   struct dde_difeq_model_##NAME {                                                              \
     static constexpr int N = (NEQ), NP = (NPARMS), N_OUT = (NOUT);                             \
+    static constexpr bool SCOPED = (IS_SCOPED);                                                \
+    typedef SCOPE_TYPE(NAME) Scoped;                                                           \
+    static __device__ __forceinline__ void target_scoped(Scoped &sc, size_t n, size_t step,    \
+                                                         const double *y, double *y_next,      \
+                                                         size_t n_out, double *out,            \
+                                                         const void *data) {                   \
+      SCOPE_CALL(sc, TARGET)(n, step, y, y_next, n_out, out, data);                            \
+    }                                                                                          \
     static __device__ __forceinline__ void target(size_t n, size_t step, const double *y,      \
                                                   double *y_next, size_t n_out, double *out,   \
                                                   const void *data) {                          \

@@ -57,6 +57,93 @@ struct DifeqArgs {
   unsigned long long *next_rep;
 };
 
+/* What a difference equation sees instead of the global yprev_* functions when its source
+ * is compiled a second time INSIDE a struct derived from this one (dde_model_scoped.inc with
+ * DDE_SCOPED_BASE ::dde::DifeqScope): the replicate's history state -- the current step, the
+ * first one, where the ring's head is, how many entries it holds -- as members, i.e. in
+ * registers of the thread that iterates the replicate.  The model ABI carries no solver
+ * handle (src/difeq.h:19-21; the reference keeps a process global, src/difeq.c:12), so the
+ * global functions keep that state in a per-thread block of shared memory and every step
+ * writes and re-reads it (lag_ctx.cuh: sd_step, sd_head, sd_count, sd_error ...: 58
+ * instructions per step of the delayed SIR map for 8 flops of model); with the state in
+ * registers the compiler sees through the look-up.  Same semantics, src/difeq.c:261-281. */
+struct DifeqScope {
+  long long step_now; /* the step target() is being called for */
+  long long step0;    /* the first step (on a restart: the oldest surviving entry's) */
+  const double *y0;
+  const double *ring; /* the replicate's ring in HBM (history not on chip) */
+  unsigned hist_col;  /* history on chip: shared-window address of this thread's column */
+  unsigned count;     /* entries committed */
+  int head;           /* slot of the next commit */
+  int cap, n, hl;
+  bool staged, error;
+  int code;
+  __device__ __forceinline__ bool find(int step, int *slot) {
+    const int offset = (int) step_now - step;
+    const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
+    /* cap == 0 || offset < 0 || offset >= used, as one comparison: no capacity is nothing
+       used, a negative offset a huge unsigned one */
+    if ((unsigned) offset >= used) {
+      error = true;
+      code = -9; /* DDE_ERR_DIFEQ_HISTORY */
+      return false;
+    }
+    *slot = ring_slot_back(head, offset + 1, cap);
+    return true;
+  }
+  __device__ __forceinline__ double read(int slot, size_t comp) const {
+    if (staged) {
+      return lds_f64(hist_col + (unsigned) ((slot * n + (int) comp) * (DDE_TPB * 8)));
+    }
+    return ring[(size_t) slot * (size_t) hl + 1 + comp];
+  }
+  __device__ __forceinline__ double yprev_1(int step, size_t i) {
+    if (step <= (int) step0) {
+      return y0[i];
+    }
+    int slot;
+    return find(step, &slot) ? read(slot, i) : na_real();
+  }
+  __device__ __forceinline__ void yprev_all(int step, double *y) {
+    if (step <= (int) step0) {
+      for (int i = 0; i < n; ++i) {
+        y[i] = y0[i];
+      }
+      return;
+    }
+    int slot;
+    if (find(step, &slot)) {
+      for (int i = 0; i < n; ++i) {
+        y[i] = read(slot, (size_t) i);
+      }
+    }
+  }
+  template <class Index>
+  __device__ __forceinline__ void yprev_indexed(int step, const Index *idx, size_t nidx,
+                                                double *y) {
+    if (step <= (int) step0) {
+      for (size_t i = 0; i < nidx; ++i) {
+        y[i] = y0[idx[i]];
+      }
+      return;
+    }
+    int slot;
+    if (find(step, &slot)) {
+      for (size_t i = 0; i < nidx; ++i) {
+        y[i] = read(slot, (size_t) idx[i]);
+      }
+    }
+  }
+  __device__ __forceinline__ void yprev_vec(int step, const size_t *idx, size_t nidx, double *y) {
+    yprev_indexed<size_t>(step, idx, nidx, y);
+  }
+  __device__ __forceinline__ void yprev_vec_int(int step, const int *idx, size_t nidx, double *y) {
+    yprev_indexed<int>(step, idx, nidx, y);
+  }
+  __device__ __forceinline__ double dde_scope_pow(double x, double y) { return dde_pow(x, y); }
+  __device__ __forceinline__ double dde_scope_exp(double x) { return dde_exp(x); }
+};
+
 /* RESTART: compiled with the difeq_continue paths (start from / leave a history
  * in HBM); the plain instantiation is ~10 % faster on C4 without them. */
 /* STAGED: the history lives in shared memory (a.staged, decided at launch); a
@@ -130,13 +217,32 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     unsigned long long step = step_first;
     int steps_idx = 1;
     double *ring = a.ring + (size_t) rep * (size_t) cap * (size_t) hl;
-    sd_ring[s] = ring;
-    sd_y0[s] = y0;
-    sd_step0[s] = (long long) step_first;
-    sd_step[s] = (long long) step;
-    sd_code[s] = 0;
-    sd_error[s] = 0;
-    sd_cfg[s] = cfg;
+    /* the history state the model's yprev_* read: members of `sc` (registers) for a model
+       compiled in scope, the per-thread block in shared memory otherwise */
+    constexpr bool SCOPED = M::SCOPED;
+    typename M::Scoped sc;
+    sc.step_now = (long long) step;
+    sc.step0 = (long long) step_first;
+    sc.y0 = y0;
+    sc.ring = ring;
+    sc.hist_col = hist_col;
+    sc.count = 0;
+    sc.head = 0;
+    sc.cap = cap;
+    sc.n = n;
+    sc.hl = hl;
+    sc.staged = STAGED;
+    sc.error = false;
+    sc.code = 0;
+    if (!SCOPED) {
+      sd_ring[s] = ring;
+      sd_y0[s] = y0;
+      sd_step0[s] = (long long) step_first;
+      sd_step[s] = (long long) step;
+      sd_code[s] = 0;
+      sd_error[s] = 0;
+      sd_cfg[s] = cfg;
+    }
 
     int head = 0;
     unsigned count = 0;
@@ -147,7 +253,10 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       head = (int) (count % (unsigned) cap);
       const unsigned used = count < (unsigned) cap ? count : (unsigned) cap;
       if (count > 0) {
-        sd_step0[s] = (long long) (a.step_origin + (count - used));
+        sc.step0 = (long long) (a.step_origin + (count - used));
+        if (!SCOPED) {
+          sd_step0[s] = sc.step0;
+        }
       }
       if (STAGED) { /* back on chip */
         for (unsigned k = 0; k < used; ++k) {
@@ -160,8 +269,12 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         }
       }
     }
-    sd_count[s] = count;
-    sd_head[s] = head;
+    sc.count = count;
+    sc.head = head;
+    if (!SCOPED) {
+      sd_count[s] = count;
+      sd_head[s] = head;
+    }
 #define DDE_DIFEQ_COMMIT(yy)                                  \
   do {                                                        \
     if (cap > 0) {                                            \
@@ -184,10 +297,29 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
       }                                                       \
       head = head + 1 == cap ? 0 : head + 1;                  \
       ++count;                                                \
-      sd_head[s] = head;                                       \
-      sd_count[s] = count;                                     \
+      sc.head = head;                                         \
+      sc.count = count;                                       \
+      if (!SCOPED) {                                          \
+        sd_head[s] = head;                                    \
+        sd_count[s] = count;                                  \
+      }                                                       \
     }                                                         \
   } while (0)
+#define DDE_DIFEQ_TARGET()                                                           \
+  do {                                                                               \
+    sc.step_now = (long long) step;                                                  \
+    if (SCOPED) {                                                                    \
+      M::target_scoped(sc, (size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p); \
+    } else {                                                                         \
+      sd_step[s] = (long long) step;                                                 \
+      if (NC > 0) { /* what yprev_* will read: lets the optimiser drop the other path */ \
+        __builtin_assume(sd_cfg[s] == cfg);                                          \
+      }                                                                              \
+      M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);          \
+    }                                                                                \
+  } while (0)
+#define DDE_DIFEQ_ERRORED() (SCOPED ? sc.error : sd_error[s] != 0)
+#define DDE_DIFEQ_CODE() (SCOPED ? sc.code : sd_code[s])
 
     /* the initial state is the first entry, src/difeq.c:140-156; on a restart
        the ring already ends with the state the last run stopped at, and the
@@ -212,12 +344,8 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     /* the next step a row is wanted at: read when the row index moves, not per step */
     unsigned long long step_out = steps_idx < n_steps ? a.steps[steps_idx] : ~0ULL;
     for (;;) {
-      sd_step[s] = (long long) step;
-      if (NC > 0) { /* what yprev_* will read: lets the optimiser drop the other path */
-        __builtin_assume(sd_cfg[s] == cfg);
-      }
-      M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
-      if (sd_error[s]) {
+      DDE_DIFEQ_TARGET();
+      if (DDE_DIFEQ_ERRORED()) {
         failed = true; /* Rf_error in difeq_find_step, src/difeq.c:267-270 */
         break;
       }
@@ -263,9 +391,8 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
     if (!failed && has_output && store_next_output) {
       /* trailing call for the outputs of the last stored row,
          src/difeq.c:249-255 */
-      sd_step[s] = (long long) step;
-      M::target((size_t) n, (size_t) step, y, y_next, (size_t) n_out, o, p);
-      if (sd_error[s]) {
+      DDE_DIFEQ_TARGET();
+      if (DDE_DIFEQ_ERRORED()) {
         failed = true;
       } else {
 #pragma unroll
@@ -276,8 +403,11 @@ __global__ void __launch_bounds__(DDE_TPB) difeq_tpt_kernel(const DifeqArgs a) {
         }
       }
     }
+    a.code[rep] = failed ? DDE_DIFEQ_CODE() : 1; /* OK_COMPLETE */
 #undef DDE_DIFEQ_COMMIT
-    a.code[rep] = failed ? sd_code[s] : 1; /* OK_COMPLETE */
+#undef DDE_DIFEQ_TARGET
+#undef DDE_DIFEQ_ERRORED
+#undef DDE_DIFEQ_CODE
     if (RESTART && cap > 0 && a.restartable) {
       /* what a later difeq_continue needs: the count, and an on-chip history
          written back to the replicate's ring (slot order is the same) */

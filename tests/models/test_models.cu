@@ -32,10 +32,26 @@ DDE_REGISTER_DOPRI(       delayed_growth_vec, delayed_growth_vec, 0, -1)
 DDE_REGISTER_DOPRI(       delayed_growth_all, delayed_growth_all, 0, -1)
 DDE_REGISTER_DOPRI_LAGS(  mg_wrong_lag,   mg_wrong_lag,   1, 3,       mg_wrong_lag_lags, 1)
 
-/*                  name       target     n  n_parms n_out */
-DDE_REGISTER_DIFEQ(logistic,  logistic,  0, -1,     0)
-DDE_REGISTER_DIFEQ(additive,  additive,  0, -1,     -1)
-DDE_REGISTER_DIFEQ(fibonacci, fibonacci, 5, -1,     0)
-DDE_REGISTER_DIFEQ(fib_out,   fib_out,   1, -1,     1)
-DDE_REGISTER_DIFEQ(fib_all,   fib_all,   0, -1,     0)
-DDE_REGISTER_DIFEQ(fib_vec,   fib_vec,   0, -1,     0)
+/* three of the look-back fixtures compiled in scope as well (yprev_1 / yprev_all / yprev_vec
+   then read the history state from registers, difeq_kernels.cuh: DifeqScope); the others
+   stay on the global functions, so that the parity tests cover both */
+#define DDE_SCOPED_MODEL fibonacci
+#define DDE_SCOPED_SOURCE "difeq_fixtures.h"
+#define DDE_SCOPED_BASE ::dde::DifeqScope
+#include <dde_b200/dde_model_scoped.inc>
+#define DDE_SCOPED_MODEL fib_all
+#define DDE_SCOPED_SOURCE "difeq_fixtures.h"
+#define DDE_SCOPED_BASE ::dde::DifeqScope
+#include <dde_b200/dde_model_scoped.inc>
+#define DDE_SCOPED_MODEL fib_vec
+#define DDE_SCOPED_SOURCE "difeq_fixtures.h"
+#define DDE_SCOPED_BASE ::dde::DifeqScope
+#include <dde_b200/dde_model_scoped.inc>
+
+/*                         name       target     n  n_parms n_out */
+DDE_REGISTER_DIFEQ(       logistic,  logistic,  0, -1,     0)
+DDE_REGISTER_DIFEQ(       additive,  additive,  0, -1,     -1)
+DDE_REGISTER_DIFEQ_SCOPED(fibonacci, fibonacci, 5, -1,     0)
+DDE_REGISTER_DIFEQ(       fib_out,   fib_out,   1, -1,     1)
+DDE_REGISTER_DIFEQ_SCOPED(fib_all,   fib_all,   0, -1,     0)
+DDE_REGISTER_DIFEQ_SCOPED(fib_vec,   fib_vec,   0, -1,     0)
