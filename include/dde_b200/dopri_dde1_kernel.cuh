@@ -50,6 +50,9 @@
 #ifndef DDE1_WIN
 #define DDE1_WIN 5 /* entries in the staged window */
 #endif
+#ifndef DDE1_WALK
+#define DDE1_WALK 4 /* ring entries probed per round trip by a query above the window */
+#endif
 #ifndef DDE1_MIN_BLOCKS
 #define DDE1_MIN_BLOCKS 4 /* resident 128-thread blocks per SM (128 registers) */
 #endif
@@ -204,7 +207,7 @@ __device__ __forceinline__ double dde1_lookup(const Dde1Win &w, double t0, doubl
  * idx sits in slot idx % cap.  `top` is the first entry above the window (wbase + wn) and
  * `wtop` its start time (+inf: there is none): a query at or above it -- a step attempt
  * that spans more old entries than the window holds -- is found by walking up from there,
- * two probes per round trip; anything else by bisection.  Out of line and by value. */
+ * DDE1_WALK probes per round trip; anything else by bisection.  Out of line and by value. */
 struct Dde1Found {
   double value;
   bool failed; /* ERR_YLAG_FAIL */
@@ -229,13 +232,25 @@ static __device__ __noinline__ Dde1Found dde1_lookup_ring(const double *ring, un
     DDE_LAG_COUNT(0);
     DDE_CHECK(top < count && count - top <= (unsigned) cap);
     lo = top;
+    /* the start times of the next DDE1_WALK entries in ONE round trip to L2 / HBM (a lone
+       lane walks while its warp waits: what counts is round trips, not instructions).
+       They are sorted, so how many of them are <= tq is how far to go. */
+    unsigned slot = (lo + 1) % (unsigned) cap;
     for (;;) {
-      const double t1 = lo + 1 < count ? DDE1_TIME(lo + 1) : pos_inf();
-      const double t2 = lo + 2 < count ? DDE1_TIME(lo + 2) : pos_inf();
-      if (t2 <= tq) {
-        lo += 2;
-      } else {
-        lo += t1 <= tq ? 1u : 0u;
+      double ts[DDE1_WALK];
+#pragma unroll
+      for (int k = 0; k < DDE1_WALK; ++k) {
+        DDE_CHECK(!(lo + 1 + k < count) || count - (lo + 1 + k) <= (unsigned) cap);
+        ts[k] = lo + 1 + k < count ? (DDE_LAG_COUNT(5), ring[(size_t) slot * 10u + 8u]) : pos_inf();
+        slot = slot + 1 == (unsigned) cap ? 0u : slot + 1;
+      }
+      unsigned adv = 0;
+#pragma unroll
+      for (int k = 0; k < DDE1_WALK; ++k) {
+        adv += ts[k] <= tq ? 1u : 0u;
+      }
+      lo += adv;
+      if (adv < DDE1_WALK) {
         break;
       }
     }
