@@ -503,6 +503,12 @@ def main():
             try:
                 sys.path.insert(0, str(ROOT / "tools"))
                 import bench_configs
+                from dde_b200 import workloads as _w
+                # C3 at a quarter of its size per sweep (1 M x 1000 rows = 24 GB of rows on the
+                # device; the full 4 M per sweep: tools/bench_configs.py, profiles/), kernel only
+                # -- end to end these are bound by moving the rows over PCIe
+                line["c3_lorenz_1M"] = bench_configs.c3(_w.lorenz_sweep, 1 << 20, 1001, e2e=False)
+                line["c3_rossler_1M"] = bench_configs.c3(_w.rossler_sweep, 1 << 20, 1001, e2e=False)
                 line["c4_difeq_sir_delay"] = bench_configs.c4(1 << 20, 10000)
                 line["c5_seir_age_4096"] = bench_configs.c5(4096)
             except Exception as exc:

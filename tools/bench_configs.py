@@ -107,28 +107,35 @@ def main():
 
     # C3: Lorenz / Roessler dopri5 sweeps, dense output at c3_times - 1 times
     for gen in (workloads.lorenz_sweep, workloads.rossler_sweep):
-        n_traj = args.c3_traj
-        model, y0, parms, times, kw = gen(n_traj, n_times=args.c3_times)
-        out_bytes = n_traj * (args.c3_times - 1) * 3 * 8
-        ms, stats, code, _ = time_dopri(model, y0, parms, times, kw, 3, reps=2, e2e=False)
-        S, A, E = (stats[:, k].astype(np.float64).sum() for k in (1, 2, 0))
-        frhs = 9 if model == "lorenz" else 7
-        flops = 3 * (76 * S + 6 * A + 8 * n_traj * (args.c3_times - 1)) + E * frhs
-        line = {"workload": "C3 %s dopri5 sweep" % model, "n_traj": n_traj,
-                "n_out_times": args.c3_times - 1, "ms": ms,
-                "trajectories_per_s": n_traj / (ms * 1e-3),
-                "accepted_steps_per_s": A / (ms * 1e-3),
-                "output_GB": out_bytes / 1e9, "failed": int((code != 1).sum())}
-        line.update(rates(flops, out_bytes + 8.0 * 6 * n_traj, ms))
+        print(json.dumps(c3(gen, args.c3_traj, args.c3_times)))
+
+    print(json.dumps(c4(args.c4_rep, args.c4_steps)))
+
+
+def c3(gen, n_traj, n_times, e2e=True):
+    """C3: one of the two dopri5 parameter sweeps (workloads.lorenz_sweep / rossler_sweep) with
+    dense output at n_times - 1 times; returns the result line"""
+    model, y0, parms, times, kw = gen(n_traj, n_times=n_times)
+    out_bytes = n_traj * (n_times - 1) * 3 * 8
+    ms, stats, code, _ = time_dopri(model, y0, parms, times, kw, 3, reps=2, e2e=False)
+    S, A, E = (stats[:, k].astype(np.float64).sum() for k in (1, 2, 0))
+    frhs = 9 if model == "lorenz" else 7
+    flops = 3 * (76 * S + 6 * A + 8 * n_traj * (n_times - 1)) + E * frhs
+    line = {"workload": "C3 %s dopri5 sweep" % model, "n_traj": n_traj,
+            "n_out_times": n_times - 1, "ms": ms,
+            "trajectories_per_s": n_traj / (ms * 1e-3),
+            "accepted_steps_per_s": A / (ms * 1e-3),
+            "output_GB": out_bytes / 1e9, "failed": int((code != 1).sum()),
+            "bound": "FP64 issue (rows leave as whole 32-byte sectors: HBM is not the limit)"}
+    line.update(rates(flops, out_bytes + 8.0 * 6 * n_traj, ms))
+    if e2e:
         # end to end on a slice whose 6.3 GB of rows fit a pinned host buffer comfortably
         n_e2e = min(n_traj, 1 << 18)
         _, _, _, e2e_ms = time_dopri(model, y0[:n_e2e], parms[:n_e2e], times, kw, 3, reps=2)
         line["e2e"] = {"n_traj": n_e2e, "ms": e2e_ms,
                        "trajectories_per_s": n_e2e / (e2e_ms * 1e-3),
-                       "d2h_GBps": n_e2e * (args.c3_times - 1) * 24 / (e2e_ms * 1e-3) / 1e9}
-        print(json.dumps(line))
-
-    print(json.dumps(c4(args.c4_rep, args.c4_steps)))
+                       "d2h_GBps": n_e2e * (n_times - 1) * 24 / (e2e_ms * 1e-3) / 1e9}
+    return line
 
 
 def c4(n_rep, n_steps):
