@@ -4,5 +4,8 @@
 
 #include "../models/seir_age.h"
 
-/*                       name      deriv     threads components n_parms */
-DDE_REGISTER_DOPRI_COOP(seir_age, seir_age, 256,    2,         3)
+#ifndef DDE_SEIR_AGE_THREADS
+#define DDE_SEIR_AGE_THREADS 256
+#endif
+/*                       name      deriv     threads               components                   n_parms */
+DDE_REGISTER_DOPRI_COOP(seir_age, seir_age, DDE_SEIR_AGE_THREADS, (512 / DDE_SEIR_AGE_THREADS), 3)

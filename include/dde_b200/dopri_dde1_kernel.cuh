@@ -696,8 +696,12 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
         const double fac11 = dde1_pow_ctrl(smem, err, step_constant);
         double fac = fac11 / 1.0;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
-        h_new = h / fac;
-        if ((err <= 1) || force_this_step) {
+        const bool accepted = (err <= 1) || force_this_step;
+        /* one division for both outcomes: a rejected lane divides by its own factor
+           (src/dopri.c:495-499) */
+        const double fac_rej = fmin(1 / step_factor_min, fac11 / step_factor_safe);
+        h_new = h / (accepted ? fac : fac_rej);
+        if (accepted) {
           my_stages = NST - 1;
           fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
           ++n_accept;
@@ -717,7 +721,6 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
           tn = dp8_stage_time(13, t, h);
         } else {
           /* rejected, src/dopri.c:495-509 */
-          h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);
           reject = true;
           if (n_accept >= 1) {
             ++n_reject;

@@ -830,8 +830,12 @@ dopri_tpt_kernel(const DopriArgs a) {
                                       : dde_pow_ctrl(fac_old, step_beta));
         double fac = fac11 / facb;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
-        h_new = h / fac;
         accepted = (err <= 1) || force_this_step;
+        /* one division for both outcomes -- a rejected lane divides by its own factor,
+           src/dopri.c:495-499 -- instead of a second one that only the rejected lanes of the
+           warp execute */
+        const double fac_rej = fmin(1 / step_factor_min, fac11 / step_factor_safe);
+        h_new = h / (accepted ? fac : fac_rej);
         if (accepted) {
           my_stages = NST;
           fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
@@ -850,7 +854,6 @@ dopri_tpt_kernel(const DopriArgs a) {
           }
         } else {
           /* rejected, src/dopri.c:495-509 */
-          h_new = h / fmin(1 / step_factor_min, fac11 / step_factor_safe);
           reject = true;
           if (n_accept >= 1) {
             ++n_reject;
