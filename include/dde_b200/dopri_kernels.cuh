@@ -64,6 +64,9 @@ namespace dde {
    trajectories, 10 rows 37.2 -> 25.1 ms) */
 #define DDE_MIN_BLOCKS_UNROLLED 3
 #endif
+#ifndef DDE_ROW_GROUP
+#define DDE_ROW_GROUP 2 /* output rows the unrolled kernel forms per trip of its row loop */
+#endif
 #ifndef DDE_STAGE_ROW_DOUBLES
 /* doubles of output rows a thread of the unrolled kernel holds back until they fill an
    aligned 32-byte sector of the result array (lcm(n, 4) for n <= 4; pitch 13) */
@@ -307,7 +310,6 @@ dopri_tpt_kernel(const DopriArgs a) {
      before the previous row's interpolation so that a dense output grid does not
      wait for it */
   double t_out = 0.0;
-  double t_out2 = 0.0; /* times[times_idx + 1]: the sector path emits rows two at a time */
   int n_eval = 0, n_step = 0, n_accept = 0, n_reject = 0;
   unsigned long long stiff_n_stiff = 0, stiff_n_nonstiff = 0;
 
@@ -372,7 +374,6 @@ dopri_tpt_kernel(const DopriArgs a) {
         sec_rd = sec_wr - sec_skip; /* >= 0: SBUF is a multiple of four */
       }
       t_out = n_times > 1 ? a.times[1] : 0.0;
-      t_out2 = STAGE_OUT && n_times > 2 ? a.times[2] : 0.0;
       tcrit_idx = a.tcrit_idx0;
       n_eval = n_step = n_accept = n_reject = 0;
       stiff_n_stiff = stiff_n_nonstiff = 0;
@@ -971,33 +972,51 @@ dopri_tpt_kernel(const DopriArgs a) {
           h_rcp = dde_div_prepare(h);
         }
         if (STAGE_OUT && n_out == 0) {
-          /* two rows per trip: a dense grid asks for a few rows per step, a different number
-             in every lane, and a row is one dependent chain (its time, the quotient, the
-             Horner form); in pairs the warp makes half the trips and each trip overlaps two
-             chains.  The second row is computed whether it is due or not, and kept if it is. */
+          /* DDE_ROW_GROUP rows per trip: a dense grid asks for a few rows per step, a different
+             number in every lane, and a row is one dependent chain (its time, the quotient,
+             the Horner form); in groups the warp makes fewer trips and each trip overlaps
+             several chains.  Every row of the group is computed whether it is due or not
+             (the due ones are a prefix: the times ascend), and kept if it is. */
+          constexpr int G = DDE_ROW_GROUP;
           while (times_idx < n_times && (last || sign * t_out <= sign * t)) {
-            const double t3 = times_idx + 2 < n_times ? a.times[times_idx + 2] : 0.0;
-            const double t4 = times_idx + 3 < n_times ? a.times[times_idx + 3] : 0.0;
-            const bool due2 = times_idx + 1 < n_times && (last || sign * t_out2 <= sign * t);
-            const double theta_a = dde_div_prepared(t_out - t_old, h, h_rcp);
-            const double theta_b = dde_div_prepared(t_out2 - t_old, h, h_rcp);
-            const double theta1_a = 1 - theta_a, theta1_b = 1 - theta_b;
-            double row_a[NMAX], row_b[NMAX];
+            double tq[G + 1];
+            tq[0] = t_out;
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
-              row_a[i] = METHOD == 0 ? interp5(n, theta_a, theta1_a, hd + i)
-                                     : interp853(n, theta_a, theta1_a, hd + i);
-              row_b[i] = METHOD == 0 ? interp5(n, theta_b, theta1_b, hd + i)
-                                     : interp853(n, theta_b, theta1_b, hd + i);
+            for (int k = 1; k <= G; ++k) {
+              tq[k] = times_idx + k < n_times ? a.times[times_idx + k] : 0.0;
             }
-            put_row(row_a);
-            if (due2) {
-              put_row(row_b);
+            int due = 1;
+#pragma unroll
+            for (int k = 1; k < G; ++k) {
+              due += (due == k && times_idx + k < n_times && (last || sign * tq[k] <= sign * t))
+                         ? 1 : 0;
             }
-            yo_next += due2 ? 2 * n : n;
-            times_idx += due2 ? 2 : 1;
-            t_out = due2 ? t3 : t_out2;
-            t_out2 = due2 ? t4 : t3;
+            double rows[G][NMAX];
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+              const double theta = dde_div_prepared(tq[k] - t_old, h, h_rcp);
+              const double theta1 = 1 - theta;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+                rows[k][i] = METHOD == 0 ? interp5(n, theta, theta1, hd + i)
+                                         : interp853(n, theta, theta1, hd + i);
+              }
+            }
+            put_row(rows[0]);
+#pragma unroll
+            for (int k = 1; k < G; ++k) {
+              if (k < due) {
+                put_row(rows[k]);
+              }
+            }
+            yo_next += due * n;
+            times_idx += due;
+            double tn = tq[G];
+#pragma unroll
+            for (int k = G - 1; k >= 1; --k) {
+              tn = due == k ? tq[k] : tn;
+            }
+            t_out = tn;
           }
         }
         for (;;) {
