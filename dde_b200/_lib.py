@@ -61,6 +61,8 @@ SYMBOLS = [
     ("dde_dopri_batch_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _SZ]),
     ("dde_dopri_batch_set_times", C.c_int, [C.c_void_p, c_double_p, _SZ, c_double_p, _SZ]),
     ("dde_dopri_batch_set_events", C.c_int, [C.c_void_p, c_int32_p, _SZ]),
+    ("dde_dopri_batch_set_order", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("dde_dopri_batch_order_by_last_run", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_run", C.c_int, [C.c_void_p]),
     ("dde_dopri_batch_continue", C.c_int, [C.c_void_p, C.c_void_p, c_double_p, _SZ, c_double_p,
                                            _SZ]),
@@ -106,6 +108,7 @@ SYMBOLS = [
     ("dde_dopri_shards_upload", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _SZ]),
     ("dde_dopri_shards_set_times", C.c_int, [C.c_void_p, c_double_p, _SZ, c_double_p, _SZ]),
     ("dde_dopri_shards_set_events", C.c_int, [C.c_void_p, c_int32_p, _SZ]),
+    ("dde_dopri_shards_order_by_last_run", C.c_int, [C.c_void_p, C.c_int32]),
     ("dde_dopri_shards_run_download", C.c_int, [C.c_void_p] + [C.c_void_p] * 6),
     ("dde_dopri_shards_last_ms", C.c_double, [C.c_void_p]),
     ("dde_shard_range", None, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),

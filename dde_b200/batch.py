@@ -68,6 +68,19 @@ class DopriBatch:
         self._check(self._lib.dde_dopri_batch_set_events(
             self._h, ev.ctypes.data_as(_lib.c_int32_p), ev.shape[0]))
 
+    def set_order(self, order):
+        """The order in which trajectories are handed out to the device's threads (a
+        permutation of 0 .. n_traj - 1; None: index order).  Results do not depend on it."""
+        if order is None:
+            self._check(self._lib.dde_dopri_batch_set_order(self._h, None))
+            return
+        o = np.ascontiguousarray(order, dtype=np.uint32).ravel()
+        self._check(self._lib.dde_dopri_batch_set_order(self._h, o.ctypes.data_as(C.c_void_p)))
+
+    def order_by_last_run(self):
+        """Longest first, by the step attempts of this handle's last run."""
+        self._check(self._lib.dde_dopri_batch_order_by_last_run(self._h))
+
     def run(self):
         self._check(self._lib.dde_dopri_batch_run(self._h))
 
@@ -226,6 +239,10 @@ class DopriShards:
         ev = np.ascontiguousarray(events, dtype=np.int32).ravel()
         self._check(self._lib.dde_dopri_shards_set_events(
             self._h, ev.ctypes.data_as(_lib.c_int32_p), ev.shape[0]))
+
+    def order_by_last_run(self, enable=True):
+        """every shard's hand-out order from its own last run (False: back to index order)"""
+        self._check(self._lib.dde_dopri_shards_order_by_last_run(self._h, 1 if enable else 0))
 
     def run_download_into(self, y_out=None, out=None, stats=None, code=None, t_last=None,
                           step_size=None):

@@ -138,6 +138,49 @@ __global__ void ring_regrow_kernel(const double *old_ring, double *new_ring,
   }
 }
 
+/* hand-out order by the last run's step counts (dde_dopri_batch_order_by_last_run): a
+   counting sort, most attempts first.  Bin = min(attempts, DDE_ORDER_BINS - 1). */
+#define DDE_ORDER_BINS 4096
+__global__ void order_hist_kernel(const int *stats, long long n, unsigned *hist) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int k = stats[4 * i + 1];
+    k = k < 0 ? 0 : (k > DDE_ORDER_BINS - 1 ? DDE_ORDER_BINS - 1 : k);
+    atomicAdd(&hist[k], 1u);
+  }
+}
+/* one block: hist[k] becomes the number of trajectories in bins above k */
+__global__ void order_scan_kernel(unsigned *hist) {
+  __shared__ unsigned part[256];
+  constexpr int PER = DDE_ORDER_BINS / 256;
+  const int t = threadIdx.x; /* thread t owns bins [BINS - (t + 1) PER, BINS - t PER), top first */
+  unsigned sum = 0;
+  for (int j = 0; j < PER; ++j) {
+    sum += hist[DDE_ORDER_BINS - 1 - (t * PER + j)];
+  }
+  part[t] = sum;
+  __syncthreads();
+  unsigned before = 0;
+  for (int u = 0; u < t; ++u) {
+    before += part[u];
+  }
+  for (int j = 0; j < PER; ++j) {
+    const int k = DDE_ORDER_BINS - 1 - (t * PER + j);
+    const unsigned c = hist[k];
+    hist[k] = before;
+    before += c;
+  }
+}
+__global__ void order_scatter_kernel(const int *stats, long long n, unsigned *offset,
+                                     unsigned *order) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int k = stats[4 * i + 1];
+    k = k < 0 ? 0 : (k > DDE_ORDER_BINS - 1 ? DDE_ORDER_BINS - 1 : k);
+    order[atomicAdd(&offset[k], 1u)] = (unsigned) i;
+  }
+}
+
 __global__ void fill_int_kernel(int *x, long long n, int value) {
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if (i < n) {
@@ -211,6 +254,8 @@ struct dde_dopri_batch_s {
   int *d_stats = nullptr, *d_code = nullptr;
   double *d_ring = nullptr;
   double *d_init_k1 = nullptr, *d_init_h = nullptr, *d_y_final = nullptr;
+  unsigned *d_order = nullptr; /* [n_traj] the order trajectories are handed out in, when set */
+  bool have_order = false;
   int *d_event = nullptr; /* [cap_event] event index per critical time, or none set */
   size_t cap_event = 0;
   bool have_events = false;
@@ -442,6 +487,7 @@ void dde_dopri_batch_free(dde_dopri_batch_t *b) {
   free_dev(b->d_init_h);
   free_dev(b->d_y_final);
   free_dev(b->d_event);
+  free_dev(b->d_order);
   free_dev(b->d_ring_count);
   free_dev(b->d_next);
   free_dev(b->d_chunk_done);
@@ -748,6 +794,7 @@ int dopri_run_impl(dde_dopri_batch_t *b, int restart) {
     a.restart = restart;
     a.y_final = b->d_y_final;
     a.next_traj = b->d_next;
+    a.order = b->have_order ? b->d_order : nullptr;
     if (b->streaming) {
       DDE_CUDA(cudaMemsetAsync(b->d_chunk_done, 0, sizeof(unsigned) * b->n_chunks, b->stream));
       a.chunk_done = b->d_chunk_done;
@@ -953,6 +1000,71 @@ int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event, size_
     DDE_CUDA(cudaStreamSynchronize(b->stream));
   }
   b->have_events = any;
+  return 0;
+}
+
+/* The order in which the persistent threads take trajectories (default: index order).
+ * Results do not depend on it -- every trajectory is integrated exactly as before -- but
+ * the time of a batch does: it ends when its last trajectory does, so handing out the
+ * expensive ones first shortens the tail in which most lanes have run out of work. */
+int dde_dopri_batch_set_order(dde_dopri_batch_t *b, const uint32_t *order) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (order == nullptr) {
+    b->have_order = false;
+    return 0;
+  }
+  if (b->n_traj > 0xffffffffULL) {
+    return fail("a hand-out order holds 32-bit indices");
+  }
+  std::vector<bool> seen(b->n_traj, false);
+  for (size_t i = 0; i < b->n_traj; ++i) {
+    if (order[i] >= b->n_traj || seen[order[i]]) {
+      return fail("order must be a permutation of 0 .. n_traj - 1 (entry %zu)", i);
+    }
+    seen[order[i]] = true;
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (b->d_order == nullptr) {
+    DDE_CUDA(cudaMalloc(&b->d_order, sizeof(unsigned) * (b->n_traj + DDE_ORDER_BINS)));
+  }
+  DDE_CUDA(cudaMemcpyAsync(b->d_order, order, sizeof(unsigned) * b->n_traj, cudaMemcpyHostToDevice,
+                           b->stream));
+  DDE_CUDA(cudaStreamSynchronize(b->stream));
+  b->have_order = true;
+  return 0;
+}
+
+/* ... longest first, by the number of step attempts each trajectory made in the LAST run of
+ * this handle: for a handle that is run again on the same or on slowly changing inputs (a
+ * fitting loop, a scan refined around the last one), where the last run's costs predict the
+ * next run's.  Built on the device (a counting sort of the statistics), asynchronous on the
+ * handle's stream.  Stays in force until dde_dopri_batch_set_order(b, NULL). */
+int dde_dopri_batch_order_by_last_run(dde_dopri_batch_t *b) {
+  if (b == nullptr) {
+    return fail("NULL handle");
+  }
+  if (!b->ran) {
+    return fail("no run of this handle to take the order from");
+  }
+  if (b->n_traj > 0xffffffffULL) {
+    return fail("a hand-out order holds 32-bit indices");
+  }
+  DDE_CUDA(cudaSetDevice(b->device));
+  if (b->d_order == nullptr) {
+    DDE_CUDA(cudaMalloc(&b->d_order, sizeof(unsigned) * (b->n_traj + DDE_ORDER_BINS)));
+  }
+  unsigned *hist = b->d_order + b->n_traj;
+  DDE_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * DDE_ORDER_BINS, b->stream));
+  const int threads = 256;
+  const unsigned blocks = (unsigned) (((long long) b->n_traj + threads - 1) / threads);
+  order_hist_kernel<<<blocks, threads, 0, b->stream>>>(b->d_stats, (long long) b->n_traj, hist);
+  order_scan_kernel<<<1, 256, 0, b->stream>>>(hist);
+  order_scatter_kernel<<<blocks, threads, 0, b->stream>>>(b->d_stats, (long long) b->n_traj, hist,
+                                                         b->d_order);
+  DDE_CUDA(cudaGetLastError());
+  b->have_order = true;
   return 0;
 }
 
@@ -2398,6 +2510,15 @@ int dde_dopri_shards_set_times(dde_dopri_shards_t *h, const double *times, size_
 int dde_dopri_shards_set_events(dde_dopri_shards_t *h, const int32_t *event, size_t n_tcrit) {
   return for_each_shard(h, false, [&](size_t r) {
     return dde_dopri_batch_set_events(h->shard[r], event, n_tcrit);
+  });
+}
+
+/* every shard's own order, from its own last run (dde_dopri_batch_order_by_last_run);
+   enable == 0 returns to index order */
+int dde_dopri_shards_order_by_last_run(dde_dopri_shards_t *h, int32_t enable) {
+  return for_each_shard(h, false, [&](size_t r) {
+    return enable ? dde_dopri_batch_order_by_last_run(h->shard[r])
+                  : dde_dopri_batch_set_order(h->shard[r], nullptr);
   });
 }
 

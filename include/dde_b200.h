@@ -174,6 +174,16 @@ int dde_dopri_batch_set_times(dde_dopri_batch_t *b, const double *times,
  * change the trajectory's parameters; the change lasts for the run. */
 int dde_dopri_batch_set_events(dde_dopri_batch_t *b, const int32_t *event,
                                size_t n_tcrit);
+/* The order in which the device's persistent threads take trajectories (default: index
+ * order; no counterpart in the reference, whose loop over replicates is serial,
+ * src/r_difeq.c:94-103).  Results do not depend on it; the time of a batch does -- it ends
+ * when its last trajectory does.  order: a permutation of 0 .. n_traj - 1, or NULL for index
+ * order.  Thread-per-trajectory models. */
+int dde_dopri_batch_set_order(dde_dopri_batch_t *b, const uint32_t *order);
+/* ... longest first by the step attempts of this handle's LAST run: for a handle run again
+ * on the same or slowly changing inputs (a fitting loop).  Built on the device,
+ * asynchronous.  In force until dde_dopri_batch_set_order(b, NULL). */
+int dde_dopri_batch_order_by_last_run(dde_dopri_batch_t *b);
 /* dopri_integrate for every trajectory, from the resident y0/parms.
  * Asynchronous on the handle's stream (blocking with ctl.grow_history). */
 int dde_dopri_batch_run(dde_dopri_batch_t *b);
@@ -376,6 +386,8 @@ int dde_dopri_shards_set_times(dde_dopri_shards_t *h, const double *times,
                                size_t n_tcrit);
 int dde_dopri_shards_set_events(dde_dopri_shards_t *h, const int32_t *event,
                                 size_t n_tcrit);
+/* every shard's own order from its own last run; enable == 0: back to index order */
+int dde_dopri_shards_order_by_last_run(dde_dopri_shards_t *h, int32_t enable);
 int dde_dopri_shards_run_download(dde_dopri_shards_t *h, double *y_out,
                                   double *out, int32_t *stats, int32_t *code,
                                   double *t_last, double *step_size);

@@ -51,6 +51,8 @@ struct DopriArgs {
   double *y_final;       /* [n x n_traj] obj->y on return */
   /* work distribution: next trajectory index to hand out */
   unsigned long long *next_traj;
+  /* ... and which trajectory the k-th one handed out is (NULL: the k-th) */
+  const unsigned *order;
   /* streamed download (dde_dopri_batch_run_download): trajectories are handed
      out in index order, so the results of chunk c = [c << chunk_shift,
      (c + 1) << chunk_shift) are complete long before the kernel ends.  The

@@ -430,6 +430,9 @@ __global__ void __launch_bounds__(DDE_TPB, DDE1_MIN_BLOCKS) dopri_dde1_kernel(co
       if (traj >= a.n_traj) {
         break;
       }
+      if (a.order != nullptr) {
+        traj = (long long) a.order[traj];
+      }
       active = true;
       done = false;
 #pragma unroll

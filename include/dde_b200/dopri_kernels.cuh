@@ -346,6 +346,9 @@ dopri_tpt_kernel(const DopriArgs a) {
       if (traj >= a.n_traj) {
         break;
       }
+      if (a.order != nullptr) {
+        traj = (long long) a.order[traj];
+      }
       active = true;
       done = false;
 #pragma unroll

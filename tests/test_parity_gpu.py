@@ -847,6 +847,48 @@ def test_rows_by_sector_blocks_that_straddle_sectors(backend, n_times, return_in
     assert_bits_equal(got.y[1:], half.y, "the same trajectories at shifted offsets")
 
 
+@pytest.mark.parametrize("workload", ["mackey_glass", "lorenz_sweep"])
+def test_hand_out_order_does_not_change_results(backend, workload):
+    """dde_dopri_batch_set_order / _order_by_last_run: the order the device's threads take
+    trajectories in changes when a batch ends, never what it returns (both stepping kernels
+    of the thread-per-trajectory models; the streamed download under an arbitrary order)."""
+    n_traj = 40000
+    if workload == "mackey_glass":
+        model, y0, parms, times, kw = workloads.mackey_glass(n_traj, first=11)
+    else:
+        model, y0, parms, times, kw = workloads.lorenz_sweep(n_traj, first=11, n_times=23, t_end=3.0)
+    b = dde_b200.DopriBatch(model, y0.shape[1], n_traj, n_parms=parms.shape[1], **kw)
+    b.upload(y0, parms)
+    b.set_times(times)
+    b.run()
+    want = b.download()
+    rng = np.random.default_rng(5)
+
+    def check(tag):
+        b.run()
+        got = b.download()
+        np.testing.assert_array_equal(got.code, want.code)
+        np.testing.assert_array_equal(got.statistics, want.statistics)
+        assert_bits_equal(got.y, want.y, tag)
+        y = np.empty_like(want.y)
+        code = np.empty((n_traj,), dtype=np.int32)
+        b.run_download_into(y, None, None, code, None, None)  # completion flags, any order
+        np.testing.assert_array_equal(code, want.code)
+        assert_bits_equal(y, want.y, tag + " (streamed)")
+
+    b.set_order(rng.permutation(n_traj))
+    check("a random order")
+    b.order_by_last_run()
+    check("longest first")
+    b.set_order(None)
+    check("index order again")
+    with pytest.raises(dde_b200.DdeError, match="permutation"):
+        b.set_order(np.zeros(n_traj, dtype=np.uint32))
+    b.close()
+    ref = pyoracle.dopri_batch(backend, model, y0[:64], times, parms[:64], **kw)
+    assert_bits_equal(want.y[:64], ref.y, "y vs reference")
+
+
 def test_streamed_download_large_model(backend):
     """the block-per-trajectory kernel raises the same completion flags"""
     model, y0, parms, times, kw = workloads.seir_age(8)
