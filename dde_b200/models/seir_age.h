@@ -4,7 +4,7 @@
  * Rates scaled from the reference's SEIR example
  * (/root/reference/inst/examples/seir.c:8-10).
  *
- *   lambda_a(t) = beta sum_{|d| <= 4} w_|d| I_{a+d}(t) / (N_a sum w)   banded contacts,
+ *   lambda_a(t) = (beta / (N_a sum w)) sum_{|d| <= 4} w_|d| I_{a+d}(t)   banded contacts,
  *                                                       N_a = N / 128 per class
  *   new_inf_a   = S_a lambda_a
  *   lag_inf_a   = S_a(t - 14) lambda_a(t - 14) exp(-14 b)          latent period 14
@@ -51,6 +51,11 @@ DDE_MODEL_FN void seir_age(size_t n, double t, const double *y, double *dydt,
   const double *S14 = lag14, *I14 = lag14 + A;
   const double births = b * N / SEIR_AGE_CLASSES;
   const double scale = N / SEIR_AGE_CLASSES * 2.875; /* class size x sum of the weights */
+  /* transmission per unit of weighted infectives, once per evaluation -- not a division per
+     class and term: most classes' force of infection is exactly zero for most of the run
+     (the epidemic front moves four classes per latent period), and a GPU's IEEE division
+     leaves its fast path for a zero numerator */
+  const double bs = beta / scale;
   DDE_FOR(a, 0, A) {
     double force = 0.0, force14 = 0.0;
     for (int d = -SEIR_AGE_BAND; d <= SEIR_AGE_BAND; ++d) {
@@ -61,9 +66,9 @@ DDE_MODEL_FN void seir_age(size_t n, double t, const double *y, double *dydt,
         force14 += wd * I14[c];
       }
     }
-    const double new_inf = S[a] * (beta * force / scale);
-    const double lag_inf = S14[a] * (beta * force14 / scale) * surv14;
-    const double waning = delta * R[a] + sigma * lag21[a] * surv21 / 8.0;
+    const double new_inf = S[a] * (bs * force);
+    const double lag_inf = S14[a] * (bs * force14) * surv14;
+    const double waning = delta * R[a] + sigma * lag21[a] * surv21 * 0.125;
     dydt[a] = births - b * S[a] - new_inf + waning;
     dydt[A + a] = new_inf - lag_inf - b * E[a];
     dydt[2 * A + a] = lag_inf - (b + sigma) * I[a];

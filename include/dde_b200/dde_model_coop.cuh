@@ -32,7 +32,8 @@ namespace dde {
 
 template <class M, int METHOD, int TPT, int CMAX>
 cudaError_t launch_dopri_coop_method(const DopriArgs &args, int device_sms, cudaStream_t stream) {
-  auto kernel = dopri_coop_kernel<M, METHOD, TPT, CMAX>;
+  auto kernel = args.n == TPT * CMAX ? dopri_coop_kernel<M, METHOD, TPT, CMAX, TPT * CMAX>
+                                     : dopri_coop_kernel<M, METHOD, TPT, CMAX, 0>;
   const size_t table =
       args.n_history > 0 && args.n_history <= DDE_COOP_MAX_TABLE ? 2 * (size_t) args.n_history : 0;
   const size_t dyn = sizeof(double) * (DDE_COOP_NVEC * (size_t) args.n + table) + DDE_COOP_SCRATCH_BYTES;

@@ -391,6 +391,8 @@ static __constant__ CoopTerm c_dp8_d2[4][4] = {
     {{4, DP8_D713_LIT}, {10, DP8_D714_LIT}, {2, DP8_D715_LIT}, {3, DP8_D716_LIT}},
 };
 
+#include "coop_tableau_dp8.inc"
+
 /* shared-memory vectors of one trajectory, n doubles each */
 #define DDE_COOP_NVEC 16 /* y, k1..k10, stage input, 4 x scratch */
 
@@ -424,12 +426,15 @@ __device__ __forceinline__ void coop_seqsum(int n, const double *red, double *re
   __syncthreads(); /* b_val and red may be reused */
 }
 
-template <class M, int METHOD, int TPT, int CMAX>
+/* NFIX: n at compile time (the registered capacity TPT * CMAX, when the batch has exactly that
+   many equations: every vector of the solver object then sits at an immediate offset from
+   one base, and the per-component loops have a fixed trip count), or 0: n from the arguments */
+template <class M, int METHOD, int TPT, int CMAX, int NFIX>
 __global__ void
 __launch_bounds__(TPT, (TPT >= 256 ? DDE_COOP_MINB256 : (TPT >= 128 ? 4 : 8)))
 dopri_coop_kernel(const DopriArgs a) {
   constexpr int ORDER = METHOD == 0 ? 5 : 8;
-  const int n = a.n;
+  const int n = NFIX > 0 ? NFIX : a.n;
   const int hl = ORDER * n + 2;
   const int tid = threadIdx.x;
   /* the solver object of src/dopri.h:55-161 for one trajectory, in shared memory */
@@ -679,27 +684,28 @@ dopri_coop_kernel(const DopriArgs a) {
         err = sqrt(err / (double) n);
       } else {
         /* dopri853_step, src/dopri_853.c:159-247 */
+        /* the stage sums as straight-line code (coop_tableau_dp8.inc, generated from the
+           tables above): a term is an LDS off a loop-invariant base and two FP64
+           instructions, where walking the tables cost an LDC pair, a multiplication by n and
+           an address per term (27 % of the kernel's instructions in round 1) */
 #pragma unroll 1
         for (int j = 0; j < 11; ++j) {
-          DDE_COOP_STAGE(c_dp8_stages[j], j == 0, YIN);
+          if (j == 0) { /* written h * A21 * k1, i.e. (h A21) k1 */
+            DDE_EACH(i) { YIN[i] = Y[i] + h * DP8_A21 * KV(1)[i]; }
+          } else {
+            DDE_COOP_DP8_STAGE_INPUT(j)
+          }
+          DDE_COOP_EVAL(DDE_COOP_DP8_STAGE_TIME(j), YIN, KV(DDE_COOP_DP8_STAGE_DST(j)));
         }
         DDE_EACH(i) {
-          double b = c_dp8_b[0].a * KV(c_dp8_b[0].k)[i];
-#pragma unroll
-          for (int q = 1; q < 8; ++q) {
-            b = b + c_dp8_b[q].a * KV(c_dp8_b[q].k)[i];
-          }
+          const double b = DDE_COOP_DP8_B;
           KV(4)[i] = b;
           KV(5)[i] = Y[i] + h * b;
           /* dopri853_error, src/dopri_853.c:249-283 */
           const double sk = atol + rtol * fmax(fabs(Y[i]), fabs(KV(5)[i]));
           double erri = KV(4)[i] - DP8_BHH1 * KV(1)[i] - DP8_BHH2 * KV(9)[i] - DP8_BHH3 * KV(3)[i];
           RED[n + i] = csq(erri / sk);
-          erri = c_dp8_er[0].a * KV(c_dp8_er[0].k)[i];
-#pragma unroll
-          for (int q = 1; q < 8; ++q) {
-            erri = erri + c_dp8_er[q].a * KV(c_dp8_er[q].k)[i];
-          }
+          erri = DDE_COOP_DP8_ER;
           RED[i] = csq(erri / sk);
         }
         if (s_cc.error) {
@@ -778,19 +784,15 @@ dopri_coop_kernel(const DopriArgs a) {
            reused), three more stages */
         DDE_COOP_EVAL(t + h, KV(5), KV(4));
         DDE_EACH(i) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            double d = c_dp8_d1[r][0].a * KV(c_dp8_d1[r][0].k)[i];
-#pragma unroll
-            for (int q = 1; q < 8; ++q) {
-              d = d + c_dp8_d1[r][q].a * KV(c_dp8_d1[r][q].k)[i];
-            }
-            RED[(size_t) r * n + i] = d;
-          }
+          RED[i] = DDE_COOP_DP8_D1_0;
+          RED[(size_t) n + i] = DDE_COOP_DP8_D1_1;
+          RED[2 * (size_t) n + i] = DDE_COOP_DP8_D1_2;
+          RED[3 * (size_t) n + i] = DDE_COOP_DP8_D1_3;
         }
 #pragma unroll 1
         for (int j = 0; j < 3; ++j) {
-          DDE_COOP_STAGE(c_dp8_extra[j], false, YIN);
+          DDE_COOP_DP8_EXTRA_INPUT(j)
+          DDE_COOP_EVAL(DDE_COOP_DP8_EXTRA_TIME(j), YIN, KV(DDE_COOP_DP8_EXTRA_DST(j)));
         }
       }
 
@@ -823,15 +825,10 @@ dopri_coop_kernel(const DopriArgs a) {
           c[1] = ydiff;
           c[2] = bspl;
           c[3] = ydiff - h * KV(4)[i] - bspl;
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            double d = RED[(size_t) r * n + i];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              d = d + c_dp8_d2[r][q].a * KV(c_dp8_d2[r][q].k)[i];
-            }
-            c[4 + r] = h * d;
-          }
+          c[4] = h * DDE_COOP_DP8_D2_0(RED[i]);
+          c[5] = h * DDE_COOP_DP8_D2_1(RED[(size_t) n + i]);
+          c[6] = h * DDE_COOP_DP8_D2_2(RED[2 * (size_t) n + i]);
+          c[7] = h * DDE_COOP_DP8_D2_3(RED[3 * (size_t) n + i]);
         }
         if (dst != nullptr) {
 #pragma unroll
