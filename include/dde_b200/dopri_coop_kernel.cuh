@@ -70,6 +70,10 @@ struct CoopCtx {
   unsigned hint[4];
   int hint_slot[4]; /* their ring slots (no division on the fast path) */
   unsigned hint_next;
+  /* [hint_ts, hint_tn): the sign-adjusted times a hinted entry answers for (+inf, .): none.
+     Kept up to date where the ring changes (a commit gives the newest entry a successor
+     and may recycle the oldest), so that testing a hint is two loads and two comparisons */
+  double hint_ts[4], hint_tn[4];
   /* cached bracket: entry c_idx covers [c_ts, c_tn) in sign-adjusted time */
   unsigned c_idx;
   int c_valid;
@@ -111,25 +115,20 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
     /* every thread tests the entries it owns: the wanted one starts at or
        before t while its successor (if any) starts after t */
     const double st = s_cc.sign * t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double tj = s_cc.hint_ts[q];
+      if (tj <= st && st < s_cc.hint_tn[q]) {
+        *idx = s_cc.hint[q];
+        *t_old = s_cc.sign * tj;
+        *h = DDE_COOP_TAB_H[s_cc.hint_slot[q]];
+        return true; /* the same answer in every thread: no barrier needed */
+      }
+    }
     const unsigned count = s_cc.count;
     const unsigned cap = (unsigned) s_cc.cap;
     const unsigned used = count < cap ? count : cap;
     const unsigned tail = count - used;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const unsigned j = s_cc.hint[q];
-      if (j >= tail && j < count) {
-        const int slot = s_cc.hint_slot[q];
-        const int next = slot + 1 == (int) cap ? 0 : slot + 1;
-        const double tj = DDE_COOP_TAB_T[slot];
-        if (tj <= st && (j + 1 == count || !(DDE_COOP_TAB_T[next] <= st))) {
-          *idx = j;
-          *t_old = s_cc.sign * tj;
-          *h = DDE_COOP_TAB_H[slot];
-          return true; /* the same answer in every thread: no barrier needed */
-        }
-      }
-    }
     if (threadIdx.x == 0) {
       s_cc.b_ok = 0;
     }
@@ -151,8 +150,11 @@ __device__ __forceinline__ bool coop_locate(double t, unsigned *idx, double *t_o
     *h = s_cc.b_h;
     if (threadIdx.x == 0) { /* (everybody read the hints before the first barrier) */
       if (found) {
-        s_cc.hint[s_cc.hint_next & 3u] = s_cc.b_idx;
-        s_cc.hint_slot[s_cc.hint_next & 3u] = (int) (s_cc.b_idx % cap);
+        const unsigned q = s_cc.hint_next & 3u, j = s_cc.b_idx;
+        s_cc.hint[q] = j;
+        s_cc.hint_slot[q] = (int) (j % cap);
+        s_cc.hint_ts[q] = DDE_COOP_TAB_T[j % cap];
+        s_cc.hint_tn[q] = j + 1 < count ? DDE_COOP_TAB_T[(j + 1) % cap] : coop_inf();
         s_cc.hint_next++;
       } else {
         s_cc.error = 1;
@@ -507,6 +509,8 @@ dopri_coop_kernel(const DopriArgs a) {
       s_cc.c_valid = 0;
       for (int q = 0; q < 4; ++q) {
         s_cc.hint[q] = 0xffffffffu;
+        s_cc.hint_ts[q] = coop_inf();
+        s_cc.hint_tn[q] = coop_inf();
       }
       s_cc.hint_next = 0;
       /* the table of step times follows the model's scratch area */
@@ -860,6 +864,23 @@ dopri_coop_kernel(const DopriArgs a) {
         const unsigned newest = s_cc.count;
         s_cc.head = s_cc.head + 1 == a.n_history ? 0 : s_cc.head + 1;
         s_cc.count = newest + 1;
+        if (s_cc.tab_off >= 0) {
+          /* the hinted entries: the newest one has a successor now, the oldest may be gone */
+          const unsigned gone = newest + 1 > (unsigned) a.n_history
+                                    ? newest + 1 - (unsigned) a.n_history : 0u;
+          for (int q = 0; q < 4; ++q) {
+            const unsigned j = s_cc.hint[q];
+            if (j != 0xffffffffu) {
+              if (j + 1 == newest) {
+                s_cc.hint_tn[q] = sign * t_old;
+              }
+              if (j < gone) {
+                s_cc.hint[q] = 0xffffffffu;
+                s_cc.hint_ts[q] = coop_inf();
+              }
+            }
+          }
+        }
         if (s_cc.c_valid) {
           const unsigned tail = s_cc.count > (unsigned) a.n_history
                                     ? s_cc.count - (unsigned) a.n_history : 0u;
