@@ -187,7 +187,8 @@ def c5(n_traj):
     line = {"workload": "C5 seir_age dop853 n=512 block-per-trajectory", "n_traj": n_traj,
             "ms": ms, "e2e_ms": e2e_ms, "trajectories_per_s": n_traj / (ms * 1e-3),
             "accepted_steps_per_s": A / (ms * 1e-3), "failed": int((code != 1).sum())}
-    line["bound"] = "block barriers around the ordered norms, then FP64 issue"
+    line["bound"] = ("latency: the look-ups read their coefficients from L2 at every evaluation, "
+                     "block barriers, one thread sums the ordered norms")
     line.update(rates(flops, ring_bytes, ms))
     return line
 
