@@ -889,6 +889,33 @@ def test_hand_out_order_does_not_change_results(backend, workload):
     assert_bits_equal(want.y[:64], ref.y, "y vs reference")
 
 
+def test_shards_hand_out_order(backend):
+    """dde_dopri_shards_order_by_last_run: every shard takes its order from its own last
+    run; the results do not change"""
+    n_traj = 30000
+    model, y0, parms, times, kw = workloads.mackey_glass(n_traj, first=5)
+    sh = dde_b200.DopriShards(model, 1, n_traj, devices=None, n_parms=3, **kw)
+    sh.set_times(times)
+    nt = times.shape[0]
+    outs = []
+    for mode in (None, True, False):
+        if mode is not None:
+            sh.order_by_last_run(mode)
+        y = np.empty((n_traj, nt, 1))
+        stats = np.empty((n_traj, 4), dtype=np.int32)
+        code = np.empty((n_traj,), dtype=np.int32)
+        sh.upload(y0, parms)
+        sh.run_download_into(y, None, stats, code, None, None)
+        outs.append((y, stats, code))
+    sh.close()
+    for y, stats, code in outs[1:]:
+        np.testing.assert_array_equal(code, outs[0][2])
+        np.testing.assert_array_equal(stats, outs[0][1])
+        assert_bits_equal(y, outs[0][0], "y")
+    want = pyoracle.dopri_batch(backend, model, y0[:64], times, parms[:64], **kw)
+    assert_bits_equal(outs[0][0][:64], want.y, "y vs reference")
+
+
 def test_streamed_download_large_model(backend):
     """the block-per-trajectory kernel raises the same completion flags"""
     model, y0, parms, times, kw = workloads.seir_age(8)
