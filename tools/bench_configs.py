@@ -153,14 +153,23 @@ def c4(n_rep, n_steps):
         ms.append(b.last_ms())
     ms = float(np.median(ms))
     y, _, code, _ = b.download()
+    # end to end: pinned host buffers in, pinned host buffers out (what a caller of the C-ABI
+    # hands over, as in the headline's leg)
+    import torch
+    h_y0 = torch.from_numpy(np.ascontiguousarray(y0)).pin_memory()
+    h_p = torch.from_numpy(np.ascontiguousarray(parms)).pin_memory()
+    h_y = torch.empty(y.shape, dtype=torch.float64).pin_memory()
+    h_c = torch.empty((n_rep,), dtype=torch.int32).pin_memory()
+    h_f = torch.empty((n_rep, 3), dtype=torch.float64).pin_memory()
     t = []
-    for _ in range(3):  # end to end: host arrays in, host arrays out
+    for _ in range(4):
         b.sync()
         t0 = time.perf_counter()
-        b.upload(y0, parms)
+        b.upload(h_y0, h_p)
         b.run()
-        b.download()
+        b.download_into(h_y, None, h_c, h_f)
         t.append(1e3 * (time.perf_counter() - t0))
+    assert np.array_equal(h_y.numpy().view(np.uint64), y.view(np.uint64))
     b.close()
     n_steps_total = float(n_rep) * n_steps
     line = {"workload": "C4 delayed SIR difeq_replicate", "n_rep": n_rep,
