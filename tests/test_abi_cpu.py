@@ -170,3 +170,14 @@ def test_argument_validation_matches_the_reference():
     if not torch.cuda.is_available():
         with pytest.raises(dde_b200.DdeError, match="no CUDA device"):
             dde_b200.dopri_batch([[1.0]], [0.0, 1.0], "exponential", [[1.0]], grow_history=True)
+
+
+def test_generated_tableau_is_in_sync():
+    """include/dde_b200/coop_tableau_dp8.inc (the block-per-trajectory kernel's dop853 stage
+    sums as straight-line code) is what tools/gen_coop_tableau.py makes of the tables in
+    dopri_coop_kernel.cuh"""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run([sys.executable, str(root / "tools" / "gen_coop_tableau.py"), "--check"],
+                   check=True)

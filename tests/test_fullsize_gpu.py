@@ -134,9 +134,11 @@ def test_c4_delayed_sir_full_batch(backend):
 
 
 def test_c5_seir_age_batch(backend):
-    """n = 512 with two lags, block per trajectory: more trajectories than one wave of
-    resident blocks (444), slice invariance and the reference on a few of them."""
-    n_traj = 1024
+    """n = 512 with two lags, block per trajectory, at the size one GPU of eight integrates of
+    the configuration's 65 536 (8192 trajectories, 34 GB of history rings; the sharded whole:
+    tools/run_c5_sharded.py): many waves of resident blocks (444), slice invariance and the
+    reference on a few of them."""
+    n_traj = 8192
     model, y0, parms, times, kw = workloads.seir_age(n_traj)
     full = dde_b200.dopri_batch(y0, times, model, parms, **kw)
     assert (full.code == 1).all()
