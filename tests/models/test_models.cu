@@ -27,6 +27,11 @@ DDE_EVENT_TABLE(growth_events, identity, double_variables, halve_variables, doub
                 halve_parameters)
 DDE_REGISTER_DOPRI_EVENTS(exponential,    exponential,    0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
 DDE_REGISTER_DOPRI_EVENTS(linear,         linear,         0, -1,      DDE_NO_OUTPUT, 0, growth_events, 5)
+/* the same right-hand side with n fixed at compile time: small models without history run
+   the unrolled kernel, whose rows leave by sector (1, 2 and 4 doubles per row) */
+DDE_REGISTER_DOPRI(       exponential1,   exponential,    1, 1)
+DDE_REGISTER_DOPRI(       exponential2,   exponential,    2, 2)
+DDE_REGISTER_DOPRI(       exponential4,   exponential,    4, 4)
 DDE_REGISTER_DOPRI(       delayed_growth, delayed_growth, 0, -1)
 DDE_REGISTER_DOPRI(       delayed_growth_vec, delayed_growth_vec, 0, -1)
 DDE_REGISTER_DOPRI(       delayed_growth_all, delayed_growth_all, 0, -1)

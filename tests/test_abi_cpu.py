@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 PRODUCT_MODELS = {"lorenz", "rossler", "mackey_glass", "sir_delay", "seir_age"}
-FIXTURE_MODELS = {"seir", "seir_int", "exponential", "linear", "delayed_growth", "delayed_growth_vec",
+FIXTURE_MODELS = {"seir", "seir_int", "exponential", "exponential1", "exponential2", "exponential4", "linear", "delayed_growth", "delayed_growth_vec",
                   "delayed_growth_all", "mg_wrong_lag", "logistic", "additive", "fibonacci", "fib_out", "fib_all",
                   "fib_vec", "exponential_wide", "delayed_growth_wide"}
 

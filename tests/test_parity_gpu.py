@@ -916,6 +916,29 @@ def test_shards_hand_out_order(backend):
     assert_bits_equal(outs[0][0][:64], want.y, "y vs reference")
 
 
+@pytest.mark.parametrize("n", [1, 2, 4])
+@pytest.mark.parametrize("n_times,return_initial", [(8, False), (8, True), (11, True), (402, False)])
+def test_rows_by_sector_other_widths(backend, n, n_times, return_initial):
+    """rows of one, two and four doubles through the unrolled kernel's sector buffer (four
+    rows, two rows, one row per 32-byte sector), blocks that straddle sectors included: the
+    exponential fixture registered with n fixed at compile time, against the reference's
+    run of the same right-hand side"""
+    n_traj = 3001
+    rng = np.random.default_rng(10 * n + n_times)
+    y0 = rng.uniform(0.5, 2.0, size=(n_traj, n))
+    r = rng.uniform(0.1, 3.0, size=(n_traj, n))
+    times = np.linspace(0.0, 4.0, n_times)
+    kw = dict(method="dopri5", rtol=1e-7, atol=1e-7, return_initial=return_initial)
+    got = dde_b200.dopri_batch(y0, times, "exponential%d" % n, r, **kw)
+    assert (got.code == 1).all()
+    for sl in (slice(0, 80), slice(n_traj - 80, n_traj)):
+        want = pyoracle.dopri_batch(backend, "exponential", y0[sl], times, r[sl], **kw)
+        np.testing.assert_array_equal(got.statistics[sl], want.statistics)
+        assert_bits_equal(got.y[sl], want.y, "y vs reference")
+    again = dde_b200.dopri_batch(y0[1:], times, "exponential%d" % n, r[1:], **kw)
+    assert_bits_equal(got.y[1:], again.y, "the same trajectories at shifted offsets")
+
+
 def test_streamed_download_large_model(backend):
     """the block-per-trajectory kernel raises the same completion flags"""
     model, y0, parms, times, kw = workloads.seir_age(8)
