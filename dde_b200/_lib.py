@@ -115,6 +115,7 @@ SYMBOLS = [
     ("dde_host_alloc", C.c_void_p, [_SZ]),
     ("dde_host_free", None, [C.c_void_p]),
     ("dde_pow_host", C.c_double, [C.c_double, C.c_double]),
+    ("dde_pow2_host", None, [C.c_double, C.c_double, C.c_double, c_double_p]),
     ("dde_exp_host", C.c_double, [C.c_double]),
     ("dde_fp64_peak", C.c_double, [C.c_int]),
 ]

@@ -405,6 +405,11 @@ int dde_dopri_strerror(int32_t code, double t, uint64_t n_history, char *buf, si
 
 double dde_pow_host(double x, double y) { return dde_pow(x, y); }
 double dde_exp_host(double x) { return dde_exp(x); }
+void dde_pow2_host(double x, double y1, double y2, double *out) {
+  const DdePow2 r = dde_pow2(x, y1, y2);
+  out[0] = r.a;
+  out[1] = r.b;
+}
 
 /* TFLOP/s of the FP64 pipe on the current device (see fp64_peak_kernel). */
 double dde_fp64_peak(int fma) {

@@ -414,6 +414,9 @@ void dde_host_free(void *p);
  * that runs on the device; exported so tests can pin it against libm. */
 double dde_pow_host(double x, double y);
 double dde_exp_host(double x);
+/* out[0] = x^y1, out[1] = x^y2 with the logarithm of x computed once (the dopri5 step-size
+ * controller's two powers): each the bits dde_pow_host gives alone */
+void dde_pow2_host(double x, double y1, double y2, double *out);
 
 /* Measured FP64 issue ceiling of the current device in TFLOP/s: fma != 0 a
  * chain of DFMA (2 flop/instr), fma == 0 alternating DMUL/DADD (1 flop/instr,

@@ -440,6 +440,41 @@ DDE_HD double dde_pow(double x, double y) {
 }
 
 
+/* x^y1 and x^y2 at once.  pow(x, y) is exp(y log x) with log x a double-double that does
+ * not depend on y, so two powers of one base share it -- the table read, the polynomial,
+ * half of the work -- and each is, bit for bit, what dde_pow(x, y) returns alone.  The
+ * dopri5 step-size controller wants err^0.17 now and max(err, 1e-4)^0.04 at the next step
+ * (/root/reference/src/dopri.c:517,521: fac_old is the accepted step's error). */
+struct DdePow2 {
+  double a, b;
+};
+
+DDE_HD struct DdePow2 dde_pow2(double x, double y1, double y2) {
+  const uint32_t topx = dde_top12(x);
+  const int rare_x = topx - 0x001u >= 0x7ffu - 0x001u;
+  const int rare1 = rare_x | ((dde_top12(y1) & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  const int rare2 = rare_x | ((dde_top12(y2) & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  double lo;
+  const double hi = dde_pow_log_inline(dde_asuint64(x), &lo);
+  int er1, er2;
+  const struct DdeExpReduced red1 = dde_pow_exp_reduce(y1, hi, lo, &er1);
+  const struct DdeExpReduced red2 = dde_pow_exp_reduce(y2, hi, lo, &er2);
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 e1 = __ldg(&dde_exp_tab_d[red1.ki % 128]);
+  const ulonglong2 e2 = __ldg(&dde_exp_tab_d[red2.ki % 128]);
+  const double c1 = dde_pow_exp_finish(red1, dde_asdouble((uint64_t) e1.x), (uint64_t) e1.y);
+  const double c2 = dde_pow_exp_finish(red2, dde_asdouble((uint64_t) e2.x), (uint64_t) e2.y);
+#else
+  const uint64_t i1 = 2 * (red1.ki % 128), i2 = 2 * (red2.ki % 128);
+  const double c1 = dde_pow_exp_finish(red1, dde_asdouble(DDE_EXP_TAB(i1)), DDE_EXP_TAB(i1 + 1));
+  const double c2 = dde_pow_exp_finish(red2, dde_asdouble(DDE_EXP_TAB(i2)), DDE_EXP_TAB(i2 + 1));
+#endif
+  struct DdePow2 out;
+  out.a = (rare1 | er1) ? dde_pow_rare(x, y1, c1) : c1;
+  out.b = (rare2 | er2) ? dde_pow_rare(x, y2, c2) : c2;
+  return out;
+}
+
 #if defined(__CUDACC__) || defined(DDE_HOST_EMU)
 /* ---- the same pow with the two tables in a kernel's shared memory --------------------
  * at shared-window address `base`: {invc, logc} x 128, then logctail x 128, then
@@ -486,6 +521,48 @@ __device__ __forceinline__ double dde_pow_shared(unsigned base, double x, double
     return dde_pow_rare(x, y, common);
   }
   return common;
+}
+
+/* dde_pow2 from the kernel's copy of the tables */
+__device__ __forceinline__ struct DdePow2 dde_pow2_shared(unsigned base, double x, double y1,
+                                                          double y2) {
+  const uint32_t topx = dde_top12(x);
+  const int rare_x = topx - 0x001u >= 0x7ffu - 0x001u;
+  const int rare1 = rare_x | ((dde_top12(y1) & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  const int rare2 = rare_x | ((dde_top12(y2) & 0x7ff) - 0x3beu >= 0x43eu - 0x3beu);
+  const uint64_t ix = dde_asuint64(x);
+  const unsigned i = (unsigned) dde_pow_log_index(ix);
+  double invc, logc, logctail;
+#if defined(DDE_HOST_EMU)
+  invc = ((const double *) dde_emu_shared(base + 16u * i))[0];
+  logc = ((const double *) dde_emu_shared(base + 16u * i))[1];
+  logctail = *(const double *) dde_emu_shared(base + 2048u + 8u * i);
+#else
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(base + 16u * i));
+  asm("ld.shared.f64 %0, [%1];" : "=d"(logctail) : "r"(base + 2048u + 8u * i));
+#endif
+  double lo;
+  const double hi = dde_pow_log_finish(ix, invc, logc, logctail, &lo);
+  int er1, er2;
+  const struct DdeExpReduced red1 = dde_pow_exp_reduce(y1, hi, lo, &er1);
+  const struct DdeExpReduced red2 = dde_pow_exp_reduce(y2, hi, lo, &er2);
+  const unsigned k1 = (unsigned) red1.ki % 128u, k2 = (unsigned) red2.ki % 128u;
+  double t1, s1, t2, s2;
+#if defined(DDE_HOST_EMU)
+  t1 = ((const double *) dde_emu_shared(base + 3072u + 16u * k1))[0];
+  s1 = ((const double *) dde_emu_shared(base + 3072u + 16u * k1))[1];
+  t2 = ((const double *) dde_emu_shared(base + 3072u + 16u * k2))[0];
+  s2 = ((const double *) dde_emu_shared(base + 3072u + 16u * k2))[1];
+#else
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t1), "=d"(s1) : "r"(base + 3072u + 16u * k1));
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t2), "=d"(s2) : "r"(base + 3072u + 16u * k2));
+#endif
+  const double c1 = dde_pow_exp_finish(red1, t1, dde_asuint64(s1));
+  const double c2 = dde_pow_exp_finish(red2, t2, dde_asuint64(s2));
+  struct DdePow2 out;
+  out.a = (rare1 | er1) ? dde_pow_rare(x, y1, c1) : c1;
+  out.b = (rare2 | er2) ? dde_pow_rare(x, y2, c2) : c2;
+  return out;
 }
 #endif
 

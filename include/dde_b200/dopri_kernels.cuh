@@ -109,8 +109,12 @@ __device__ __forceinline__ void stg_sector(double *dst, double a, double b, doub
    loop holds one copy of pow, the model's (measured: +1.2 %) */
 #ifndef DDE_CTRL_POW_INLINE
 static __device__ __noinline__ double dde_pow_ctrl(double x, double y) { return dde_pow(x, y); }
+static __device__ __noinline__ DdePow2 dde_pow2_ctrl(double x, double y1, double y2) {
+  return dde_pow2(x, y1, y2);
+}
 #else
 #define dde_pow_ctrl dde_pow
+#define dde_pow2_ctrl dde_pow2
 #endif
 
 /* shared memory by shared-window address: 64- and 128-bit accesses.  volatile, so the
@@ -152,6 +156,9 @@ __device__ __forceinline__ void dde1_sts2(unsigned addr, double a, double b) {
    block's copy of the tables */
 static __device__ __noinline__ double dde1_pow_ctrl(unsigned tab, double x, double y) {
   return dde_pow_shared(tab, x, y);
+}
+static __device__ __noinline__ DdePow2 dde1_pow2_ctrl(unsigned tab, double x, double y1, double y2) {
+  return dde_pow2_shared(tab, x, y1, y2);
 }
 
 /* the block's copy of the tables (dde_math.h: dde_pow_shared); a barrier follows */
@@ -303,7 +310,11 @@ dopri_tpt_kernel(const DopriArgs a) {
      note in dopri_init_kernel below) */
   double loc[4][NMAX];
   double *const y = loc[0], *const k1 = loc[1], *const yin = loc[2], *const kt = loc[3];
-  double t = 0.0, h = 0.0, fac_old = 1e-4, h_save = 0.0;
+  double t = 0.0, h = 0.0, h_save = 0.0;
+  /* pow(fac_old, step_beta) of the controller (src/dopri.c:521), and its value for the
+     fac_old = 1e-4 every integration starts from and never goes below */
+  const double facb_floor = METHOD == 0 ? dde_pow(1e-4, step_beta) : 1.0;
+  double facb = facb_floor;
   bool stop = false, last = false, reject = false;
   int times_idx = 1, tcrit_idx = 0;
   /* times[times_idx]: read once per output row, not once per step, and requested
@@ -395,7 +406,7 @@ dopri_tpt_kernel(const DopriArgs a) {
       s_error[s] = 0;
 
       /* dopri_integrate prologue, src/dopri.c:300-339 */
-      fac_old = 1e-4;
+      facb = facb_floor; /* fac_old = 1e-4 */
       stop = last = reject = false;
       h_save = 0.0;
       /* k1 = f(t0, y0) and the first step size come from dopri_init_kernel */
@@ -825,13 +836,21 @@ dopri_tpt_kernel(const DopriArgs a) {
           err = sign * err * sqrt(1.0 / ((double) n * deno));
         }
         /* dopri_h_new, src/dopri.c:516-525 */
-        const double fac11 =
-            TAB_SHARED ? dde1_pow_ctrl(tab, err, step_constant) : dde_pow_ctrl(err, step_constant);
-        /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x */
-        const double facb =
-            METHOD != 0 ? 1.0
-                        : (TAB_SHARED ? dde1_pow_ctrl(tab, fac_old, step_beta)
-                                      : dde_pow_ctrl(fac_old, step_beta));
+        /* dop853 has step_beta = 0 and pow(x, 0) == 1 for every x.  dopri5 wants
+           pow(err, 0.17) now and, if this step is accepted, pow(fac_old = max(err, 1e-4),
+           0.04) at the attempts that follow it: two powers of one base, whose logarithm
+           (half of a pow) is computed once (dde_pow2); facb is the value kept from the step
+           that set fac_old */
+        double fac11, facb_next = 1.0;
+        if (METHOD == 0) {
+          const DdePow2 pw = TAB_SHARED ? dde1_pow2_ctrl(tab, err, step_constant, step_beta)
+                                        : dde_pow2_ctrl(err, step_constant, step_beta);
+          fac11 = pw.a;
+          facb_next = pw.b;
+        } else {
+          fac11 = TAB_SHARED ? dde1_pow_ctrl(tab, err, step_constant)
+                             : dde_pow_ctrl(err, step_constant);
+        }
         double fac = fac11 / facb;
         fac = fmax(1.0 / step_factor_max, fmin(1.0 / step_factor_min, fac / step_factor_safe));
         accepted = (err <= 1) || force_this_step;
@@ -842,7 +861,8 @@ dopri_tpt_kernel(const DopriArgs a) {
         h_new = h / (accepted ? fac : fac_rej);
         if (accepted) {
           my_stages = NST;
-          fac_old = fmax(err, 1e-4); /* src/dopri.c:398-399 */
+          /* fac_old = fmax(err, 1e-4), src/dopri.c:398-399: kept as pow(fac_old, step_beta) */
+          facb = err >= 1e-4 ? facb_next : facb_floor;
           ++n_accept;
           if (METHOD == 0) {
             step_done = true;

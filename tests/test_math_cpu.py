@@ -46,6 +46,23 @@ def test_pow_controller_domain():
         check_pow(err.tolist(), [e] * n)
 
 
+def test_pow2_shares_the_logarithm_and_nothing_else():
+    """dde_pow2(x, y1, y2): the dopri5 controller's err^0.17 and err^0.04 from one log(err);
+    each result the bits of libm's pow, special bases included"""
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    xs = np.concatenate([np.exp(rng.uniform(-60, 20, 40000)), rng.uniform(0.9, 1.1, 5000),
+                         [0.0, -0.0, 1.0, 1e-4, np.inf, np.nan, 5e-324, 2.2e-308, -1.0, 1e308]])
+    out = (C.c_double * 2)()
+    for y1, y2 in ((0.2 - 0.04 * 0.75, 0.04), (0.125, 0.0), (3.0, -2.5)):
+        bad = []
+        for x in xs.tolist():
+            lib.dde_pow2_host(x, y1, y2, out)
+            if not (same(out[0], libm.pow(x, y1)) and same(out[1], libm.pow(x, y2))):
+                bad.append((x, out[0], out[1]))
+        assert not bad, "%d mismatches, first %r" % (len(bad), bad[0])
+
+
 def test_pow_model_domain():
     # Mackey-Glass: y^n with y in (0, 2.5), n in [8, 12]
     rng = np.random.default_rng(8)
